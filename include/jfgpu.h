@@ -1,0 +1,178 @@
+/* jfgpu.h -- C ABI of the B200 k-mer counting engine (libjfgpu.so).
+ *
+ * This is the drop-in boundary for the `jellyfish count` hot path.  The reference
+ * (gmarcais/Jellyfish) has no FFI: its seam is the C++ template trio
+ *   mer_overlap_sequence_parser  (include/jellyfish/mer_overlap_sequence_parser.hpp:61-114)
+ *   hash_counter                 (include/jellyfish/hash_counter.hpp:50-172)
+ *   dumper_t / sorted_dumper     (include/jellyfish/dumper.hpp:68-78, sorted_dumper.hpp:57-101)
+ * driven by mer_counter_base::start (sub_commands/count_main.cc:152-184).  Each entry
+ * point below names the reference interface it replaces.  Plain pointers and sizes
+ * only; no C++ or torch types; no exception crosses the boundary: every call returns a
+ * status (0 = OK) and jfgpu_last_error() gives the message.
+ *
+ * There is NO CPU fallback: every call that computes runs hand-written sm_100a CUDA.
+ */
+#ifndef JFGPU_H
+#define JFGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jfgpu_engine* jfgpu_handle;
+
+/* status codes */
+enum {
+  JFGPU_OK          = 0,
+  JFGPU_ERR_ARG     = 1,  /* invalid argument / unsupported configuration           */
+  JFGPU_ERR_CUDA    = 2,  /* CUDA runtime error (no device, launch failure, ...)    */
+  JFGPU_ERR_FULL    = 3,  /* "Hash full": reference hash_counter.hpp:194-195         */
+  JFGPU_ERR_FORMAT  = 4,  /* "Unsupported format": mer_overlap_sequence_parser.hpp:146 */
+  JFGPU_ERR_STATE   = 5,  /* call sequence error                                    */
+  JFGPU_ERR_NOMEM   = 6,  /* allocation failure (reference array::ErrorAllocation)   */
+  JFGPU_ERR_SINK    = 7   /* the dump sink callback reported an error               */
+};
+
+/* feed flags */
+enum {
+  JFGPU_FILE_BEGIN = 1u,  /* first bytes of an input file: format is sniffed here    */
+  JFGPU_FILE_END   = 2u   /* last bytes of an input file: no k-mer spans the file end
+                             (mer_overlap_sequence_parser.hpp:111)                  */
+};
+
+/* operations of mer_counter_base (sub_commands/count_main.cc:133,152-184) */
+enum { JFGPU_OP_COUNT = 0, JFGPU_OP_PRIME = 1, JFGPU_OP_UPDATE = 2 };
+
+/* Constructor arguments: the union of hash_counter's constructor
+ * (hash_counter.hpp:50-64: size, key_len, val_len, nb_threads, reprobe_limit) and the
+ * switches of `jellyfish count` that act on the hot path
+ * (sub_commands/count_main_cmdline.yaggo:4-112). */
+typedef struct {
+  uint32_t struct_size;    /* sizeof(jfgpu_params), for ABI evolution                */
+  uint32_t k;              /* -m : mer length, 1..64                                  */
+  uint64_t size;           /* -s : requested number of table slots (GLOBAL table);
+                              rounded up to 2^l and clipped to 4^k exactly like
+                              large_hash::array (large_hash_array.hpp:992-1002)      */
+  uint32_t counter_len;    /* -c : "val_len" recorded in the header (default 7)       */
+  uint32_t max_reprobe;    /* -p : reprobe limit before clipping (default 126)        */
+  uint32_t canonical;      /* -C                                                      */
+  uint32_t allow_regrow;   /* 1: double the table when full (hash_counter.hpp:200-238);
+                              0: --disk behaviour is not implemented -> JFGPU_ERR_FULL */
+  int32_t  device;         /* CUDA device ordinal                                     */
+  uint32_t shard_index;    /* this engine owns the slots whose top log2(n_shards)     */
+  uint32_t n_shards;       /*   position bits equal shard_index (1 = whole table)     */
+  uint32_t matrix_skip;    /* number of hash matrices to draw and discard first (so a
+                              caller can reproduce a later point of the reference's
+                              unseeded random() stream); normally 0                   */
+  uint64_t bf_size;        /* --bf-size : expected number of k-mers, 0 = no filter     */
+  double   bf_fp;          /* --bf-fp                                                 */
+  uint64_t max_batch_bytes;/* device staging buffer size for jfgpu_feed (0 = default) */
+  uint64_t reserved[6];
+} jfgpu_params;
+
+/* What file_header::update_from_ary records (file_header.hpp:26-33). */
+typedef struct {
+  uint64_t size;           /* global number of slots, power of two                    */
+  uint32_t lsize;          /* log2(size)                                              */
+  uint32_t key_len;        /* 2k                                                      */
+  uint32_t val_len;        /* -c                                                      */
+  uint32_t max_reprobe;    /* clipped limit (large_hash_array.hpp:29-39,160)           */
+  uint32_t matrix_r, matrix_c;
+  uint32_t matrix_identity;/* 1 when the table is as large as the key space            */
+  uint32_t slot_bits;      /* device slot width (32/64/128); informational            */
+  uint64_t local_slots;    /* slots resident on this device (incl. overflow margin)   */
+  uint64_t table_bytes;
+  const uint64_t* matrix_columns; /* matrix_c columns (NULL when identity); owned by
+                                     the engine, valid until the next regrow/destroy  */
+  const uint64_t* reprobes;       /* max_reprobe+1 offsets (lib/storage.cc:13-41)      */
+} jfgpu_table_info;
+
+typedef struct {
+  uint64_t kmers;          /* k-mer windows emitted by the extractor                  */
+  uint64_t inserted;       /* k-mers that reached the table (after filters)           */
+  uint64_t distinct;       /* slots claimed                                           */
+  uint64_t reprobes;       /* extra probes beyond the first, summed                   */
+  uint64_t overflowed;     /* counter-field wrap events (exact: carried to side table)*/
+  uint64_t regrows;        /* table doublings                                         */
+  uint64_t bytes;          /* input bytes consumed                                    */
+  double   seconds_count;  /* device time spent in counting kernels (CUDA events)     */
+} jfgpu_stats;
+
+/* -- life cycle: hash_counter ctor / dtor (hash_counter.hpp:50-68) ------------------ */
+int  jfgpu_create(const jfgpu_params* params, jfgpu_handle* out);
+void jfgpu_destroy(jfgpu_handle h);
+const char* jfgpu_last_error(jfgpu_handle h);   /* h may be NULL: error of a failed create */
+
+/* -- input: replaces mer_overlap_sequence_parser::produce + mer_iterator::operator++ +
+ *    hash_counter::add for a whole buffer of FASTA text
+ *    (mer_overlap_sequence_parser.hpp:88-114,161-185; mer_iterator.hpp:51-81;
+ *     hash_counter.hpp:91-115).  Bytes of one file may be fed in any number of
+ *    consecutive calls; state (header/sequence line, the k-1 base seam) is carried on
+ *    the device.  `bytes` is HOST memory (pinned memory gives asynchronous copies). */
+int  jfgpu_feed(jfgpu_handle h, const char* bytes, size_t n, uint32_t flags);
+/* Same with the text already resident in device memory (16-byte aligned pointer).
+ * `stream` is a cudaStream_t (NULL = the engine's own stream). */
+int  jfgpu_feed_device(jfgpu_handle h, const void* dev_bytes, size_t n, uint32_t flags, void* stream);
+
+/* -- multi-GPU stages (no reference analogue) ------------------
+ * Extract canonical k-mers from device-resident text and bucket them by owning shard
+ * (top bits of the hash position).  dev_keys: n_shards * capacity packed keys
+ * (8 bytes each for k<=32, 16 for k<=64), bucket d at offset d*capacity;
+ * dev_counts: n_shards uint64 counters (accumulated; caller zeroes).
+ * Returns JFGPU_ERR_FULL if a bucket overflowed (counts still exact, keys truncated). */
+int  jfgpu_extract_route(jfgpu_handle h, const void* dev_bytes, size_t n, uint32_t flags,
+                         void* dev_keys, uint64_t capacity, uint64_t* dev_counts, void* stream);
+/* Insert n packed keys (as produced by jfgpu_extract_route) that this shard owns:
+ * hash_counter::add for each (hash_counter.hpp:91-115). */
+int  jfgpu_insert_keys(jfgpu_handle h, const void* dev_keys, uint64_t n, void* stream);
+
+/* -- hash_counter::done (hash_counter.hpp:169-172): drain all device work ------------ */
+int  jfgpu_finish(jfgpu_handle h, jfgpu_stats* stats /* may be NULL */);
+int  jfgpu_get_stats(jfgpu_handle h, jfgpu_stats* stats);
+int  jfgpu_table_info_get(jfgpu_handle h, jfgpu_table_info* info);
+
+/* -- output: replaces sorted_dumper::_dump/start + binary_writer::write
+ *    (sorted_dumper.hpp:57-101, binary_dumper.hpp:36-40).  Streams this shard's records,
+ *    ascending by (position, key), each = ceil(2k/8) little-endian key bytes followed by
+ *    min(count, 2^(8*out_counter_len)-1) as out_counter_len little-endian bytes; only
+ *    counts in [lower, upper] are emitted.  `sink` is called on the calling thread with
+ *    consecutive byte ranges (whole records); a non-zero return aborts the dump. */
+typedef int (*jfgpu_sink_fn)(void* ctx, const void* records, size_t nbytes);
+int  jfgpu_dump(jfgpu_handle h, uint64_t lower, uint64_t upper, uint32_t out_counter_len,
+                jfgpu_sink_fn sink, void* ctx, uint64_t* n_records /* may be NULL */);
+
+/* -- lookup: array::get_val_for_key (large_hash_array.hpp:384-405).  keys: n packed
+ *    k-mers in HOST memory (1 or 2 uint64 words each, word 0 first); vals: n counts
+ *    (0 when absent).  Keys not owned by this shard give 0. */
+int  jfgpu_lookup(jfgpu_handle h, const uint64_t* keys, size_t n, uint64_t* vals);
+
+/* -- histogram straight from the resident table (what `jellyfish histo` computes from
+ *    the dump, sub_commands/histo_main.cc:33-45): hist[min(count,n_bins-1)]++ for every
+ *    distinct k-mer of this shard.  hist: n_bins uint64 in HOST memory. */
+int  jfgpu_histogram(jfgpu_handle h, uint64_t* hist, uint32_t n_bins);
+
+/* -- helpers ------------------------------------------------------------------------ */
+/* The hash matrix the reference would draw as its (skip+1)-th matrix for a table of
+ * 2^r slots and 2k = c key bits (rectangular_binary_matrix.cc:240-247 fed by the
+ * unseeded glibc random() of lib/misc.cc:66-72).  cols: c uint64. Host-only arithmetic. */
+int  jfgpu_reference_matrix(uint32_t r, uint32_t c, uint32_t skip, uint64_t* cols);
+/* Synthetic FASTA of the shape jellyfish/generate_sequence.cc:119-149 writes (one
+ * ">read1" record, 70 bases per line, iid uniform ACGT) generated directly in device
+ * memory with a counter-based RNG.  Returns the number of bytes written in *n_bytes
+ * (capacity must be >= jfgpu_synth_fasta_bytes(n_bases)). */
+uint64_t jfgpu_synth_fasta_bytes(uint64_t n_bases);
+int  jfgpu_synth_fasta_device(int device, void* dev_out, uint64_t capacity, uint64_t n_bases,
+                              uint64_t seed, uint64_t* n_bytes, void* stream);
+/* Pinned host memory for jfgpu_feed sources and dump sinks. */
+void* jfgpu_host_alloc(size_t bytes);
+void  jfgpu_host_free(void* p);
+/* Number of engine kernels launched so far by this process (bench "gpu_launches"). */
+uint64_t jfgpu_kernel_launches(void);
+const char* jfgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JFGPU_H */

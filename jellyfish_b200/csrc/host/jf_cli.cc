@@ -1,0 +1,642 @@
+// jf_cli.cc -- `jellyfish-b200`: the host driver that keeps the reference's command line
+// for the count path and calls the sm_100a engine through the C ABI (include/jfgpu.h).
+//
+//   jellyfish-b200 count  ...   switches of sub_commands/count_main_cmdline.yaggo:4-112
+//   jellyfish-b200 dump   ...   sub_commands/dump_main_cmdline.yaggo  (CPU reader of the format)
+//   jellyfish-b200 query  ...   sub_commands/query_main_cmdline.yaggo (CPU reader of the format)
+//   jellyfish-b200 info / histo / stats / merge      small CPU readers used by the tests
+//
+// The flow of `count` mirrors count_main (sub_commands/count_main.cc:218-385): header
+// fill_standard + cmdline, build the table, stream the input files, dump, --timing.
+#include <fcntl.h>
+#include <getopt.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jfgpu.h"
+#include "jf_file_header.hpp"
+
+namespace {
+
+[[noreturn]] void die(const std::string& msg) {
+  std::cerr << msg << std::endl;
+  exit(EXIT_FAILURE);
+}
+[[noreturn]] void usage_error(const std::string& msg) {
+  std::cerr << "Error: " << msg << std::endl;
+  exit(EXIT_FAILURE);
+}
+
+// SI suffixes, powers of 1000 (doc/jellyfish.man:137-139)
+uint64_t parse_u64(const char* s, bool suffix, const char* name) {
+  errno = 0;
+  char* end = nullptr;
+  while(*s == ' ') ++s;
+  if(*s == '-') usage_error(std::string("Invalid negative value for switch ") + name);
+  unsigned long long v = strtoull(s, &end, 0);
+  if(errno || end == s) usage_error(std::string("Invalid numeric value '") + s + "' for switch " + name);
+  if(*end) {
+    uint64_t mult = 0;
+    if(suffix && end[1] == '\0') switch(*end) {
+      case 'k': mult = 1000ULL; break;
+      case 'M': mult = 1000000ULL; break;
+      case 'G': mult = 1000000000ULL; break;
+      case 'T': mult = 1000000000000ULL; break;
+      case 'P': mult = 1000000000000000ULL; break;
+      case 'E': mult = 1000000000000000000ULL; break;
+    }
+    if(!mult) usage_error(std::string("Invalid numeric value '") + s + "' for switch " + name);
+    v *= mult;
+  }
+  return v;
+}
+
+// 2-bit packed k-mer <-> text: first base in the most significant pair (mer_dna.hpp:451-462,525-542)
+std::string mer_to_string(const uint64_t* w, unsigned k) {
+  std::string s(k, 'A');
+  for(unsigned i = 0; i < k; ++i) {
+    unsigned bit = 2 * (k - 1 - i);
+    s[i] = "ACGT"[(w[bit >> 6] >> (bit & 63)) & 3];
+  }
+  return s;
+}
+bool string_to_mer(const char* s, unsigned k, uint64_t* w) {
+  w[0] = w[1] = 0;
+  if(strlen(s) != k) return false;
+  for(unsigned i = 0; i < k; ++i) {
+    int c;
+    switch(s[i]) { case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break;
+                   case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break; default: return false; }
+    unsigned bit = 2 * (k - 1 - i);
+    w[bit >> 6] |= (uint64_t)c << (bit & 63);
+  }
+  return true;
+}
+void reverse_complement(const uint64_t* in, unsigned k, uint64_t* out) {
+  out[0] = out[1] = 0;
+  for(unsigned i = 0; i < k; ++i) {
+    unsigned bit = 2 * i;
+    uint64_t c = 3 - ((in[bit >> 6] >> (bit & 63)) & 3);
+    unsigned ob = 2 * (k - 1 - i);
+    out[ob >> 6] |= c << (ob & 63);
+  }
+}
+bool mer_less(const uint64_t* a, const uint64_t* b) { return a[1] != b[1] ? a[1] < b[1] : a[0] < b[0]; }
+
+// ------------------------------------------------------------------------------------------
+// reader of the binary/sorted format (binary_dumper.hpp:83-109)
+// ------------------------------------------------------------------------------------------
+struct db_reader {
+  jfb::file_header header;
+  const unsigned char* base = nullptr;   // mmap
+  size_t file_size = 0, body_off = 0, n_records = 0;
+  unsigned k = 0, key_bytes = 0, counter_len = 0, rec = 0;
+  jfb::gf2_matrix matrix;
+  uint64_t size_mask = 0;
+  int fd = -1;
+
+  void open(const char* path) {
+    fd = ::open(path, O_RDONLY);
+    if(fd < 0) die(std::string("Failed to open input file '") + path + "'");
+    struct stat st;
+    fstat(fd, &st);
+    file_size = st.st_size;
+    base = file_size ? (const unsigned char*)mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    if(file_size && base == MAP_FAILED) die(std::string("Can't mmap file '") + path + "'");
+    if(!header.read((const char*)base, file_size)) die(std::string("Failed to parse header of file '") + path + "'");
+    body_off = header.offset();
+    k = header.key_len() / 2;
+    key_bytes = (header.key_len() + 7) / 8;
+    counter_len = header.counter_len();
+    rec = key_bytes + counter_len;
+    if(header.format() == "binary/sorted") {
+      matrix = header.matrix(1);
+      size_mask = header.size() - 1;
+      n_records = rec ? (file_size - body_off) / rec : 0;
+    }
+  }
+  void key_at(size_t i, uint64_t* w) const {
+    w[0] = w[1] = 0;
+    memcpy(w, base + body_off + i * rec, key_bytes);
+  }
+  uint64_t val_at(size_t i) const {
+    uint64_t v = 0;
+    memcpy(&v, base + body_off + i * rec + key_bytes, counter_len);
+    return v;
+  }
+  uint64_t pos_of(const uint64_t* w) const { return matrix.times(w) & size_mask; }
+  ~db_reader() { if(base && base != MAP_FAILED) munmap((void*)base, file_size); if(fd >= 0) close(fd); }
+};
+
+// ------------------------------------------------------------------------------------------
+// count
+// ------------------------------------------------------------------------------------------
+struct count_args {
+  uint32_t mer_len = 0; bool mer_len_given = false;
+  uint64_t size = 0; bool size_given = false;
+  uint32_t threads = 1, Files = 1, Generators = 1;
+  const char* output = "mer_counts.jf";
+  uint32_t counter_len = 7, out_counter_len = 4, reprobes = 126;
+  bool canonical = false, text = false, disk = false, no_merge = false, no_unlink = false, no_write = false;
+  bool bc_given = false, bf_size_given = false, if_given = false, generator_given = false, sam_given = false;
+  bool qual_given = false, timing_given = false, lower_given = false, upper_given = false;
+  uint64_t bf_size = 0, lower = 0, upper = 0;
+  double bf_fp = 0.01;
+  const char* timing = "";
+  int device = 0;
+  std::vector<const char*> files;
+};
+
+struct sink_ctx { FILE* f; bool ok; };
+int file_sink(void* ctx, const void* recs, size_t n) {
+  sink_ctx* c = (sink_ctx*)ctx;
+  if(fwrite(recs, 1, n, c->f) != n) { c->ok = false; return 1; }
+  return 0;
+}
+
+int count_main(int argc, char* argv[]) {
+  using clk = std::chrono::system_clock;
+  auto start_time = clk::now();
+  jfb::file_header header;
+  header.fill_standard();
+  header.set_cmdline(argc, argv);
+
+  count_args a;
+  enum { O_SAM = 1000, O_OCL, O_BC, O_BFSIZE, O_BFFP, O_IF, O_QSTART, O_MINQ, O_TEXT, O_DISK, O_NOMERGE, O_NOUNLINK,
+         O_TIMING, O_NOWRITE, O_DEVICE };
+  static struct option longs[] = {
+    {"mer-len", required_argument, 0, 'm'}, {"size", required_argument, 0, 's'}, {"threads", required_argument, 0, 't'},
+    {"sam", required_argument, 0, O_SAM}, {"Files", required_argument, 0, 'F'}, {"generator", required_argument, 0, 'g'},
+    {"Generators", required_argument, 0, 'G'}, {"shell", required_argument, 0, 'S'}, {"output", required_argument, 0, 'o'},
+    {"counter-len", required_argument, 0, 'c'}, {"out-counter-len", required_argument, 0, O_OCL},
+    {"canonical", no_argument, 0, 'C'}, {"bc", required_argument, 0, O_BC}, {"bf-size", required_argument, 0, O_BFSIZE},
+    {"bf-fp", required_argument, 0, O_BFFP}, {"if", required_argument, 0, O_IF}, {"min-qual-char", required_argument, 0, 'Q'},
+    {"quality-start", required_argument, 0, O_QSTART}, {"min-quality", required_argument, 0, O_MINQ},
+    {"reprobes", required_argument, 0, 'p'}, {"text", no_argument, 0, O_TEXT}, {"disk", no_argument, 0, O_DISK},
+    {"no-merge", no_argument, 0, O_NOMERGE}, {"no-unlink", no_argument, 0, O_NOUNLINK},
+    {"lower-count", required_argument, 0, 'L'}, {"upper-count", required_argument, 0, 'U'},
+    {"timing", required_argument, 0, O_TIMING}, {"no-write", no_argument, 0, O_NOWRITE},
+    {"device", required_argument, 0, O_DEVICE}, {"help", no_argument, 0, 'h'}, {0, 0, 0, 0} };
+  optind = 1;
+  int c;
+  while((c = getopt_long(argc, argv, "m:s:t:F:g:G:S:o:c:CQ:p:L:U:h", longs, 0)) != -1) {
+    switch(c) {
+    case 'm': a.mer_len = (uint32_t)parse_u64(optarg, false, "-m"); a.mer_len_given = true; break;
+    case 's': a.size = parse_u64(optarg, true, "-s"); a.size_given = true; break;
+    case 't': a.threads = (uint32_t)parse_u64(optarg, false, "-t"); break;
+    case 'F': a.Files = (uint32_t)parse_u64(optarg, false, "-F"); break;
+    case 'g': a.generator_given = true; break;
+    case 'G': a.Generators = (uint32_t)parse_u64(optarg, false, "-G"); break;
+    case 'S': break;
+    case 'o': a.output = optarg; break;
+    case 'c': a.counter_len = (uint32_t)parse_u64(optarg, false, "-c"); break;
+    case O_OCL: a.out_counter_len = (uint32_t)parse_u64(optarg, false, "--out-counter-len"); break;
+    case 'C': a.canonical = true; break;
+    case O_BC: a.bc_given = true; break;
+    case O_BFSIZE: a.bf_size = parse_u64(optarg, true, "--bf-size"); a.bf_size_given = true; break;
+    case O_BFFP: a.bf_fp = atof(optarg); break;
+    case O_IF: a.if_given = true; break;
+    case 'Q': case O_QSTART: case O_MINQ: a.qual_given = true; break;
+    case 'p': a.reprobes = (uint32_t)parse_u64(optarg, false, "-p"); break;
+    case O_TEXT: a.text = true; break;
+    case O_DISK: a.disk = true; break;
+    case O_NOMERGE: a.no_merge = true; break;
+    case O_NOUNLINK: a.no_unlink = true; break;
+    case 'L': a.lower = parse_u64(optarg, false, "-L"); a.lower_given = true; break;
+    case 'U': a.upper = parse_u64(optarg, false, "-U"); a.upper_given = true; break;
+    case O_TIMING: a.timing = optarg; a.timing_given = true; break;
+    case O_NOWRITE: a.no_write = true; break;
+    case O_DEVICE: a.device = atoi(optarg); break;
+    case 'h': std::cout << "Usage: jellyfish-b200 count [options] file:path+\n"; return 0;
+    default: usage_error("Invalid command line. Usage: jellyfish-b200 count [options] file:path+");
+    }
+  }
+  for(int i = optind; i < argc; ++i) a.files.push_back(argv[i]);
+  if(!a.mer_len_given) usage_error("Missing required switch --mer-len");
+  if(!a.size_given) usage_error("Missing required switch --size");
+  if(a.bc_given && a.bf_size_given) usage_error("Switches [--bf-size] and [--bc] conflict");
+  if(a.sam_given) usage_error("SAM/BAM/CRAM not supported (missing htslib).");
+  if(a.generator_given) usage_error("generators (-g) are not supported by jellyfish-b200");
+  if(a.bc_given || a.bf_size_given) usage_error("Bloom prefilters (--bc/--bf-size) are not implemented yet in jellyfish-b200");
+  if(a.if_given) usage_error("--if is not implemented yet in jellyfish-b200");
+  if(a.qual_given) usage_error("quality filtering (-Q/--min-quality) is not implemented yet in jellyfish-b200");
+  if(a.text) usage_error("--text is not implemented yet in jellyfish-b200");
+  if(a.disk) usage_error("--disk is not implemented in jellyfish-b200 (the table is doubled on the device instead)");
+  if(a.mer_len < 1 || a.mer_len > 64) usage_error("jellyfish-b200 supports mer lengths 1..64");
+
+  header.canonical(a.canonical);
+  jfgpu_params p;
+  memset(&p, 0, sizeof(p));
+  p.struct_size = sizeof(p);
+  p.k = a.mer_len; p.size = a.size; p.counter_len = a.counter_len; p.max_reprobe = a.reprobes;
+  p.canonical = a.canonical; p.allow_regrow = 1; p.device = a.device; p.shard_index = 0; p.n_shards = 1;
+  jfgpu_handle h = nullptr;
+  if(jfgpu_create(&p, &h) != JFGPU_OK) die(std::string("Failed to create the device hash: ") + jfgpu_last_error(nullptr));
+  auto after_init_time = clk::now();
+
+  // ---- stream the files through the engine: a reader thread fills pinned buffers --------------
+  const size_t BUF = (size_t)64 << 20;
+  struct chunk { char* data; size_t n; uint32_t flags; bool last; std::string error; };
+  const int NBUF = 3;
+  std::vector<char*> bufs(NBUF);
+  for(int i = 0; i < NBUF; ++i) { bufs[i] = (char*)jfgpu_host_alloc(BUF); if(!bufs[i]) die("pinned host allocation failed"); }
+  std::mutex mu; std::condition_variable cv;
+  std::queue<chunk> ready; std::queue<char*> freeb;
+  for(int i = 0; i < NBUF; ++i) freeb.push(bufs[i]);
+  std::thread reader([&] {
+    auto get_buf = [&]() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !freeb.empty(); }); char* b = freeb.front(); freeb.pop(); return b; };
+    auto put = [&](chunk c) { std::unique_lock<std::mutex> l(mu); ready.push(c); cv.notify_all(); };
+    for(size_t fi = 0; fi < a.files.size(); ++fi) {
+      int fd = ::open(a.files[fi], O_RDONLY);
+      if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + a.files[fi] + "'"}); return; }
+      bool first = true, eof = false;
+      char* cur = get_buf();
+      size_t have = 0;
+      // read one chunk ahead so that the last one can carry FILE_END
+      auto fill = [&](char* b) -> size_t { size_t n = 0; while(n < BUF) { ssize_t r = ::read(fd, b + n, BUF - n); if(r <= 0) { eof = true; break; } n += r; } return n; };
+      have = fill(cur);
+      while(true) {
+        char* nxt = nullptr; size_t nn = 0;
+        if(!eof) { nxt = get_buf(); nn = fill(nxt); }
+        bool last_of_file = eof && nn == 0;
+        uint32_t fl = (first ? JFGPU_FILE_BEGIN : 0) | (last_of_file ? JFGPU_FILE_END : 0);
+        put(chunk{cur, have, fl, false, ""});
+        first = false;
+        if(last_of_file) { if(nxt) { std::unique_lock<std::mutex> l(mu); freeb.push(nxt); } break; }
+        cur = nxt; have = nn;
+      }
+      ::close(fd);
+    }
+    put(chunk{nullptr, 0, 0, true, ""});
+  });
+  std::string feed_error;
+  int feed_rc = 0;
+  while(true) {
+    chunk ck;
+    { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !ready.empty(); }); ck = ready.front(); ready.pop(); }
+    if(ck.last) { if(!ck.error.empty()) feed_error = ck.error; break; }
+    if(!feed_rc && feed_error.empty()) {
+      feed_rc = jfgpu_feed(h, ck.data, ck.n, ck.flags);
+      if(feed_rc) feed_error = jfgpu_last_error(h);
+    }
+    { std::unique_lock<std::mutex> l(mu); freeb.push(ck.data); cv.notify_all(); }
+  }
+  reader.join();
+  if(!feed_error.empty()) die(feed_error);
+  jfgpu_stats st;
+  if(jfgpu_finish(h, &st) != JFGPU_OK) die(jfgpu_last_error(h));
+  auto after_count_time = clk::now();
+
+  // ---- dump (binary_dumper::_dump -> sorted_dumper::_dump, binary_dumper.hpp:62-69) ------------
+  if(!a.no_write) {
+    jfgpu_table_info ti;
+    jfgpu_table_info_get(h, &ti);
+    header.size(ti.size);
+    header.key_len(ti.key_len);
+    header.val_len(ti.val_len);
+    if(ti.matrix_identity) header.matrix(ti.matrix_r == ti.matrix_c ? jfb::gf2_matrix::identity(ti.matrix_c)
+                                                                      : jfb::gf2_matrix::low_identity(ti.matrix_r, ti.matrix_c));
+    else header.matrix(jfb::gf2_matrix(ti.matrix_r, ti.matrix_c, ti.matrix_columns));
+    header.max_reprobe(ti.max_reprobe);
+    header.set_reprobes(ti.reprobes);
+    header.format("binary/sorted");
+    header.counter_len(a.out_counter_len);
+    std::ofstream out(a.output, std::ios::binary);
+    if(!out.good()) die(std::string("Can't open output file '") + a.output + "'");
+    header.write(out);
+    out.close();
+    FILE* f = fopen(a.output, "ab");
+    if(!f) die(std::string("Can't open output file '") + a.output + "'");
+    std::vector<char> iobuf((size_t)8 << 20);
+    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+    sink_ctx sc = { f, true };
+    const uint64_t lo = a.lower_given ? a.lower : 0, hi = a.upper_given ? a.upper : std::numeric_limits<uint64_t>::max();
+    int rc = jfgpu_dump(h, lo, hi, a.out_counter_len, file_sink, &sc, nullptr);
+    fclose(f);
+    if(rc != JFGPU_OK) die(std::string("Error while dumping: ") + jfgpu_last_error(h));
+  }
+  auto after_dump_time = clk::now();
+  if(a.timing_given) {
+    auto secs = [](clk::duration d) { return std::chrono::duration_cast<std::chrono::duration<double>>(d).count(); };
+    std::ofstream tf(a.timing);
+    tf << "Init     " << secs(after_init_time - start_time) << "\n"
+       << "Counting " << secs(after_count_time - after_init_time) << "\n"
+       << "Writing  " << secs(after_dump_time - after_count_time) << "\n";
+  }
+  for(int i = 0; i < NBUF; ++i) jfgpu_host_free(bufs[i]);
+  jfgpu_destroy(h);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// dump (sub_commands/dump_main.cc:35-88)
+// ------------------------------------------------------------------------------------------
+int dump_main(int argc, char* argv[]) {
+  bool column = false, tab = false, lower_given = false, upper_given = false;
+  uint64_t lower = 0, upper = std::numeric_limits<uint64_t>::max();
+  const char* output = nullptr;
+  static struct option longs[] = { {"column", no_argument, 0, 'c'}, {"tab", no_argument, 0, 't'},
+    {"lower-count", required_argument, 0, 'L'}, {"upper-count", required_argument, 0, 'U'},
+    {"output", required_argument, 0, 'o'}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "ctL:U:o:", longs, 0)) != -1) switch(c) {
+    case 'c': column = true; break; case 't': tab = true; break;
+    case 'L': lower = parse_u64(optarg, false, "-L"); lower_given = true; break;
+    case 'U': upper = parse_u64(optarg, false, "-U"); upper_given = true; break;
+    case 'o': output = optarg; break;
+    default: usage_error("Usage: jellyfish-b200 dump [options] db:path");
+  }
+  (void)lower_given; (void)upper_given;
+  if(argc - optind != 1) usage_error("Requires exactly 1 argument.");
+  db_reader db; db.open(argv[optind]);
+  if(db.header.format() != "binary/sorted") die("Unknown format '" + db.header.format() + "'");
+  FILE* out = output ? fopen(output, "w") : stdout;
+  if(!out) die(std::string("Error opening output file '") + output + "'");
+  uint64_t w[2];
+  for(size_t i = 0; i < db.n_records; ++i) {
+    uint64_t v = db.val_at(i);
+    if(v < lower || v > upper) continue;
+    db.key_at(i, w);
+    std::string s = mer_to_string(w, db.k);
+    if(column) fprintf(out, "%s%c%llu\n", s.c_str(), tab ? '\t' : ' ', (unsigned long long)v);
+    else fprintf(out, ">%llu\n%s\n", (unsigned long long)v, s.c_str());
+  }
+  if(output) fclose(out);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// query (sub_commands/query_main.cc:86-123; binary_dumper.hpp:148-189): the file is sorted by
+// (position, key), so a plain binary search on that pair finds a k-mer.
+// ------------------------------------------------------------------------------------------
+uint64_t db_lookup(const db_reader& db, const uint64_t* key) {
+  const uint64_t pos = db.pos_of(key);
+  size_t lo = 0, hi = db.n_records;
+  uint64_t w[2];
+  while(lo < hi) {
+    size_t mid = lo + (hi - lo) / 2;
+    db.key_at(mid, w);
+    uint64_t mp = db.pos_of(w);
+    bool less = mp != pos ? mp < pos : mer_less(w, key);
+    if(less) lo = mid + 1; else hi = mid;
+  }
+  if(lo < db.n_records) { db.key_at(lo, w); if(w[0] == key[0] && w[1] == key[1]) return db.val_at(lo); }
+  return 0;
+}
+
+int query_main(int argc, char* argv[]) {
+  std::vector<const char*> sequences; const char* output = nullptr; bool interactive = false;
+  static struct option longs[] = { {"sequence", required_argument, 0, 's'}, {"output", required_argument, 0, 'o'},
+    {"interactive", no_argument, 0, 'i'}, {"load", no_argument, 0, 'l'}, {"no-load", no_argument, 0, 'L'}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "s:o:ilL", longs, 0)) != -1) switch(c) {
+    case 's': sequences.push_back(optarg); break; case 'o': output = optarg; break; case 'i': interactive = true; break;
+    case 'l': case 'L': break;
+    default: usage_error("Usage: jellyfish-b200 query [options] file:path mers:string*");
+  }
+  if(argc - optind < 1) usage_error("Requires at least 1 argument.");
+  db_reader db; db.open(argv[optind]);
+  if(db.header.format() != "binary/sorted") die("Unsupported format '" + db.header.format() + "'. Must be a bloom counter or binary list.");
+  FILE* out = output ? fopen(output, "w") : stdout;
+  if(!out) die(std::string("Error opening output file '") + output + "'");
+  const bool canonical = db.header.canonical();
+  auto query_one = [&](const char* s) {
+    uint64_t m[2], r[2];
+    if(!string_to_mer(s, db.k, m)) { fprintf(stderr, "Invalid mer '%s'\n", s); return; }
+    const uint64_t* q = m;
+    if(canonical) { reverse_complement(m, db.k, r); if(mer_less(r, m)) q = r; }
+    fprintf(out, "%s %llu\n", mer_to_string(q, db.k).c_str(), (unsigned long long)db_lookup(db, q));
+  };
+  for(const char* path : sequences) {          // every k-mer of the sequence files, in order
+    std::ifstream is(path);
+    if(!is.good()) die(std::string("Can't open file '") + path + "'");
+    std::string line, seq;
+    auto flush = [&]() {
+      uint64_t m[2] = {0, 0}, r[2] = {0, 0}; unsigned filled = 0;
+      const unsigned k = db.k;
+      for(char ch : seq) {
+        int code;
+        switch(ch) { case 'A': case 'a': code = 0; break; case 'C': case 'c': code = 1; break;
+                     case 'G': case 'g': code = 2; break; case 'T': case 't': code = 3; break; default: code = -1; }
+        if(code < 0) { filled = 0; continue; }
+        // shift left m, shift right r
+        uint64_t carry = m[0] >> 62;
+        m[0] = (m[0] << 2) | (uint64_t)code; m[1] = (m[1] << 2) | carry;
+        unsigned top = 2 * k; if(top < 64) m[0] &= ((uint64_t)1 << top) - 1, m[1] = 0; else if(top < 128) m[1] &= ((uint64_t)1 << (top - 64)) - 1;
+        r[0] = (r[0] >> 2) | (r[1] << 62); r[1] >>= 2;
+        unsigned ob = 2 * (k - 1); r[ob >> 6] |= (uint64_t)(3 - code) << (ob & 63);
+        if(++filled >= k) {
+          const uint64_t* q = (canonical && mer_less(r, m)) ? r : m;
+          fprintf(out, "%s %llu\n", mer_to_string(q, k).c_str(), (unsigned long long)db_lookup(db, q));
+        }
+      }
+      seq.clear();
+    };
+    while(std::getline(is, line)) {
+      if(!line.empty() && line[0] == '>') { flush(); continue; }
+      while(!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+      seq += line;
+    }
+    flush();
+  }
+  for(int i = optind + 1; i < argc; ++i) query_one(argv[i]);
+  if(interactive) { std::string s; while(std::cin >> s) query_one(s.c_str()); }
+  if(output) fclose(out);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// info / histo / stats : sub_commands/{info,histo,stats}_main.cc
+// ------------------------------------------------------------------------------------------
+int info_main(int argc, char* argv[]) {
+  bool skip = false, js = false, cmd = false;
+  static struct option longs[] = { {"skip", no_argument, 0, 's'}, {"json", no_argument, 0, 'j'}, {"cmd", no_argument, 0, 'c'}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "sjc", longs, 0)) != -1) switch(c) {
+    case 's': skip = true; break; case 'j': js = true; break; case 'c': cmd = true; break;
+    default: usage_error("Usage: jellyfish-b200 info [options] file:path");
+  }
+  if(argc - optind != 1) usage_error("Requires exactly 1 argument.");
+  db_reader db; db.open(argv[optind]);
+  if(skip) { fwrite(db.base + db.body_off, 1, db.file_size - db.body_off, stdout); return 0; }
+  if(js) { std::cout << db.header.root().dump() << "\n"; return 0; }
+  std::vector<std::string> cl = db.header.cmdline();
+  std::string line;
+  for(size_t i = 0; i < cl.size(); ++i) { if(i) line += ' '; line += cl[i]; }
+  if(cmd) { std::cout << line << "\n"; return 0; }
+  const jfb::json& r = db.header.root();
+  std::cout << "command: " << line << "\n"
+            << "where: " << r.at("hostname").as_string() << ":" << r.at("pwd").as_string() << "\n"
+            << "when: " << r.at("time").as_string() << "\n"
+            << "canonical: " << (db.header.canonical() ? "yes" : "no") << "\n";
+  return 0;
+}
+
+int histo_main(int argc, char* argv[]) {
+  uint64_t low = 1, high = 10000, inc = 1; bool full = false; const char* output = nullptr;
+  static struct option longs[] = { {"low", required_argument, 0, 'l'}, {"high", required_argument, 0, 'h'},
+    {"increment", required_argument, 0, 'i'}, {"threads", required_argument, 0, 't'}, {"full", no_argument, 0, 'f'},
+    {"output", required_argument, 0, 'o'}, {"buffer-size", required_argument, 0, 's'}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "l:h:i:t:fo:s:v", longs, 0)) != -1) switch(c) {
+    case 'l': low = parse_u64(optarg, false, "-l"); break; case 'h': high = parse_u64(optarg, false, "-h"); break;
+    case 'i': inc = parse_u64(optarg, false, "-i"); break; case 'f': full = true; break; case 'o': output = optarg; break;
+    case 't': case 's': case 'v': break;
+    default: usage_error("Usage: jellyfish-b200 histo [options] db:path");
+  }
+  if(argc - optind != 1) usage_error("Requires exactly 1 argument.");
+  if(high < low) usage_error("High count value must be >= to low count value");
+  db_reader db; db.open(argv[optind]);
+  if(db.header.format() != "binary/sorted") die("Unknown format '" + db.header.format() + "'");
+  // histo_main.cc:33-45,64-86
+  const uint64_t base = inc >= low ? 0 : low - inc;
+  const uint64_t ceil = high + inc;
+  const uint64_t nb_buckets = (ceil + inc - base) / inc;
+  std::vector<uint64_t> histo(nb_buckets, 0);
+  for(size_t i = 0; i < db.n_records; ++i) {
+    uint64_t v = db.val_at(i);
+    if(v < base) ++histo[0];
+    else if(v > ceil) ++histo[nb_buckets - 1];
+    else ++histo[(v - base) / inc];
+  }
+  FILE* out = output ? fopen(output, "w") : stdout;
+  if(!out) die(std::string("Error opening output file '") + output + "'");
+  for(uint64_t i = 0, col = base; i < nb_buckets; ++i, col += inc)
+    if(histo[i] > 0 || full) fprintf(out, "%llu %llu\n", (unsigned long long)col, (unsigned long long)histo[i]);
+  if(output) fclose(out);
+  return 0;
+}
+
+int stats_main(int argc, char* argv[]) {
+  uint64_t lower = 0, upper = std::numeric_limits<uint64_t>::max(); const char* output = nullptr;
+  static struct option longs[] = { {"recompute", no_argument, 0, 'r'}, {"lower-count", required_argument, 0, 'L'},
+    {"upper-count", required_argument, 0, 'U'}, {"verbose", no_argument, 0, 'v'}, {"output", required_argument, 0, 'o'}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "rL:U:vo:", longs, 0)) != -1) switch(c) {
+    case 'L': lower = parse_u64(optarg, false, "-L"); break; case 'U': upper = parse_u64(optarg, false, "-U"); break;
+    case 'o': output = optarg; break; case 'r': case 'v': break;
+    default: usage_error("Usage: jellyfish-b200 stats [options] db:path");
+  }
+  if(argc - optind != 1) usage_error("Requires exactly 1 argument.");
+  db_reader db; db.open(argv[optind]);
+  if(db.header.format() != "binary/sorted") die("Unknown format '" + db.header.format() + "'");
+  uint64_t uniq = 0, distinct = 0, total = 0, maxc = 0;
+  for(size_t i = 0; i < db.n_records; ++i) {
+    uint64_t v = db.val_at(i);
+    if(v < lower || v > upper) continue;
+    if(v == 1) ++uniq;
+    total += v; ++distinct; maxc = std::max(maxc, v);
+  }
+  FILE* out = output ? fopen(output, "w") : stdout;
+  if(!out) die(std::string("Error opening output file '") + output + "'");
+  fprintf(out, "Unique:    %llu\nDistinct:  %llu\nTotal:     %llu\nMax_count: %llu\n", (unsigned long long)uniq,
+          (unsigned long long)distinct, (unsigned long long)total, (unsigned long long)maxc);
+  if(output) fclose(out);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// merge (SUM only): k-way merge of files sharing size/matrix/key_len (jellyfish/merge_files.cc:45-176).
+// This is how per-GPU shard dumps become one database.
+// ------------------------------------------------------------------------------------------
+int merge_main(int argc, char* argv[]) {
+  const char* output = "mer_counts_merged.jf";
+  uint64_t lower = 0, upper = std::numeric_limits<uint64_t>::max();
+  static struct option longs[] = { {"output", required_argument, 0, 'o'}, {"lower-count", required_argument, 0, 'L'},
+    {"upper-count", required_argument, 0, 'U'}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "o:L:U:", longs, 0)) != -1) switch(c) {
+    case 'o': output = optarg; break;
+    case 'L': lower = parse_u64(optarg, false, "-L"); break; case 'U': upper = parse_u64(optarg, false, "-U"); break;
+    default: usage_error("Usage: jellyfish-b200 merge [options] input:string+ (only the SUM operation is implemented)");
+  }
+  const int n = argc - optind;
+  if(n < 2) usage_error("Requires at least 2 arguments.");
+  std::vector<db_reader> dbs(n);
+  for(int i = 0; i < n; ++i) {
+    dbs[i].open(argv[optind + i]);
+    if(dbs[i].header.format() != "binary/sorted") die(std::string("Can only merge binary/sorted files: '") + argv[optind + i] + "'");
+    if(i) {
+      const jfb::file_header &a = dbs[0].header, &b = dbs[i].header;
+      if(a.key_len() != b.key_len()) die("Can't merge hashes of different key lengths");
+      if(a.size() != b.size()) die("Can't merge hash with different size");
+      if(a.matrix(1) != b.matrix(1)) die("Can't merge hash with different hash function");
+      if(a.max_reprobe_offset() != b.max_reprobe_offset()) die("Can't merge hashes with different reprobing strategies");
+    }
+  }
+  jfb::file_header oh;
+  oh.fill_standard();
+  oh.set_cmdline(argc, argv);
+  const jfb::file_header& h0 = dbs[0].header;
+  oh.size(h0.size()); oh.key_len(h0.key_len()); oh.val_len(h0.val_len()); oh.matrix(h0.matrix(1));
+  oh.max_reprobe(h0.max_reprobe()); { std::vector<uint64_t> r = h0.reprobes(); oh.set_reprobes(r.data()); }
+  oh.format("binary/sorted"); oh.counter_len(h0.counter_len()); oh.canonical(h0.canonical());
+  std::ofstream out(output, std::ios::binary);
+  if(!out.good()) die(std::string("Can't open out file '") + output + "'");
+  oh.write(out);
+  struct item { uint64_t pos; uint64_t key[2]; int src; };
+  auto greater = [](const item& a, const item& b) {
+    if(a.pos != b.pos) return a.pos > b.pos;
+    if(a.key[1] != b.key[1]) return a.key[1] > b.key[1];
+    return a.key[0] > b.key[0];
+  };
+  std::priority_queue<item, std::vector<item>, decltype(greater)> heap(greater);
+  std::vector<size_t> cur(n, 0);
+  auto push = [&](int i) {
+    if(cur[i] < dbs[i].n_records) { item it; dbs[i].key_at(cur[i], it.key); it.pos = dbs[i].pos_of(it.key); it.src = i; heap.push(it); }
+  };
+  for(int i = 0; i < n; ++i) push(i);
+  const unsigned key_bytes = dbs[0].key_bytes, ocl = dbs[0].counter_len;
+  const uint64_t maxv = ocl >= 8 ? ~(uint64_t)0 : (((uint64_t)1 << (8 * ocl)) - 1);
+  while(!heap.empty()) {
+    item top = heap.top();
+    uint64_t sum = 0;
+    while(!heap.empty() && heap.top().key[0] == top.key[0] && heap.top().key[1] == top.key[1]) {
+      int i = heap.top().src; heap.pop();
+      sum += dbs[i].val_at(cur[i]); ++cur[i];
+      push(i);
+    }
+    if(sum >= lower && sum <= upper) {
+      out.write((const char*)top.key, key_bytes);
+      uint64_t v = std::min(sum, maxv);
+      out.write((const char*)&v, ocl);
+    }
+  }
+  out.close();
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  if(argc < 2) { std::cerr << "Too few arguments\nUsage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, dump, query, info, histo, stats, merge.\n"; return 1; }
+  std::string cmd = argv[1];
+  if(cmd == "count") return count_main(argc - 1, argv + 1);
+  if(cmd == "dump")  return dump_main(argc - 1, argv + 1);
+  if(cmd == "query") return query_main(argc - 1, argv + 1);
+  if(cmd == "info")  return info_main(argc - 1, argv + 1);
+  if(cmd == "histo") return histo_main(argc - 1, argv + 1);
+  if(cmd == "stats") return stats_main(argc - 1, argv + 1);
+  if(cmd == "merge") return merge_main(argc - 1, argv + 1);
+  if(cmd == "--version" || cmd == "-V") { std::cout << jfgpu_version() << std::endl; return 0; }
+  if(cmd == "--help" || cmd == "-h" || cmd == "help") { std::cout << "Usage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, dump, query, info, histo, stats, merge.\n"; return 0; }
+  std::cerr << "Unknown command '" << cmd << "'\n";
+  return 1;
+}

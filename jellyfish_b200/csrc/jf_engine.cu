@@ -1,0 +1,833 @@
+// jf_engine.cu -- C-ABI implementation (include/jfgpu.h) of the B200 k-mer counting engine.
+// Host orchestration only: every byte of the hot path is processed by the kernels in
+// jf_kernels.cuh.  There is no CPU fallback; without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jfgpu.h"
+#include "host/jf_matrix.hpp"
+#include "jf_kernels.cuh"
+
+using namespace jfk;
+
+static std::atomic<unsigned long long> g_launches(0);
+static thread_local std::string g_create_error;
+
+#define JF_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+namespace {
+
+unsigned ceil_log2(uint64_t x) { unsigned l = 0; while(l < 64 && ((uint64_t)1 << l) < x) ++l; return l; }
+unsigned bitsize(uint64_t x) { unsigned b = 0; while(x) { ++b; x >>= 1; } return b ? b : 1; }
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  cudaError_t alloc(size_t n) { free(); bytes = n; return n ? cudaMalloc(&p, n) : cudaSuccess; }
+  void free() { if(p) cudaFree(p); p = nullptr; bytes = 0; }
+  template<typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// byte-indexed tables of a GF(2) matrix: entry [b*256+v] = product with the vector whose
+// byte b equals v (reference column order: bit i selects columns[c-1-i],
+// rectangular_binary_matrix.hpp:223-261)
+std::vector<uint64_t> build_lut(const jfb::gf2_matrix& m, unsigned nbytes) {
+  std::vector<uint64_t> lut((size_t)nbytes * 256, 0);
+  const unsigned c = m.c(), r = m.r();
+  for(unsigned b = 0; b < nbytes; ++b) {
+    uint64_t col[8];
+    for(unsigned j = 0; j < 8; ++j) {
+      unsigned i = 8 * b + j;
+      if(i >= c) col[j] = 0;
+      else if(m.is_identity()) col[j] = i < r ? ((uint64_t)1 << i) : 0;
+      else col[j] = m[c - 1 - i];
+    }
+    for(unsigned v = 0; v < 256; ++v) {
+      uint64_t x = 0;
+      for(unsigned j = 0; j < 8; ++j) if(v & (1u << j)) x ^= col[j];
+      lut[(size_t)b * 256 + v] = x;
+    }
+  }
+  return lut;
+}
+
+struct Table {
+  unsigned lsize = 0, local_lsize = 0, max_reprobe = 0, rbits = 1, fbits = 1, slot_bits = 32, hb = 0;
+  uint64_t size = 0, local_size = 0, margin = 0, local_slots = 0;
+  jfb::gf2_matrix M, Minv;
+  DevBuf slots, lut, inv_lut, ovf_keys, ovf_vals;
+  std::vector<uint64_t> reprobes;
+  void release() { slots.free(); lut.free(); inv_lut.free(); ovf_keys.free(); ovf_vals.free(); }
+  size_t bytes() const { return (size_t)local_slots * (slot_bits / 8); }
+};
+
+}  // namespace
+
+struct jfgpu_engine {
+  jfgpu_params p;
+  int device = 0;
+  unsigned k = 0, kw = 1, nbytes = 0, shard_bits = 0;
+  cudaStream_t cs = nullptr, hs = nullptr;
+  int n_sm = 148;
+  jfb::glibc_random rng;
+  Table tab;
+  DevBuf stats, carry[2], fail_keys[2], fail_counts[2];
+  uint64_t ovf_size = 0, fail_cap = 0;
+  int carry_cur = 0, fail_cur = 0;
+  unsigned long long* h_stats = nullptr;    // pinned mirror
+  // staging for host feeds
+  size_t batch_bytes = 0;
+  DevBuf stage[2]; cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
+  int stage_cur = 0;
+  // per-batch scratch
+  DevBuf nlA, nlB, tstate; uint64_t scratch_tiles = 0;
+  // bookkeeping
+  bool in_file = false;
+  uint64_t bytes_fed = 0, regrows = 0;
+  double count_ms = 0;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  std::string err;
+  std::vector<uint64_t> matrix_cols_host;   // for jfgpu_table_info_get
+  int count_smem = 0;
+};
+
+namespace {
+
+int fail(jfgpu_engine* e, int code, const std::string& msg) {
+  if(e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CUDA_OK(e, call) do { cudaError_t _c = (call); if(_c != cudaSuccess) \
+  return fail(e, JFGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_c)); } while(0)
+
+TableDev table_dev(const jfgpu_engine* e, const Table& t) {
+  TableDev d;
+  memset(&d, 0, sizeof(d));
+  d.slots = t.slots.p;
+  d.local_mask = t.local_size - 1;
+  d.local_lsize = t.local_lsize;
+  d.lsize = t.lsize;
+  d.shard_index = e->p.shard_index;
+  d.kbits = 2 * e->k;
+  d.rbits = t.rbits;
+  d.fbits = t.fbits;
+  d.max_reprobe = t.max_reprobe;
+  d.ovf_keys = t.ovf_keys.as<unsigned long long>();
+  d.ovf_vals = t.ovf_vals.as<unsigned long long>();
+  d.ovf_mask = e->ovf_size - 1;
+  d.stats = e->stats.as<unsigned long long>();
+  d.fail_keys = e->fail_keys[e->fail_cur].as<uint64_t>();
+  d.fail_counts = e->fail_counts[e->fail_cur].as<uint64_t>();
+  d.fail_cap = e->fail_cap;
+  return d;
+}
+
+// Geometry of a table of 2^lsize GLOBAL slots -- large_hash_array.hpp:150-173,29-39.
+int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix& M) {
+  const unsigned kbits = 2 * e->k;
+  t.lsize = lsize;
+  t.size = (uint64_t)1 << lsize;
+  t.local_lsize = lsize - e->shard_bits;
+  t.local_size = (uint64_t)1 << t.local_lsize;
+  t.hb = kbits > lsize ? kbits - lsize : 0;
+  unsigned limit = kbits > lsize ? e->p.max_reprobe : 0;
+  // reprobes[0] = 1, reprobes[i] = i(i+1)/2 (lib/storage.cc:13-41); clip so that reprobes[limit] < size
+  auto rp = [](unsigned i) -> uint64_t { return i == 0 ? 1 : tri(i); };
+  while(limit >= 1 && rp(limit) >= t.size) --limit;
+  t.max_reprobe = limit;
+  t.reprobes.resize(limit + 1);
+  for(unsigned i = 0; i <= limit; ++i) t.reprobes[i] = rp(i);
+  t.rbits = bitsize(limit + 1);
+  t.fbits = t.hb + t.rbits;
+  if(t.fbits <= 24) t.slot_bits = 32;
+  else if(t.fbits <= 56) t.slot_bits = 64;
+  else if(t.fbits <= 120) t.slot_bits = 128;
+  else return fail(e, JFGPU_ERR_ARG, "key too long for this table size (key field > 120 bits)");
+  if(e->kw == 2 && t.slot_bits == 32) t.slot_bits = 64;
+  t.margin = limit ? tri(limit) : 0;
+  t.local_slots = t.local_size + t.margin + 8;
+  t.M = M;
+  t.Minv = M.pseudo_inverse();
+  if(cudaMalloc(&t.slots.p, t.bytes()) != cudaSuccess) {
+    cudaGetLastError();
+    t.slots.p = nullptr;
+    char buf[128]; snprintf(buf, sizeof(buf), "Failed to allocate %zu bytes of device memory", t.bytes());
+    return fail(e, JFGPU_ERR_NOMEM, buf);
+  }
+  t.slots.bytes = t.bytes();
+  CUDA_OK(e, cudaMemsetAsync(t.slots.p, 0, t.bytes(), e->cs));
+  CUDA_OK(e, t.ovf_keys.alloc(e->ovf_size * 8));
+  CUDA_OK(e, t.ovf_vals.alloc(e->ovf_size * 8));
+  CUDA_OK(e, cudaMemsetAsync(t.ovf_keys.p, 0, e->ovf_size * 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(t.ovf_vals.p, 0, e->ovf_size * 8, e->cs));
+  std::vector<uint64_t> l1 = build_lut(t.M, e->nbytes), l2 = build_lut(t.Minv, e->nbytes);
+  CUDA_OK(e, t.lut.alloc(l1.size() * 8));
+  CUDA_OK(e, t.inv_lut.alloc(l2.size() * 8));
+  CUDA_OK(e, cudaMemcpyAsync(t.lut.p, l1.data(), l1.size() * 8, cudaMemcpyHostToDevice, e->cs));
+  CUDA_OK(e, cudaMemcpyAsync(t.inv_lut.p, l2.data(), l2.size() * 8, cudaMemcpyHostToDevice, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));     // l1/l2 are about to go out of scope
+  return JFGPU_OK;
+}
+
+// The matrix large_hash::array draws for a table of 2^lsize slots (large_hash_array.hpp:992-1002)
+jfb::gf2_matrix draw_matrix(jfgpu_engine* e, uint64_t requested_size, unsigned lsize) {
+  const unsigned kbits = 2 * e->k;
+  const bool smaller = kbits >= 64 || requested_size < ((uint64_t)1 << kbits);
+  if(!smaller) return jfb::gf2_matrix::identity(kbits);
+  jfb::gf2_matrix m(lsize, kbits);
+  return m.randomize_pseudo_inverse(e->rng);
+}
+
+template<typename F>
+int dispatch(jfgpu_engine* e, unsigned kw, unsigned sb, F&& f) {
+  if(kw == 1 && sb == 32)  return f(std::integral_constant<int, 1>(), std::integral_constant<int, 32>());
+  if(kw == 1 && sb == 64)  return f(std::integral_constant<int, 1>(), std::integral_constant<int, 64>());
+  if(kw == 1 && sb == 128) return f(std::integral_constant<int, 1>(), std::integral_constant<int, 128>());
+  if(kw == 2 && sb == 64)  return f(std::integral_constant<int, 2>(), std::integral_constant<int, 64>());
+  if(kw == 2 && sb == 128) return f(std::integral_constant<int, 2>(), std::integral_constant<int, 128>());
+  return fail(e, JFGPU_ERR_ARG, "unsupported key/slot combination");
+}
+
+size_t count_smem_bytes(unsigned nbytes) { return ((sizeof(CountSmem) + 15) & ~(size_t)15) + (size_t)nbytes * 256 * 8; }
+
+int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
+  if(n_tiles <= e->scratch_tiles) return JFGPU_OK;
+  uint64_t want = std::max<uint64_t>(n_tiles, 1024);
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  CUDA_OK(e, e->nlA.alloc(want * 8));
+  CUDA_OK(e, e->nlB.alloc(want * 8));
+  CUDA_OK(e, e->tstate.alloc(want));
+  e->scratch_tiles = want;
+  return JFGPU_OK;
+}
+
+// One batch of device-resident text through K0a, K0b, K1 on `stream`.
+int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, cudaStream_t stream,
+              int mode, uint64_t* route_keys, unsigned long long* route_counts, uint64_t route_cap) {
+  if(n == 0) return JFGPU_OK;
+  const uint64_t n_tiles = (n + TILE - 1) / TILE;
+  int rc = ensure_scratch(e, n_tiles);
+  if(rc) return rc;
+  const int g0 = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 8);
+  nl_scan_kernel<<<g0, 256, 0, stream>>>(dev, n, n_tiles, e->nlA.as<long long>(), e->nlB.as<long long>());
+  JF_LAUNCHED();
+  tile_state_kernel<<<1, 1024, 0, stream>>>(dev, n_tiles, e->nlA.as<long long>(), e->nlB.as<long long>(),
+                                            e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
+  JF_LAUNCHED();
+  CountArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = dev; a.n = n; a.n_look = n_look; a.n_tiles = n_tiles;
+  a.tile_state = e->tstate.as<uint8_t>();
+  a.carry_in = e->carry[e->carry_cur].as<Carry>();
+  a.carry_out = e->carry[e->carry_cur ^ 1].as<Carry>();
+  a.lut = e->tab.lut.as<uint64_t>();
+  a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode;
+  a.T = table_dev(e, e->tab);
+  a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
+  const size_t smem = count_smem_bytes(e->nbytes);
+  const int ctas_per_sm = std::max(1, std::min(3, (int)(220 * 1024 / smem)));
+  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * ctas_per_sm);
+  rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
+    auto kern = count_kernel<decltype(KW)::value, decltype(SB)::value>;
+    cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(c));
+    kern<<<grid, NT, smem, stream>>>(a);
+    return JFGPU_OK;
+  });
+  if(rc) return rc;
+  JF_LAUNCHED();
+  CUDA_OK(e, cudaGetLastError());
+  e->carry_cur ^= 1;
+  return JFGPU_OK;
+}
+
+int reset_carry(jfgpu_engine* e, cudaStream_t stream) {
+  Carry c;
+  c.state = ST_L; c.pad = 0;
+  memset(c.sym, SYM_BREAK, sizeof(c.sym));
+  // (stream ordered; source is copied synchronously into the driver's staging for pageable memory)
+  CUDA_OK(e, cudaMemcpyAsync(e->carry[e->carry_cur].p, &c, sizeof(c), cudaMemcpyHostToDevice, stream));
+  CUDA_OK(e, cudaStreamSynchronize(stream));
+  return JFGPU_OK;
+}
+
+int read_stats(jfgpu_engine* e) {
+  CUDA_OK(e, cudaMemcpyAsync(e->h_stats, e->stats.p, STAT_N * 8, cudaMemcpyDeviceToHost, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  return JFGPU_OK;
+}
+
+int insert_keys_into(jfgpu_engine* e, Table& t, const uint64_t* keys, const uint64_t* counts, uint64_t n, cudaStream_t stream) {
+  if(n == 0) return JFGPU_OK;
+  TableDev T = table_dev(e, t);
+  const size_t smem = (size_t)e->nbytes * 256 * 8;
+  const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)e->n_sm * 8);
+  int rc = dispatch(e, e->kw, t.slot_bits, [&](auto KW, auto SB) -> int {
+    auto kern = insert_keys_kernel<decltype(KW)::value, decltype(SB)::value>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, stream>>>(T, t.lut.as<uint64_t>(), e->nbytes, keys, counts, n);
+    return JFGPU_OK;
+  });
+  if(rc) return rc;
+  JF_LAUNCHED();
+  CUDA_OK(e, cudaGetLastError());
+  return JFGPU_OK;
+}
+
+struct SegScratch {
+  DevBuf keys, counts, sort_lo, sort_lo2, sort_hi, sort_hi2, perm, perm2, n_out, cub_tmp, bytes;
+  uint64_t cap = 0;
+  size_t cub_bytes = 0;
+  void free_all() { keys.free(); counts.free(); sort_lo.free(); sort_lo2.free(); sort_hi.free(); sort_hi2.free();
+                    perm.free(); perm2.free(); n_out.free(); cub_tmp.free(); bytes.free(); cap = 0; }
+};
+
+int seg_alloc(jfgpu_engine* e, SegScratch& s, uint64_t cap, bool want_sort, unsigned rec_bytes) {
+  s.cap = cap;
+  CUDA_OK(e, s.keys.alloc(cap * 8 * e->kw));
+  CUDA_OK(e, s.counts.alloc(cap * 8));
+  CUDA_OK(e, s.n_out.alloc(8));
+  CUDA_OK(e, s.sort_lo.alloc(cap * 8));
+  if(want_sort) {
+    CUDA_OK(e, s.sort_lo2.alloc(cap * 8));
+    CUDA_OK(e, s.perm.alloc(cap * 4));
+    CUDA_OK(e, s.perm2.alloc(cap * 4));
+    if(e->kw == 2) { CUDA_OK(e, s.sort_hi.alloc(cap * 8)); CUDA_OK(e, s.sort_hi2.alloc(cap * 8)); }
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)cap, 0, 64, e->cs);
+    s.cub_bytes = tmp;
+    CUDA_OK(e, s.cub_tmp.alloc(tmp));
+    CUDA_OK(e, s.bytes.alloc(cap * rec_bytes + 16));
+  }
+  return JFGPU_OK;
+}
+
+// Collect the records of local original positions [lo, hi) of table t; returns their number.
+int collect_segment(jfgpu_engine* e, Table& t, SegScratch& s, uint64_t lo, uint64_t hi, uint64_t lower, uint64_t upper,
+                    bool want_sort, uint64_t* n_rec) {
+  CollectArgs a;
+  memset(&a, 0, sizeof(a));
+  a.T = table_dev(e, t);
+  a.inv_lut = t.inv_lut.as<uint64_t>();
+  a.nbytes = e->nbytes;
+  a.seg_lo = lo; a.seg_hi = hi;
+  a.scan_hi = std::min<uint64_t>(hi + t.margin, t.local_size + t.margin);
+  a.lower = lower; a.upper = upper;
+  a.hb = t.hb;
+  a.out_keys = s.keys.as<uint64_t>(); a.out_counts = s.counts.as<uint64_t>();
+  a.out_sort_lo = s.sort_lo.as<uint64_t>();
+  a.out_sort_hi = (want_sort && e->kw == 2) ? s.sort_hi.as<uint64_t>() : nullptr;
+  a.out_n = s.n_out.as<unsigned long long>();
+  a.out_cap = s.cap;
+  CUDA_OK(e, cudaMemsetAsync(s.n_out.p, 0, 8, e->cs));
+  const size_t smem = (size_t)e->nbytes * 256 * 8;
+  const uint64_t span = a.scan_hi - a.seg_lo;
+  const int grid = (int)std::min<uint64_t>((span + 255) / 256, (uint64_t)e->n_sm * 16);
+  int rc = dispatch(e, e->kw, t.slot_bits, [&](auto KW, auto SB) -> int {
+    auto kern = collect_kernel<decltype(KW)::value, decltype(SB)::value>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, e->cs>>>(a);
+    return JFGPU_OK;
+  });
+  if(rc) return rc;
+  JF_LAUNCHED();
+  unsigned long long n = 0;
+  CUDA_OK(e, cudaMemcpyAsync(&n, s.n_out.p, 8, cudaMemcpyDeviceToHost, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  if(n > s.cap) return fail(e, JFGPU_ERR_STATE, "internal: segment overflow in collect");
+  *n_rec = n;
+  return JFGPU_OK;
+}
+
+uint64_t pick_segment(const Table& t) {
+  uint64_t seg = std::min<uint64_t>(t.local_size, (uint64_t)1 << 24);
+  return seg;
+}
+
+// hash_counter::double_size (hash_counter.hpp:200-238): allocate a table twice as large with a
+// freshly drawn matrix, re-insert every (key, count) of the old one, then the keys that failed.
+int regrow(jfgpu_engine* e) {
+  for(;;) {
+    int rc = read_stats(e);
+    if(rc) return rc;
+    if(e->h_stats[STAT_OVF_FULL]) return fail(e, JFGPU_ERR_FULL, "counter overflow side table is full");
+    const uint64_t n_failed = e->h_stats[STAT_FAILED];
+    if(n_failed == 0) return JFGPU_OK;
+    if(e->h_stats[STAT_FAIL_DROPPED]) return fail(e, JFGPU_ERR_FULL, "Hash full (too many keys failed before the table could be doubled)");
+    if(!e->p.allow_regrow || e->shard_bits) return fail(e, JFGPU_ERR_FULL, "Hash full");
+    const unsigned kbits = 2 * e->k;
+    if(kbits < 64 && e->tab.size >= ((uint64_t)1 << kbits)) return fail(e, JFGPU_ERR_FULL, "Hash full");
+    // new table
+    Table nt;
+    const unsigned nl = e->tab.lsize + 1;
+    jfb::gf2_matrix M = draw_matrix(e, (uint64_t)1 << nl, nl);
+    // switch the failure list so that failures of the re-insertion are kept apart
+    const int old_fail = e->fail_cur;
+    e->fail_cur ^= 1;
+    if(!e->fail_keys[e->fail_cur].p) {
+      CUDA_OK(e, e->fail_keys[e->fail_cur].alloc(e->fail_cap * 8 * e->kw));
+      CUDA_OK(e, e->fail_counts[e->fail_cur].alloc(e->fail_cap * 8));
+    }
+    CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_FAILED, 0, 8, e->cs));
+    rc = table_setup(e, nt, nl, M);
+    if(rc) return rc == JFGPU_ERR_NOMEM ? fail(e, JFGPU_ERR_FULL, "Hash full (" + e->err + ")") : rc;
+    // distinct / reprobes statistics restart for the new table
+    CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_DISTINCT, 0, 8, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_REPROBES, 0, 8, e->cs));
+    const uint64_t inserted_before = e->h_stats[STAT_INSERTED];
+    SegScratch s;
+    const uint64_t seg = pick_segment(e->tab);
+    rc = seg_alloc(e, s, seg, false, 0);
+    if(rc) { s.free_all(); return rc; }
+    for(uint64_t lo = 0; lo < e->tab.local_size && !rc; lo += seg) {
+      uint64_t n = 0;
+      rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, false, &n);
+      if(!rc) rc = insert_keys_into(e, nt, s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), n, e->cs);
+    }
+    if(!rc) rc = insert_keys_into(e, nt, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
+    cudaStreamSynchronize(e->cs);
+    s.free_all();
+    if(rc) return rc;
+    // (each table owns its counter-carry side table: the old one dies with the old slots)
+    e->tab.release();
+    e->tab = nt;
+    // STAT_INSERTED counts k-mer occurrences; the re-insertion must not change it
+    CUDA_OK(e, cudaMemcpyAsync(e->stats.as<unsigned long long>() + STAT_INSERTED, &inserted_before, 8, cudaMemcpyHostToDevice, e->cs));
+    CUDA_OK(e, cudaStreamSynchronize(e->cs));
+    e->regrows++;
+  }
+}
+
+int check_after_batches(jfgpu_engine* e) {
+  int rc = read_stats(e);
+  if(rc) return rc;
+  if(e->h_stats[STAT_OVF_FULL]) return fail(e, JFGPU_ERR_FULL, "counter overflow side table is full");
+  if(e->h_stats[STAT_FAILED]) return regrow(e);
+  return JFGPU_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+const char* jfgpu_version(void) { return "jellyfish-b200 0.1 (sm_100a)"; }
+uint64_t jfgpu_kernel_launches(void) { return g_launches.load(); }
+const char* jfgpu_last_error(jfgpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void* jfgpu_host_alloc(size_t bytes) { void* p = nullptr; if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void jfgpu_host_free(void* p) { if(p) cudaFreeHost(p); }
+
+int jfgpu_reference_matrix(uint32_t r, uint32_t c, uint32_t skip, uint64_t* cols) {
+  if(r == 0 || r > 64 || c == 0 || !cols) return JFGPU_ERR_ARG;
+  jfb::glibc_random rng;
+  jfb::gf2_matrix res;
+  for(uint32_t i = 0; i <= skip; ++i) { jfb::gf2_matrix m(r, c); res = m.randomize_pseudo_inverse(rng); }
+  for(uint32_t i = 0; i < c; ++i) cols[i] = res[i];
+  return JFGPU_OK;
+}
+
+int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
+  if(!params || !out) return fail(nullptr, JFGPU_ERR_ARG, "null argument");
+  if(params->struct_size != sizeof(jfgpu_params)) return fail(nullptr, JFGPU_ERR_ARG, "jfgpu_params size mismatch");
+  if(params->k < 1 || params->k > 64) return fail(nullptr, JFGPU_ERR_ARG, "mer length must be in [1, 64]");
+  if(params->size == 0) return fail(nullptr, JFGPU_ERR_ARG, "size must be positive");
+  uint32_t ns = params->n_shards ? params->n_shards : 1;
+  if(ns & (ns - 1)) return fail(nullptr, JFGPU_ERR_ARG, "n_shards must be a power of two");
+  if(params->shard_index >= ns) return fail(nullptr, JFGPU_ERR_ARG, "shard_index out of range");
+  if(params->max_reprobe > 255) return fail(nullptr, JFGPU_ERR_ARG, "max_reprobe must be <= 255");
+
+  int ndev = 0;
+  if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, JFGPU_ERR_CUDA, "no CUDA device: the jellyfish-b200 engine has no CPU fallback");
+  }
+  if(params->device < 0 || params->device >= ndev) return fail(nullptr, JFGPU_ERR_ARG, "invalid device ordinal");
+
+  jfgpu_engine* e = new jfgpu_engine;
+  e->p = *params;
+  e->p.n_shards = ns;
+  e->device = params->device;
+  e->k = params->k;
+  e->kw = params->k > 32 ? 2 : 1;
+  e->nbytes = (2 * params->k + 7) / 8;
+  e->shard_bits = ceil_log2(ns);
+  auto bail = [&](int code) { g_create_error = e->err; jfgpu_destroy(e); return code; };
+
+  cudaError_t c;
+  if((c = cudaSetDevice(e->device)) != cudaSuccess) { e->err = cudaGetErrorString(c); return bail(JFGPU_ERR_CUDA); }
+  cudaDeviceProp prop;
+  if((c = cudaGetDeviceProperties(&prop, e->device)) != cudaSuccess) { e->err = cudaGetErrorString(c); return bail(JFGPU_ERR_CUDA); }
+  if(prop.major < 10) { e->err = "this engine is built for sm_100a (Blackwell) only"; return bail(JFGPU_ERR_CUDA); }
+  e->n_sm = prop.multiProcessorCount;
+  if(cudaStreamCreateWithFlags(&e->cs, cudaStreamNonBlocking) != cudaSuccess ||
+     cudaStreamCreateWithFlags(&e->hs, cudaStreamNonBlocking) != cudaSuccess) { e->err = "stream creation failed"; return bail(JFGPU_ERR_CUDA); }
+  cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
+  for(int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming); }
+
+  // table geometry: size rounded up to a power of two, clipped to 4^k (large_hash_array.hpp:992-1002,150-153)
+  const unsigned kbits = 2 * e->k;
+  uint64_t req = params->size;
+  if(kbits < 64 && req > ((uint64_t)1 << kbits)) req = (uint64_t)1 << kbits;
+  const unsigned lsize = ceil_log2(req);
+  if(lsize < e->shard_bits) { e->err = "table smaller than the number of shards"; return bail(JFGPU_ERR_ARG); }
+  for(uint32_t i = 0; i < params->matrix_skip; ++i) (void)draw_matrix(e, params->size, lsize);
+  jfb::gf2_matrix M = draw_matrix(e, params->size, lsize);
+
+  // side structures
+  e->ovf_size = (uint64_t)1 << 20;
+  e->batch_bytes = params->max_batch_bytes ? (size_t)((params->max_batch_bytes + 15) & ~(uint64_t)15) : ((size_t)64 << 20);
+  e->fail_cap = params->allow_regrow ? 2 * (uint64_t)e->batch_bytes : ((uint64_t)1 << 16);
+  bool ok = e->stats.alloc(STAT_N * 8) == cudaSuccess && e->carry[0].alloc(sizeof(Carry)) == cudaSuccess &&
+            e->carry[1].alloc(sizeof(Carry)) == cudaSuccess &&
+            e->fail_keys[0].alloc(e->fail_cap * 8 * e->kw) == cudaSuccess && e->fail_counts[0].alloc(e->fail_cap * 8) == cudaSuccess &&
+            cudaHostAlloc((void**)&e->h_stats, STAT_N * 8, cudaHostAllocDefault) == cudaSuccess;
+  if(!ok) { cudaGetLastError(); e->err = "device allocation failed"; return bail(JFGPU_ERR_NOMEM); }
+  cudaMemsetAsync(e->stats.p, 0, STAT_N * 8, e->cs);
+  memset(e->h_stats, 0, STAT_N * 8);
+  int rc = table_setup(e, e->tab, lsize, M);
+  if(rc) return bail(rc);
+  rc = reset_carry(e, e->cs);
+  if(rc) return bail(rc);
+  *out = e;
+  return JFGPU_OK;
+}
+
+void jfgpu_destroy(jfgpu_handle e) {
+  if(!e) return;
+  cudaSetDevice(e->device);
+  if(e->cs) cudaStreamSynchronize(e->cs);
+  if(e->hs) cudaStreamSynchronize(e->hs);
+  e->tab.release();
+  e->stats.free();
+  for(int i = 0; i < 2; ++i) {
+    e->carry[i].free(); e->fail_keys[i].free(); e->fail_counts[i].free(); e->stage[i].free();
+    if(e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    if(e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+  }
+  e->nlA.free(); e->nlB.free(); e->tstate.free();
+  if(e->h_stats) cudaFreeHost(e->h_stats);
+  if(e->ev_t0) cudaEventDestroy(e->ev_t0);
+  if(e->ev_t1) cudaEventDestroy(e->ev_t1);
+  if(e->cs) cudaStreamDestroy(e->cs);
+  if(e->hs) cudaStreamDestroy(e->hs);
+  delete e;
+}
+
+static int begin_feed(jfgpu_engine* e, uint32_t flags, int first_byte, cudaStream_t st) {
+  if(flags & JFGPU_FILE_BEGIN) {
+    // mer_overlap_sequence_parser.hpp:134-148: the first byte selects the format
+    if(first_byte >= 0 && first_byte != '>') {
+      if(first_byte == '@') return fail(e, JFGPU_ERR_FORMAT, "FASTQ input is not supported by the device parser yet");
+      return fail(e, JFGPU_ERR_FORMAT, "Unsupported format");
+    }
+    int rc = reset_carry(e, st);
+    if(rc) return rc;
+    e->in_file = true;
+  }
+  return JFGPU_OK;
+}
+
+static int end_feed(jfgpu_engine* e, uint32_t flags, cudaStream_t st) {
+  if(flags & JFGPU_FILE_END) {
+    // no k-mer spans two files: mer_overlap_sequence_parser.hpp:111
+    int rc = reset_carry(e, st);
+    if(rc) return rc;
+    e->in_file = false;
+  }
+  return JFGPU_OK;
+}
+
+int jfgpu_feed_device(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t flags, void* stream) {
+  if(!e) return JFGPU_ERR_ARG;
+  if(((uintptr_t)dev_bytes & 15) != 0) return fail(e, JFGPU_ERR_ARG, "device text must be 16-byte aligned");
+  cudaSetDevice(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  int first = -1;
+  if((flags & JFGPU_FILE_BEGIN) && n) {
+    unsigned char b = 0;
+    CUDA_OK(e, cudaMemcpyAsync(&b, dev_bytes, 1, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(e, cudaStreamSynchronize(st));
+    first = b;
+  }
+  int rc = begin_feed(e, flags, first, st);
+  if(rc) return rc;
+  const uint8_t* p = (const uint8_t*)dev_bytes;
+  cudaEventRecord(e->ev_t0, st);
+  for(size_t off = 0; off < n; ) {
+    size_t len = std::min(e->batch_bytes, n - off);
+    rc = run_batch(e, p + off, len, n - off, st, 0, nullptr, nullptr, 0);
+    if(rc) return rc;
+    off += len;
+    if(e->p.allow_regrow) {          // the failure list only holds two batches
+      if(st != e->cs) CUDA_OK(e, cudaStreamSynchronize(st));
+      rc = check_after_batches(e);
+      if(rc) return rc;
+    }
+  }
+  cudaEventRecord(e->ev_t1, st);
+  CUDA_OK(e, cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms;
+  e->bytes_fed += n;
+  return end_feed(e, flags, st);
+}
+
+int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
+  if(!e) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  int rc = begin_feed(e, flags, n ? (unsigned char)bytes[0] : -1, e->cs);
+  if(rc) return rc;
+  for(int i = 0; i < 2; ++i) if(!e->stage[i].p) CUDA_OK(e, e->stage[i].alloc(e->batch_bytes + 64));
+  cudaEventRecord(e->ev_t0, e->cs);
+  size_t off = 0;
+  while(off < n) {
+    size_t len = std::min(e->batch_bytes, n - off);
+    // never end a chunk on '\r' unless it is the end of the data: the device looks one byte ahead
+    if(off + len < n) { size_t l2 = len; while(l2 > 1 && bytes[off + l2 - 1] == '\r') --l2; if(l2 > 1) len = l2; }
+    const int s = e->stage_cur;
+    // the previous batch that used this staging buffer must be done before it is overwritten
+    CUDA_OK(e, cudaEventSynchronize(e->ev_done[s]));
+    if(e->p.allow_regrow) {
+      // peek at the live failure counter without draining the compute stream
+      CUDA_OK(e, cudaMemcpyAsync(e->h_stats + STAT_FAILED, e->stats.as<unsigned long long>() + STAT_FAILED, 8, cudaMemcpyDeviceToHost, e->hs));
+      CUDA_OK(e, cudaStreamSynchronize(e->hs));
+      if(e->h_stats[STAT_FAILED]) { rc = check_after_batches(e); if(rc) return rc; }
+    }
+    CUDA_OK(e, cudaMemcpyAsync(e->stage[s].p, bytes + off, len, cudaMemcpyHostToDevice, e->hs));
+    CUDA_OK(e, cudaEventRecord(e->ev_copied[s], e->hs));
+    CUDA_OK(e, cudaStreamWaitEvent(e->cs, e->ev_copied[s], 0));
+    rc = run_batch(e, e->stage[s].as<uint8_t>(), len, len, e->cs, 0, nullptr, nullptr, 0);
+    if(rc) return rc;
+    CUDA_OK(e, cudaEventRecord(e->ev_done[s], e->cs));
+    e->stage_cur ^= 1;
+    off += len;
+  }
+  cudaEventRecord(e->ev_t1, e->cs);
+  e->bytes_fed += n;
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms; }
+  rc = check_after_batches(e);
+  if(rc) return rc;
+  return end_feed(e, flags, e->cs);
+}
+
+int jfgpu_extract_route(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t flags, void* dev_keys, uint64_t capacity,
+                        uint64_t* dev_counts, void* stream) {
+  if(!e) return JFGPU_ERR_ARG;
+  if(((uintptr_t)dev_bytes & 15) != 0) return fail(e, JFGPU_ERR_ARG, "device text must be 16-byte aligned");
+  cudaSetDevice(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  int first = -1;
+  if((flags & JFGPU_FILE_BEGIN) && n) {
+    unsigned char b = 0;
+    CUDA_OK(e, cudaMemcpyAsync(&b, dev_bytes, 1, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(e, cudaStreamSynchronize(st));
+    first = b;
+  }
+  int rc = begin_feed(e, flags, first, st);
+  if(rc) return rc;
+  const uint8_t* p = (const uint8_t*)dev_bytes;
+  for(size_t off = 0; off < n; ) {
+    size_t len = std::min(e->batch_bytes, n - off);
+    rc = run_batch(e, p + off, len, n - off, st, 1, (uint64_t*)dev_keys, (unsigned long long*)dev_counts, capacity);
+    if(rc) return rc;
+    off += len;
+  }
+  e->bytes_fed += n;
+  CUDA_OK(e, cudaStreamSynchronize(st));
+  rc = end_feed(e, flags, st);
+  if(rc) return rc;
+  rc = read_stats(e);
+  if(rc) return rc;
+  if(e->h_stats[STAT_ROUTE_DROPPED]) return fail(e, JFGPU_ERR_FULL, "route bucket capacity exceeded");
+  return JFGPU_OK;
+}
+
+int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* stream) {
+  if(!e) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  cudaEventRecord(e->ev_t0, st);
+  int rc = insert_keys_into(e, e->tab, (const uint64_t*)dev_keys, nullptr, n, st);
+  if(rc) return rc;
+  cudaEventRecord(e->ev_t1, st);
+  CUDA_OK(e, cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms;
+  return JFGPU_OK;
+}
+
+int jfgpu_get_stats(jfgpu_handle e, jfgpu_stats* s) {
+  if(!e || !s) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  int rc = read_stats(e);
+  if(rc) return rc;
+  s->kmers = e->h_stats[STAT_KMERS];
+  s->inserted = e->h_stats[STAT_INSERTED];
+  s->distinct = e->h_stats[STAT_DISTINCT];
+  s->reprobes = e->h_stats[STAT_REPROBES];
+  s->overflowed = e->h_stats[STAT_OVERFLOWED];
+  s->regrows = e->regrows;
+  s->bytes = e->bytes_fed;
+  s->seconds_count = e->count_ms * 1e-3;
+  return JFGPU_OK;
+}
+
+int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
+  if(!e) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  CUDA_OK(e, cudaStreamSynchronize(e->hs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  CUDA_OK(e, cudaGetLastError());
+  int rc = check_after_batches(e);
+  if(rc) return rc;
+  if(s) return jfgpu_get_stats(e, s);
+  return JFGPU_OK;
+}
+
+int jfgpu_table_info_get(jfgpu_handle e, jfgpu_table_info* info) {
+  if(!e || !info) return JFGPU_ERR_ARG;
+  const Table& t = e->tab;
+  info->size = t.size; info->lsize = t.lsize; info->key_len = 2 * e->k; info->val_len = e->p.counter_len;
+  info->max_reprobe = t.max_reprobe; info->matrix_r = t.M.r(); info->matrix_c = t.M.c();
+  info->matrix_identity = t.M.is_low_identity() ? 1 : 0;
+  info->slot_bits = t.slot_bits; info->local_slots = t.local_slots; info->table_bytes = t.bytes();
+  e->matrix_cols_host.assign(t.M.c(), 0);
+  for(unsigned i = 0; i < t.M.c(); ++i) e->matrix_cols_host[i] = t.M[i];
+  info->matrix_columns = t.M.is_identity() ? nullptr : e->matrix_cols_host.data();
+  info->reprobes = t.reprobes.data();
+  return JFGPU_OK;
+}
+
+int jfgpu_dump(jfgpu_handle e, uint64_t lower, uint64_t upper, uint32_t ocl, jfgpu_sink_fn sink, void* ctx, uint64_t* n_records) {
+  if(!e || !sink) return JFGPU_ERR_ARG;
+  if(ocl < 1 || ocl > 8) return fail(e, JFGPU_ERR_ARG, "out_counter_len must be in [1, 8]");
+  cudaSetDevice(e->device);
+  int rc = jfgpu_finish(e, nullptr);
+  if(rc) return rc;
+  Table& t = e->tab;
+  const unsigned key_bytes = e->nbytes, rec = key_bytes + ocl;
+  const uint64_t seg = pick_segment(t);
+  SegScratch s;
+  rc = seg_alloc(e, s, seg, true, rec);
+  uint8_t* hbuf = nullptr;
+  if(!rc && cudaHostAlloc((void**)&hbuf, seg * rec + 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "pinned host allocation failed"); }
+  uint64_t total = 0;
+  const uint64_t relbits = ceil_log2(seg);
+  for(uint64_t lo = 0; lo < t.local_size && !rc; lo += seg) {
+    uint64_t n = 0;
+    rc = collect_segment(e, t, s, lo, std::min(lo + seg, t.local_size), lower, upper, true, &n);
+    if(rc || n == 0) continue;
+    const int g = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)e->n_sm * 8);
+    iota_u32_kernel<<<g, 256, 0, e->cs>>>(s.perm.as<uint32_t>(), n); JF_LAUNCHED();
+    size_t tmp = s.cub_bytes;
+    const uint32_t* perm_final = nullptr;
+    const unsigned total_bits = (unsigned)relbits + t.hb;
+    if(e->kw == 1 || total_bits <= 64) {
+      cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tmp, s.sort_lo.as<uint64_t>(), s.sort_lo2.as<uint64_t>(),
+                                      s.perm.as<uint32_t>(), s.perm2.as<uint32_t>(), (int64_t)n, 0, (int)std::max(1u, std::min(64u, total_bits)), e->cs);
+      JF_LAUNCHED();
+      perm_final = s.perm2.as<uint32_t>();
+    } else {
+      // 128-bit key: LSD in two stable passes, low word then high word
+      cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tmp, s.sort_lo.as<uint64_t>(), s.sort_lo2.as<uint64_t>(),
+                                      s.perm.as<uint32_t>(), s.perm2.as<uint32_t>(), (int64_t)n, 0, 64, e->cs);
+      JF_LAUNCHED();
+      gather_u64_kernel<<<g, 256, 0, e->cs>>>(s.sort_hi.as<uint64_t>(), s.perm2.as<uint32_t>(), s.sort_hi2.as<uint64_t>(), n); JF_LAUNCHED();
+      tmp = s.cub_bytes;
+      cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tmp, s.sort_hi2.as<uint64_t>(), s.sort_hi.as<uint64_t>(),
+                                      s.perm2.as<uint32_t>(), s.perm.as<uint32_t>(), (int64_t)n, 0, (int)std::max(1u, total_bits - 64), e->cs);
+      JF_LAUNCHED();
+      perm_final = s.perm.as<uint32_t>();
+    }
+    const size_t smem = (size_t)256 * rec;
+    if(e->kw == 1) serialize_kernel<1><<<g, 256, smem, e->cs>>>(s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), perm_final, n, key_bytes, ocl, s.bytes.as<uint8_t>());
+    else           serialize_kernel<2><<<g, 256, smem, e->cs>>>(s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), perm_final, n, key_bytes, ocl, s.bytes.as<uint8_t>());
+    JF_LAUNCHED();
+    cudaError_t c = cudaMemcpyAsync(hbuf, s.bytes.p, n * rec, cudaMemcpyDeviceToHost, e->cs);
+    if(c == cudaSuccess) c = cudaStreamSynchronize(e->cs);
+    if(c != cudaSuccess) { rc = fail(e, JFGPU_ERR_CUDA, std::string("dump: ") + cudaGetErrorString(c)); break; }
+    if(sink(ctx, hbuf, n * rec) != 0) { rc = fail(e, JFGPU_ERR_SINK, "dump sink failed"); break; }
+    total += n;
+  }
+  if(hbuf) cudaFreeHost(hbuf);
+  s.free_all();
+  if(n_records) *n_records = total;
+  return rc;
+}
+
+int jfgpu_lookup(jfgpu_handle e, const uint64_t* keys, size_t n, uint64_t* vals) {
+  if(!e || (n && (!keys || !vals))) return JFGPU_ERR_ARG;
+  if(n == 0) return JFGPU_OK;
+  cudaSetDevice(e->device);
+  DevBuf dk, dv;
+  CUDA_OK(e, dk.alloc(n * 8 * e->kw));
+  CUDA_OK(e, dv.alloc(n * 8));
+  CUDA_OK(e, cudaMemcpyAsync(dk.p, keys, n * 8 * e->kw, cudaMemcpyHostToDevice, e->cs));
+  TableDev T = table_dev(e, e->tab);
+  const size_t smem = (size_t)e->nbytes * 256 * 8;
+  const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)e->n_sm * 8);
+  int rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
+    auto kern = lookup_kernel<decltype(KW)::value, decltype(SB)::value>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, e->cs>>>(T, e->tab.lut.as<uint64_t>(), e->nbytes, dk.as<uint64_t>(), n, dv.as<uint64_t>(), e->shard_bits);
+    return JFGPU_OK;
+  });
+  if(!rc) { JF_LAUNCHED();
+    cudaError_t c = cudaMemcpyAsync(vals, dv.p, n * 8, cudaMemcpyDeviceToHost, e->cs);
+    if(c == cudaSuccess) c = cudaStreamSynchronize(e->cs);
+    if(c != cudaSuccess) rc = fail(e, JFGPU_ERR_CUDA, std::string("lookup: ") + cudaGetErrorString(c));
+  }
+  dk.free(); dv.free();
+  return rc;
+}
+
+int jfgpu_histogram(jfgpu_handle e, uint64_t* hist, uint32_t n_bins) {
+  if(!e || !hist || n_bins == 0) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  int rc = jfgpu_finish(e, nullptr);
+  if(rc) return rc;
+  DevBuf dh;
+  CUDA_OK(e, dh.alloc((size_t)n_bins * 8));
+  CUDA_OK(e, cudaMemsetAsync(dh.p, 0, (size_t)n_bins * 8, e->cs));
+  TableDev T = table_dev(e, e->tab);
+  const uint64_t ns = e->tab.local_size + e->tab.margin;
+  const int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 16);
+  switch(e->tab.slot_bits) {
+  case 32:  histogram_kernel<32><<<grid, 256, 0, e->cs>>>(T, ns, dh.as<unsigned long long>(), n_bins); break;
+  case 64:  histogram_kernel<64><<<grid, 256, 0, e->cs>>>(T, ns, dh.as<unsigned long long>(), n_bins); break;
+  default:  histogram_kernel<128><<<grid, 256, 0, e->cs>>>(T, ns, dh.as<unsigned long long>(), n_bins); break;
+  }
+  JF_LAUNCHED();
+  cudaError_t c = cudaMemcpyAsync(hist, dh.p, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, e->cs);
+  if(c == cudaSuccess) c = cudaStreamSynchronize(e->cs);
+  dh.free();
+  if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("histogram: ") + cudaGetErrorString(c));
+  return JFGPU_OK;
+}
+
+uint64_t jfgpu_synth_fasta_bytes(uint64_t n_bases) {
+  return SYNTH_HDR + n_bases + (n_bases + SYNTH_LINE - 1) / SYNTH_LINE;
+}
+
+int jfgpu_synth_fasta_device(int device, void* dev_out, uint64_t capacity, uint64_t n_bases, uint64_t seed, uint64_t* n_bytes, void* stream) {
+  const uint64_t need = jfgpu_synth_fasta_bytes(n_bases);
+  if(!dev_out || capacity < need) return JFGPU_ERR_ARG;
+  if(cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return JFGPU_ERR_CUDA; }
+  const int grid = (int)std::min<uint64_t>((need + 255) / 256, (uint64_t)148 * 32);
+  synth_fasta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint8_t*)dev_out, need, n_bases, seed);
+  JF_LAUNCHED();
+  if(cudaGetLastError() != cudaSuccess) return JFGPU_ERR_CUDA;
+  if(n_bytes) *n_bytes = need;
+  return JFGPU_OK;
+}
+
+}  // extern "C"
