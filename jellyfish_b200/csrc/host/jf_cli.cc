@@ -585,9 +585,10 @@ int merge_main(int argc, char* argv[]) {
   oh.fill_standard();
   oh.set_cmdline(argc, argv);
   const jfb::file_header& h0 = dbs[0].header;
-  oh.size(h0.size()); oh.key_len(h0.key_len()); oh.val_len(h0.val_len()); oh.matrix(h0.matrix(1));
+  // exactly the keys merge_files() sets (merge_files.cc:125-138,160-165): no val_len, no canonical
+  oh.size(h0.size()); oh.key_len(h0.key_len()); oh.matrix(h0.matrix(1));
   oh.max_reprobe(h0.max_reprobe()); { std::vector<uint64_t> r = h0.reprobes(); oh.set_reprobes(r.data()); }
-  oh.format("binary/sorted"); oh.counter_len(h0.counter_len()); oh.canonical(h0.canonical());
+  oh.format("binary/sorted"); oh.counter_len(h0.counter_len());
   std::ofstream out(output, std::ios::binary);
   if(!out.good()) die(std::string("Can't open out file '") + output + "'");
   oh.write(out);

@@ -91,6 +91,7 @@ struct jfgpu_engine {
   bool in_file = false;
   uint64_t bytes_fed = 0, regrows = 0;
   double count_ms = 0;
+  unsigned eff_val_len = 7;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   std::string err;
   std::vector<uint64_t> matrix_cols_host;   // for jfgpu_table_info_get
@@ -231,12 +232,14 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   a.T = table_dev(e, e->tab);
   a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
   const size_t smem = count_smem_bytes(e->nbytes);
-  const int ctas_per_sm = std::max(1, std::min(3, (int)(220 * 1024 / smem)));
-  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * ctas_per_sm);
   rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
     auto kern = count_kernel<decltype(KW)::value, decltype(SB)::value>;
     cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(c));
+    // persistent CTAs: exactly as many as are resident at once (a multiple of the SM count)
+    int per_sm = 1;
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * per_sm);
     kern<<<grid, NT, smem, stream>>>(a);
     return JFGPU_OK;
   });
@@ -351,6 +354,40 @@ uint64_t pick_segment(const Table& t) {
   return seg;
 }
 
+// Move every (key, count) of the current table, plus `n_failed` entries of failure list
+// `old_fail`, into a fresh table of 2^nl global slots hashed with M.
+int rebuild_table(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int old_fail, uint64_t n_failed) {
+  Table nt;
+  int rc = table_setup(e, nt, nl, M);
+  if(rc) { nt.release(); return rc == JFGPU_ERR_NOMEM ? fail(e, JFGPU_ERR_FULL, "Hash full (" + e->err + ")") : rc; }
+  // distinct / reprobes statistics restart for the new table; STAT_INSERTED counts k-mer
+  // occurrences and must not change
+  unsigned long long inserted_before = 0;
+  CUDA_OK(e, cudaMemcpyAsync(&inserted_before, e->stats.as<unsigned long long>() + STAT_INSERTED, 8, cudaMemcpyDeviceToHost, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_DISTINCT, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_REPROBES, 0, 8, e->cs));
+  SegScratch s;
+  const uint64_t seg = pick_segment(e->tab);
+  rc = seg_alloc(e, s, seg, false, 0);
+  for(uint64_t lo = 0; lo < e->tab.local_size && !rc; lo += seg) {
+    uint64_t n = 0;
+    rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, false, &n);
+    if(!rc) rc = insert_keys_into(e, nt, s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), n, e->cs);
+  }
+  if(!rc && n_failed)
+    rc = insert_keys_into(e, nt, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
+  cudaStreamSynchronize(e->cs);
+  s.free_all();
+  if(rc) { nt.release(); return rc; }
+  // (each table owns its counter-carry side table: the old one dies with the old slots)
+  e->tab.release();
+  e->tab = nt;
+  CUDA_OK(e, cudaMemcpyAsync(e->stats.as<unsigned long long>() + STAT_INSERTED, &inserted_before, 8, cudaMemcpyHostToDevice, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  return JFGPU_OK;
+}
+
 // hash_counter::double_size (hash_counter.hpp:200-238): allocate a table twice as large with a
 // freshly drawn matrix, re-insert every (key, count) of the old one, then the keys that failed.
 int regrow(jfgpu_engine* e) {
@@ -364,8 +401,6 @@ int regrow(jfgpu_engine* e) {
     if(!e->p.allow_regrow || e->shard_bits) return fail(e, JFGPU_ERR_FULL, "Hash full");
     const unsigned kbits = 2 * e->k;
     if(kbits < 64 && e->tab.size >= ((uint64_t)1 << kbits)) return fail(e, JFGPU_ERR_FULL, "Hash full");
-    // new table
-    Table nt;
     const unsigned nl = e->tab.lsize + 1;
     jfb::gf2_matrix M = draw_matrix(e, (uint64_t)1 << nl, nl);
     // switch the failure list so that failures of the re-insertion are kept apart
@@ -376,33 +411,41 @@ int regrow(jfgpu_engine* e) {
       CUDA_OK(e, e->fail_counts[e->fail_cur].alloc(e->fail_cap * 8));
     }
     CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_FAILED, 0, 8, e->cs));
-    rc = table_setup(e, nt, nl, M);
-    if(rc) return rc == JFGPU_ERR_NOMEM ? fail(e, JFGPU_ERR_FULL, "Hash full (" + e->err + ")") : rc;
-    // distinct / reprobes statistics restart for the new table
-    CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_DISTINCT, 0, 8, e->cs));
-    CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_REPROBES, 0, 8, e->cs));
-    const uint64_t inserted_before = e->h_stats[STAT_INSERTED];
-    SegScratch s;
-    const uint64_t seg = pick_segment(e->tab);
-    rc = seg_alloc(e, s, seg, false, 0);
-    if(rc) { s.free_all(); return rc; }
-    for(uint64_t lo = 0; lo < e->tab.local_size && !rc; lo += seg) {
-      uint64_t n = 0;
-      rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, false, &n);
-      if(!rc) rc = insert_keys_into(e, nt, s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), n, e->cs);
-    }
-    if(!rc) rc = insert_keys_into(e, nt, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
-    cudaStreamSynchronize(e->cs);
-    s.free_all();
+    rc = rebuild_table(e, nl, M, old_fail, n_failed);
     if(rc) return rc;
-    // (each table owns its counter-carry side table: the old one dies with the old slots)
-    e->tab.release();
-    e->tab = nt;
-    // STAT_INSERTED counts k-mer occurrences; the re-insertion must not change it
-    CUDA_OK(e, cudaMemcpyAsync(e->stats.as<unsigned long long>() + STAT_INSERTED, &inserted_before, 8, cudaMemcpyHostToDevice, e->cs));
-    CUDA_OK(e, cudaStreamSynchronize(e->cs));
     e->regrows++;
   }
+}
+
+// Direct-indexing regime (table as large as the key space, no reprobing).  The reference
+// cannot chain "large" continuation entries there, so a counter that outgrows val_len bits
+// makes hash_counter::double_size build a new array with val_len + 1 -- and, the size being
+// 4^k, with the IDENTITY matrix (hash_counter.hpp:205-212, large_hash_array.hpp:992-1002).
+// The observable result is: val_len = bits of the largest count, identity hash.
+int direct_index_fixup(jfgpu_engine* e) {
+  const unsigned kbits = 2 * e->k;
+  if(e->tab.lsize < kbits || e->shard_bits) return JFGPU_OK;
+  CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_MAXCOUNT, 0, 8, e->cs));
+  TableDev T = table_dev(e, e->tab);
+  const uint64_t ns = e->tab.local_size + e->tab.margin;
+  const int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 16);
+  switch(e->tab.slot_bits) {
+  case 32:  max_count_kernel<32><<<grid, 256, 0, e->cs>>>(T, ns); break;
+  case 64:  max_count_kernel<64><<<grid, 256, 0, e->cs>>>(T, ns); break;
+  default:  max_count_kernel<128><<<grid, 256, 0, e->cs>>>(T, ns); break;
+  }
+  JF_LAUNCHED();
+  int rc = read_stats(e);
+  if(rc) return rc;
+  const uint64_t maxc = e->h_stats[STAT_MAXCOUNT];
+  if(e->eff_val_len < 64 && (maxc >> e->eff_val_len) != 0) {
+    e->eff_val_len = bitsize(maxc);
+    if(!e->tab.M.is_identity()) {
+      rc = rebuild_table(e, e->tab.lsize, jfb::gf2_matrix::identity(kbits), 0, 0);
+      if(rc) return rc;
+    }
+  }
+  return JFGPU_OK;
 }
 
 int check_after_batches(jfgpu_engine* e) {
@@ -460,6 +503,7 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   e->k = params->k;
   e->kw = params->k > 32 ? 2 : 1;
   e->nbytes = (2 * params->k + 7) / 8;
+  e->eff_val_len = params->counter_len;
   e->shard_bits = ceil_log2(ns);
   auto bail = [&](int code) { g_create_error = e->err; jfgpu_destroy(e); return code; };
 
@@ -689,6 +733,8 @@ int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
   CUDA_OK(e, cudaGetLastError());
   int rc = check_after_batches(e);
   if(rc) return rc;
+  rc = direct_index_fixup(e);
+  if(rc) return rc;
   if(s) return jfgpu_get_stats(e, s);
   return JFGPU_OK;
 }
@@ -696,7 +742,7 @@ int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
 int jfgpu_table_info_get(jfgpu_handle e, jfgpu_table_info* info) {
   if(!e || !info) return JFGPU_ERR_ARG;
   const Table& t = e->tab;
-  info->size = t.size; info->lsize = t.lsize; info->key_len = 2 * e->k; info->val_len = e->p.counter_len;
+  info->size = t.size; info->lsize = t.lsize; info->key_len = 2 * e->k; info->val_len = e->eff_val_len;
   info->max_reprobe = t.max_reprobe; info->matrix_r = t.M.r(); info->matrix_c = t.M.c();
   info->matrix_identity = t.M.is_low_identity() ? 1 : 0;
   info->slot_bits = t.slot_bits; info->local_slots = t.local_slots; info->table_bytes = t.bytes();

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) count_kernel(const CountArgs a) {
   };
 
   LocalStats ls = { 0, 0, 0, 0, 0 };
-  uint32_t phase[2] = { 0, 0 };
+  uint32_t phase_bits = 0;          // bit b = parity to wait for on buffer b
   int buf = 0;
   uint64_t t = blockIdx.x;
   if(t < a.n_tiles && tid == 0) issue(t, 0);
@@ -258,7 +258,6 @@ __global__ void __launch_bounds__(NT, 1) count_kernel(const CountArgs a) {
     if(tn < a.n_tiles && tid == 0) issue(tn, buf ^ 1);
 
     const long long h = (long long)(t * (uint64_t)TILE) - HALO;      // global position of window byte 0
-    const long long body = h + HALO;                                   // first byte owned by this tile
     const long long wend_ll = (long long)n < h + WIN ? (long long)n : h + WIN;
     // tail bytes that the 16-byte granular TMA copy left out
     {
@@ -267,8 +266,8 @@ __global__ void __launch_bounds__(NT, 1) count_kernel(const CountArgs a) {
       long long g = from + copied + tid;
       if(tid < 16 && g < wend_ll) sm.win[buf][g - h] = a.in[g];
     }
-    mbar_wait(&sm.bar[buf], phase[buf]);
-    phase[buf] ^= 1;
+    mbar_wait(&sm.bar[buf], (phase_bits >> buf) & 1u);
+    phase_bits ^= 1u << buf;
     __syncthreads();
 
     // ---- phase B: classify 32 bytes per thread, build the state transition function ----
@@ -703,6 +702,28 @@ __global__ void __launch_bounds__(256) histogram_kernel(TableDev T, uint64_t n_s
       atomicAdd(&hist[cnt < n_bins ? cnt : n_bins - 1], 1ull);
     }
   }
+}
+
+template<int SB>
+__global__ void __launch_bounds__(256) max_count_kernel(TableDev T, uint64_t n_slots) {
+  unsigned long long m = 0;
+  for(uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_slots; idx += (uint64_t)gridDim.x * blockDim.x) {
+    u128 high; uint32_t rp; uint64_t cnt;
+    if(slot_decode<SB>(T, idx, high, rp, cnt)) {
+      if(T.stats[STAT_OVERFLOWED]) {
+        const uint32_t cb = (SB == 128) ? (64 - (T.fbits > 64 ? T.fbits - 64 : 0)) : (SB - T.fbits);
+        const uint64_t carries = ovf_get(T, idx);
+        if(carries) {
+          if(cb >= 64 || (carries >> (64 - cb)) != 0) cnt = ~0ull;
+          else { uint64_t add = carries << cb; cnt = (cnt + add < cnt) ? ~0ull : cnt + add; }
+        }
+      }
+      m = max(m, (unsigned long long)cnt);
+    }
+  }
+#pragma unroll
+  for(int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if((threadIdx.x & 31) == 0 && m) atomicMax(&T.stats[STAT_MAXCOUNT], m);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,302 @@
+/* jf_oracle.c -- CPU restatement of the `jellyfish count` hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may build or run this
+ * program, and only as the checker.  The product (jellyfish_b200/) never links or calls it.
+ *
+ * Parity is PINNED: tests/test_oracle.py checks this program byte for byte against the
+ * unmodified reference built in oracle/_ref (which itself reproduces the reference's golden
+ * md5s of tests/parallel_hashing.sh:10-12), and against fixtures in tests/golden/.
+ *
+ * It is written for clarity, not speed: parse -> collect every canonical k-mer -> sort ->
+ * count runs -> hash -> sort by (position, key) -> write.  Each step cites the reference code
+ * whose observable behaviour it restates (paths relative to /root/reference).
+ *
+ *   jf_oracle count -m K -s SIZE [-C] [-c VAL_LEN] [-p REPROBES] [--out-counter-len N]
+ *                   [-L LOW] [-U HIGH] [-o OUT] file...
+ *   jf_oracle matrix R C [SKIP]        print the hash matrix columns the reference would draw
+ */
+#define _GNU_SOURCE
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef unsigned __int128 u128;
+
+/* ---- glibc random(), TYPE_3, default seed 1: the stream lib/misc.cc:66-72 consumes ---------- */
+static int32_t rnd_r[34];
+static int rnd_f, rnd_b;
+static uint32_t rnd_step(void) {
+  uint32_t v = (uint32_t)rnd_r[rnd_f] + (uint32_t)rnd_r[rnd_b];
+  rnd_r[rnd_f] = (int32_t)v;
+  if(++rnd_f >= 31) rnd_f = 0;
+  if(++rnd_b >= 31) rnd_b = 0;
+  return v >> 1;
+}
+static void rnd_seed(uint32_t seed) {
+  rnd_r[0] = (int32_t)seed;
+  for(int i = 1; i < 31; ++i) {
+    int64_t w = (16807LL * rnd_r[i - 1]) % 2147483647LL;
+    if(w < 0) w += 2147483647LL;
+    rnd_r[i] = (int32_t)w;
+  }
+  rnd_f = 3; rnd_b = 0;
+  for(int i = 0; i < 310; ++i) rnd_step();
+}
+/* random_bits(64): lib/misc.cc:66-72 */
+static uint64_t random_bits64(void) {
+  uint64_t res = 0;
+  for(int i = 0; i < 64; i += 31) res ^= (uint64_t)rnd_step() << i;
+  return res;
+}
+
+/* ---- GF(2) matrix: include/jellyfish/rectangular_binary_matrix.hpp, lib/...matrix.cc -------- */
+typedef struct { unsigned r, c; int identity; uint64_t col[256]; } matrix_t;
+
+/* times(): XOR of columns[c-1-i] over set bits i (rectangular_binary_matrix.hpp:223-261) */
+static uint64_t mat_times(const matrix_t* m, u128 v) {
+  if(m->identity) return (uint64_t)v & (m->r >= 64 ? ~0ULL : ((1ULL << m->r) - 1));
+  uint64_t res = 0;
+  for(unsigned i = 0; i < m->c; ++i)
+    if((v >> i) & 1) res ^= m->col[m->c - 1 - i];
+  return res;
+}
+/* pseudo_inverse(): lib/rectangular_binary_matrix.cc:160-210.  Returns 0 when singular. */
+static int mat_pseudo_inverse(const matrix_t* m, matrix_t* res) {
+  uint64_t piv[256];
+  memcpy(piv, m->col, sizeof(uint64_t) * m->c);
+  res->r = m->r; res->c = m->c; res->identity = 0;
+  memset(res->col, 0, sizeof(res->col));
+  unsigned srow = m->r < m->c ? m->r : m->c, scol = m->c - srow;
+  for(unsigned i = scol; i < m->c; ++i) res->col[i] = 1ULL << (srow - 1 - (i - scol));
+  uint64_t mask = 1ULL << (srow - 1);
+  for(unsigned i = scol; i < m->c; ++i, mask >>= 1) {
+    if(!(piv[i] & mask)) {
+      unsigned j = i + 1;
+      while(j < m->c && !(piv[j] & mask)) ++j;
+      if(j == m->c) return 0;
+      piv[i] ^= piv[j]; res->col[i] ^= res->col[j];
+    }
+    for(unsigned j = i + 1; j < m->c; ++j)
+      if(piv[j] & mask) { piv[j] ^= piv[i]; res->col[j] ^= res->col[i]; }
+  }
+  mask = 1ULL << (srow - 1);
+  for(unsigned i = scol; i < m->c; ++i, mask >>= 1)
+    for(unsigned j = 0; j < i; ++j)
+      if(piv[j] & mask) { piv[j] ^= piv[i]; res->col[j] ^= res->col[i]; }
+  return 1;
+}
+/* randomize_pseudo_inverse(): lib/rectangular_binary_matrix.cc:240-247 */
+static void mat_draw(unsigned r, unsigned c, matrix_t* out) {
+  matrix_t m;
+  m.r = r; m.c = c; m.identity = 0;
+  uint64_t cmask = r >= 64 ? ~0ULL : ((1ULL << r) - 1);
+  do {
+    for(unsigned i = 0; i < c; ++i) m.col[i] = random_bits64() & cmask;
+  } while(!mat_pseudo_inverse(&m, out));
+}
+
+/* ---- k-mer extraction ---------------------------------------------------------------------- */
+static unsigned K;
+static int canonical;
+static u128* mers; static size_t n_mers, cap_mers;
+static void emit(u128 m) {
+  if(n_mers == cap_mers) { cap_mers = cap_mers ? cap_mers * 2 : (1 << 20); mers = realloc(mers, cap_mers * sizeof(u128)); if(!mers) { perror("realloc"); exit(1); } }
+  mers[n_mers++] = m;
+}
+/* codes[]: include/jellyfish/mer_dna.hpp:38-55 */
+static int code(int c) {
+  switch(c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; }
+  return -1;
+}
+static u128 fwd, rev; static unsigned filled;
+/* one character of clean sequence: mer_iterator.hpp:67-76; shift_left / shift_right: mer_dna.hpp:322-370 */
+static void feed_char(int ch) {
+  int c = code(ch);
+  if(c < 0) { filled = 0; return; }
+  u128 mask = K == 64 ? ~(u128)0 : (((u128)1 << (2 * K)) - 1);
+  fwd = ((fwd << 2) | (u128)c) & mask;
+  rev = (rev >> 2) | ((u128)(3 - c) << (2 * K - 2));
+  if(filled < K) ++filled;
+  if(filled >= K) emit(canonical && rev < fwd ? rev : fwd);   /* operator<: mer_dna.hpp:227-250 */
+}
+/* One file: mer_overlap_sequence_parser.hpp:134-148 (format sniffing), :161-185 read_fasta
+ * (headers dropped, an 'N' between records), :260-274 read_sequence ('\n' and line-end '\r'
+ * dropped, lines concatenated), :111 (no k-mer across files). */
+static int count_file(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if(!f) { fprintf(stderr, "Can't open file '%s'\n", path); return 0; }
+  fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+  unsigned char* d = malloc(n + 1);
+  if(n && fread(d, 1, n, f) != (size_t)n) { perror("fread"); exit(1); }
+  fclose(f);
+  filled = 0; fwd = rev = 0;
+  if(n == 0) { free(d); return 1; }
+  if(d[0] != '>') { fprintf(stderr, "Unsupported format\n"); exit(134); }
+  long p = 0;
+  int at_line_start = 1;
+  while(p < n) {
+    if(at_line_start) {
+      while(p < n && (d[p] == '\n' || d[p] == '\r')) ++p;                 /* skip_newlines */
+      if(p >= n) break;
+      if(d[p] == '>') { feed_char('N'); while(p < n && d[p] != '\n') ++p; if(p < n) ++p; continue; }   /* ignore_line + 'N' */
+      at_line_start = 0;
+    }
+    long e = p; while(e < n && d[e] != '\n') ++e;                          /* istream::get up to '\n' */
+    long t = e; while(t > p && d[t - 1] == '\r') --t;                      /* strip line-end '\r' */
+    for(long i = p; i < t; ++i) feed_char(d[i]);
+    p = e; at_line_start = 1;
+  }
+  free(d);
+  filled = 0;
+  return 1;
+}
+
+static int cmp_u128(const void* a, const void* b) { u128 x = *(const u128*)a, y = *(const u128*)b; return x < y ? -1 : x > y; }
+typedef struct { uint64_t pos; u128 key; uint64_t count; } rec_t;
+static int cmp_rec(const void* a, const void* b) {
+  const rec_t* x = a; const rec_t* y = b;
+  if(x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+  return x->key < y->key ? -1 : x->key > y->key;
+}
+static unsigned ceil_log2(uint64_t x) { unsigned l = 0; while(l < 64 && (1ULL << l) < x) ++l; return l; }
+static unsigned bitsize(uint64_t x) { unsigned b = 0; while(x) { ++b; x >>= 1; } return b ? b : 1; }
+static uint64_t reprobe_off(unsigned i) { return i == 0 ? 1 : (uint64_t)i * (i + 1) / 2; }   /* lib/storage.cc:13-41 */
+
+/* Would every distinct key find a slot within `limit` reprobes?  claim_key probing,
+ * large_hash_array.hpp:509-597 (one slot per key; continuation entries of counts > 2^val_len
+ * are not modelled, so the fullness decision is exact only for data without such counts). */
+static int fits(const rec_t* recs, size_t n, uint64_t size, unsigned limit, const matrix_t* m, const u128* order, size_t n_order) {
+  unsigned char* used = calloc(size, 1);
+  (void)recs; (void)n;
+  int ok = 1;
+  for(size_t i = 0; i < n_order && ok; ++i) {
+    uint64_t pos = mat_times(m, order[i]) & (size - 1);
+    unsigned r = 0; uint64_t id = pos;
+    while(used[id]) { if(++r > limit) { ok = 0; break; } id = (pos + reprobe_off(r)) & (size - 1); }
+    if(ok) used[id] = 1;
+  }
+  free(used);
+  return ok;
+}
+
+static uint64_t parse_size(const char* s) {
+  char* end; double v = strtod(s, &end); uint64_t u = strtoull(s, &end, 0); (void)v;
+  switch(*end) { case 'k': u *= 1000ULL; break; case 'M': u *= 1000000ULL; break; case 'G': u *= 1000000000ULL; break; case 'T': u *= 1000000000000ULL; break; }
+  return u;
+}
+
+int main(int argc, char** argv) {
+  rnd_seed(1);
+  if(argc >= 4 && !strcmp(argv[1], "matrix")) {
+    unsigned r = atoi(argv[2]), c = atoi(argv[3]), skip = argc > 4 ? atoi(argv[4]) : 0;
+    matrix_t m;
+    for(unsigned i = 0; i <= skip; ++i) mat_draw(r, c, &m);
+    for(unsigned i = 0; i < c; ++i) printf("%llu\n", (unsigned long long)m.col[i]);
+    return 0;
+  }
+  if(argc < 2 || strcmp(argv[1], "count")) { fprintf(stderr, "usage: jf_oracle count ... | matrix R C [SKIP]\n"); return 1; }
+  uint64_t size = 0, low = 0, high = ~0ULL; unsigned val_len = 7, reprobes = 126, ocl = 4; const char* out = "mer_counts.jf";
+  int first_file = argc;
+  for(int i = 2; i < argc; ++i) {
+    if(!strcmp(argv[i], "-m")) K = atoi(argv[++i]);
+    else if(!strcmp(argv[i], "-s")) size = parse_size(argv[++i]);
+    else if(!strcmp(argv[i], "-C")) canonical = 1;
+    else if(!strcmp(argv[i], "-c")) val_len = atoi(argv[++i]);
+    else if(!strcmp(argv[i], "-p")) reprobes = atoi(argv[++i]);
+    else if(!strcmp(argv[i], "--out-counter-len")) ocl = atoi(argv[++i]);
+    else if(!strcmp(argv[i], "-L")) low = strtoull(argv[++i], 0, 0);
+    else if(!strcmp(argv[i], "-U")) high = strtoull(argv[++i], 0, 0);
+    else if(!strcmp(argv[i], "-o")) out = argv[++i];
+    else if(!strcmp(argv[i], "-t")) ++i;
+    else { first_file = i; break; }
+  }
+  if(K < 1 || K > 64 || size == 0) { fprintf(stderr, "need -m (1..64) and -s\n"); return 1; }
+  const unsigned kbits = 2 * K;
+
+  /* table + first matrix are created BEFORE the input is read: count_main.cc:275 */
+  uint64_t key_space = kbits >= 64 ? ~0ULL / 2 : (1ULL << kbits);
+  unsigned lsize = ceil_log2(size < key_space ? size : key_space);
+  matrix_t M;
+  if(size < key_space) mat_draw(lsize, kbits, &M); else { M.identity = 1; M.r = M.c = kbits; }
+
+  for(int i = first_file; i < argc; ++i) if(!count_file(argv[i])) return 1;
+
+  /* first-occurrence order of the distinct keys (insertion order of a -t 1 run) */
+  u128* order = malloc((n_mers ? n_mers : 1) * sizeof(u128));
+  memcpy(order, mers, n_mers * sizeof(u128));
+  qsort(mers, n_mers, sizeof(u128), cmp_u128);
+  size_t n_rec = 0;
+  rec_t* recs = malloc((n_mers ? n_mers : 1) * sizeof(rec_t));
+  for(size_t i = 0; i < n_mers; ) {
+    size_t j = i; while(j < n_mers && mers[j] == mers[i]) ++j;
+    recs[n_rec].key = mers[i]; recs[n_rec].count = j - i; ++n_rec; i = j;
+  }
+  /* distinct keys in first-occurrence order: mark seen through a sorted lookup */
+  size_t n_order = 0;
+  {
+    unsigned char* seen = calloc(n_rec ? n_rec : 1, 1);
+    for(size_t i = 0; i < n_mers; ++i) {
+      size_t lo = 0, hi = n_rec;
+      while(lo < hi) { size_t mid = (lo + hi) / 2; if(recs[mid].key < order[i]) lo = mid + 1; else hi = mid; }
+      if(!seen[lo]) { seen[lo] = 1; order[n_order++] = order[i]; }
+    }
+    free(seen);
+  }
+
+  /* size doubling: hash_counter.hpp:200-238 -- a new array (new matrix draw) twice as large
+   * until everything fits; at 4^k the table is direct-indexed with the identity matrix and the
+   * value field grows instead (:205-212). */
+  unsigned limit;
+  for(;;) {
+    uint64_t tsize = 1ULL << lsize;
+    limit = kbits > lsize ? reprobes : 0;                                 /* large_hash_array.hpp:160 */
+    while(limit >= 1 && reprobe_off(limit) >= tsize) --limit;             /* reprobe_limit_t :29-39 */
+    if(fits(recs, n_rec, tsize, limit, &M, order, n_order)) break;
+    ++lsize;
+    if(kbits < 64 && (1ULL << lsize) >= (1ULL << kbits)) { lsize = kbits; M.identity = 1; M.r = M.c = kbits; }
+    else mat_draw(lsize, kbits, &M);
+  }
+  uint64_t tsize = 1ULL << lsize, maxc = 0;
+  for(size_t i = 0; i < n_rec; ++i) { recs[i].pos = mat_times(&M, recs[i].key) & (tsize - 1); if(recs[i].count > maxc) maxc = recs[i].count; }
+  if(kbits <= lsize && maxc >= (1ULL << val_len)) {       /* direct indexing: val_len grows, matrix becomes identity */
+    val_len = bitsize(maxc);
+    M.identity = 1; M.r = M.c = kbits;
+    for(size_t i = 0; i < n_rec; ++i) recs[i].pos = mat_times(&M, recs[i].key) & (tsize - 1);
+  }
+  /* sorted_dumper: ascending (position, key): sorted_dumper.hpp:72-101, mer_heap.hpp:26-30 */
+  qsort(recs, n_rec, sizeof(rec_t), cmp_rec);
+
+  /* header: generic_file_header.hpp:88-111, file_header.hpp:26-108 (keys sorted, terse JSON) */
+  FILE* f = fopen(out, "wb");
+  if(!f) { fprintf(stderr, "Can't open output file '%s'\n", out); return 1; }
+  char* js = malloc(1 << 20); size_t o = 0;
+  o += sprintf(js + o, "{\"alignment\":8,\"canonical\":%s,\"cmdline\":[\"jf_oracle\"],\"counter_len\":%u,\"exe_path\":\"jf_oracle\",\"format\":\"binary/sorted\",\"hostname\":\"hostname\",\"key_len\":%u,\"matrix1\":{\"c\":%u,",
+               canonical ? "true" : "false", ocl, kbits, M.c);
+  if(!M.identity) {
+    o += sprintf(js + o, "\"columns\":[");
+    for(unsigned i = 0; i < M.c; ++i) o += sprintf(js + o, "%s%llu", i ? "," : "", (unsigned long long)M.col[i]);
+    o += sprintf(js + o, "],\"identity\":false,");
+  } else o += sprintf(js + o, "\"identity\":true,");
+  o += sprintf(js + o, "\"r\":%u},\"max_reprobe\":%u,\"pwd\":\".\",\"reprobes\":[", M.r, limit);
+  for(unsigned i = 0; i <= limit; ++i) o += sprintf(js + o, "%s%llu", i ? "," : "", (unsigned long long)reprobe_off(i));
+  o += sprintf(js + o, "],\"size\":%llu,\"time\":\"Thu Jan  1 00:00:00 1970\",\"val_len\":%u}", (unsigned long long)tsize, val_len);
+  size_t hlen = o, pad = (9 + o) % 8;
+  if(pad) hlen += 8 - pad;
+  fprintf(f, "%09zu", hlen);
+  fwrite(js, 1, o, f);
+  for(size_t i = o; i < hlen; ++i) fputc(0, f);
+  /* records: binary_dumper.hpp:36-40 */
+  unsigned kb = (kbits + 7) / 8;
+  uint64_t maxv = ocl >= 8 ? ~0ULL : ((1ULL << (8 * ocl)) - 1);
+  for(size_t i = 0; i < n_rec; ++i) {
+    if(recs[i].count < low || recs[i].count > high) continue;
+    fwrite(&recs[i].key, 1, kb, f);
+    uint64_t v = recs[i].count < maxv ? recs[i].count : maxv;
+    fwrite(&v, 1, ocl, f);
+  }
+  fclose(f);
+  fprintf(stderr, "jf_oracle: %zu k-mers, %zu distinct, size %llu\n", n_mers, n_rec, (unsigned long long)tsize);
+  return 0;
+}

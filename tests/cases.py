@@ -1,0 +1,46 @@
+"""Parity cases: name -> (count switches, input files of tests/gen.py).
+
+Configurations follow the reference's own integration tests (tests/parallel_hashing.sh,
+merge.sh, multi_file.sh, small_mers.sh, large_key.sh) scaled to inputs that the CPU reference
+counts in seconds, plus the edge cases of SURVEY.md section 8a.
+"""
+CASES = {
+    # geometry sweep: slot widths 32 / 64 / 128, one- and two-word keys
+    "k21C":         (["-m", "21", "-s", "600k", "-C"], ["plain.fa"]),
+    "k21":          (["-m", "21", "-s", "600k"], ["plain.fa"]),
+    "k15C":         (["-m", "15", "-s", "1M", "-C"], ["plain.fa"]),
+    "k31C":         (["-m", "31", "-s", "600k", "-C"], ["plain.fa"]),
+    "k32C":         (["-m", "32", "-s", "600k", "-C"], ["plain.fa"]),
+    "k33C":         (["-m", "33", "-s", "600k", "-C"], ["plain.fa"]),
+    "k40":          (["-m", "40", "-s", "600k"], ["plain.fa"]),
+    "k63C":         (["-m", "63", "-s", "700k", "-C"], ["plain.fa"]),
+    "k64C":         (["-m", "64", "-s", "700k", "-C"], ["plain.fa"]),
+    "k24_tiny":     (["-m", "24", "-s", "300k", "-C", "-p", "30"], ["plain.fa"]),
+    # small mers / direct indexing (tests/small_mers.sh)
+    "k2C":          (["-m", "2", "-s", "1M", "-C"], ["plain.fa"]),
+    "k5_1k":        (["-m", "5", "-s", "1k", "-C"], ["plain.fa"]),
+    "k8":           (["-m", "8", "-s", "10M"], ["plain.fa"]),
+    "k10C":         (["-m", "10", "-s", "1M", "-C"], ["plain.fa"]),
+    # input text semantics
+    "dos":          (["-m", "21", "-s", "600k", "-C"], ["dos.fa"]),
+    "noeol":        (["-m", "21", "-s", "600k", "-C"], ["noeol.fa"]),
+    "lower":        (["-m", "21", "-s", "600k", "-C"], ["lower.fa"]),
+    "multi":        (["-m", "17", "-s", "1M", "-C"], ["multi.fa"]),
+    "multi_files":  (["-m", "17", "-s", "1M", "-C"], ["multi.fa", "empty.fa", "multi2.fa", "header_only.fa", "dangling.fa"]),
+    "one_per_line": (["-m", "25", "-s", "100k", "-C"], ["one_per_line.fa"]),
+    "blank_runs":   (["-m", "31", "-s", "100k", "-C"], ["blank_runs.fa"]),
+    "long_header":  (["-m", "21", "-s", "100k"], ["long_header.fa"]),
+    "cr_mid":       (["-m", "4", "-s", "1k", "-C"], ["cr_mid.fa"]),
+    "oneline":      (["-m", "21", "-s", "300k", "-C"], ["oneline.fa"]),
+    "k63_multi":    (["-m", "63", "-s", "1M", "-C"], ["multi.fa", "dos.fa"]),
+    # counters: large counts, output clipping, count filters
+    "polya":        (["-m", "21", "-s", "1k", "-C"], ["polya.fa"]),
+    "repeat":       (["-m", "21", "-s", "10k", "-C"], ["repeat.fa"]),
+    "repeat_ocl1":  (["-m", "21", "-s", "10k", "-C", "--out-counter-len", "1"], ["repeat.fa"]),
+    "repeat_LU":    (["-m", "21", "-s", "10k", "-C", "-L", "300", "-U", "400"], ["repeat.fa"]),
+    "c3":           (["-m", "12", "-s", "300k", "-C", "-c", "3"], ["plain.fa"]),
+    # size doubling with new matrix draws (hash_counter.hpp:200-238)
+    "grow2":        (["-m", "21", "-s", "100k", "-C"], ["plain.fa"]),
+    "grow_k40":     (["-m", "40", "-s", "50k"], ["plain.fa"]),
+    "grow_to_full": (["-m", "8", "-s", "10k", "-C"], ["plain.fa"]),
+}

@@ -1,0 +1,65 @@
+"""Deterministic test inputs (pure Python, independent of any binary)."""
+import os
+import random
+
+
+def _seq(n, seed):
+    rng = random.Random(seed)
+    bits = rng.getrandbits(2 * n)
+    out = bytearray(n)
+    for i in range(n):
+        out[i] = b"ACGT"[(bits >> (2 * i)) & 3]
+    return bytes(out)
+
+
+def fasta(seq, line=70, name=b"read1", eol=b"\n"):
+    out = [b">" + name + eol]
+    for i in range(0, len(seq), line):
+        out.append(seq[i:i + line] + eol)
+    return b"".join(out)
+
+
+def make_all(d):
+    """-> dict name -> path.  Sizes are small so that the CPU reference runs in seconds."""
+    f = {}
+
+    def w(name, data):
+        p = os.path.join(d, name)
+        with open(p, "wb") as fh:
+            fh.write(data)
+        f[name] = p
+        return p
+
+    s300 = _seq(300000, 1)
+    w("plain.fa", fasta(s300))
+    w("dos.fa", fasta(s300, eol=b"\r\n"))
+    w("noeol.fa", fasta(s300)[:-1])
+    w("lower.fa", fasta(s300.lower()))
+    # several records, some short, N's and IUPAC codes, blank lines, '>' inside a line, spaces
+    rng = random.Random(7)
+    recs = []
+    for i in range(200):
+        s = bytearray(_seq(rng.randrange(1, 3000), 100 + i))
+        for _ in range(rng.randrange(0, 4)):
+            s[rng.randrange(len(s))] = rng.choice(b"NnRYKMSWBDHVU-. >\t")
+        body = fasta(bytes(s), line=rng.choice([1, 7, 60, 70, 200]), name=b"r%d some description" % i)
+        if rng.random() < 0.3:
+            body = body.replace(b"\n", b"\n\n", 2)
+        recs.append(body)
+    w("multi.fa", b"".join(recs))
+    w("multi2.fa", b"".join(reversed(recs[:50])))
+    w("empty.fa", b"")
+    w("header_only.fa", b">just a header\n")
+    w("dangling.fa", fasta(_seq(5000, 3)) + b">read2\n")
+    # pathological line structure: one base per line, runs of blank lines, very long header
+    s2 = _seq(20000, 5)
+    w("one_per_line.fa", fasta(s2, line=1))
+    w("blank_runs.fa", b">x\n" + b"".join(s2[i:i + 50] + b"\n" * (1 + (i // 50) % 400) for i in range(0, 5000, 50)))
+    w("long_header.fa", b">" + b"h" * 70000 + b"\n" + s2[:3000] + b"\n>" + b"ACGT" * 300 + b"\n" + s2[3000:6000] + b"\n")
+    w("cr_mid.fa", b">x\nACGTACGTAC\rGTACGTTGCA\r\r\nACGTAGCTAGCTAGCTAGGGATCGATCGACTAGCTA\r\n\r\nACGATCGATCGTTTAGC\r")
+    w("oneline.fa", b">x\n" + _seq(100000, 9) + b"\n")
+    # repetitive: counts far beyond 2^val_len
+    w("polya.fa", fasta(b"A" * 100000))
+    w("repeat.fa", fasta(_seq(500, 11) * 400))
+    w("plain1m.fa", fasta(_seq(1000000, 2)))
+    return f

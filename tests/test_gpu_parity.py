@@ -1,0 +1,173 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (by the C++ host driver
+`jellyfish-b200 count` and by the ctypes mirror), against
+  * the committed golden fixtures written by the unmodified reference (tests/golden/), and
+  * the reference binary itself (oracle/_ref/jellyfish) run on the same inputs, when present.
+Integer / byte work: the bar is bit-exact record bodies and equal semantic header keys."""
+import json
+import os
+import random
+
+import pytest
+
+import jfutil
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def _count_cli(workdir, inputs, name, args, ins, extra=()):
+    db = os.path.join(workdir, "gpu_%s.jf" % name)
+    jfutil.run([jfutil.OUR_JF, "count"] + list(args) + list(extra) + ["-o", db] + [inputs[i] for i in ins])
+    return jfutil.split_db(db)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cli_count_matches_reference_golden(name, built, workdir, inputs):
+    args, ins = CASES[name]
+    h, b = _count_cli(workdir, inputs, name, args, ins)
+    g = GOLDEN[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"]
+    assert jfutil.md5(b) == g["body_md5"]
+
+
+@pytest.mark.skipif(not os.path.exists(jfutil.REF_JF), reason="oracle/_ref not built")
+def test_against_reference_binary_1m(built, workdir, inputs):
+    """Same input through both programs, body compared byte for byte (1 Mbp, k=21 canonical,
+    the shape of BASELINE configs[0])."""
+    ref = os.path.join(workdir, "ref_1m.jf")
+    jfutil.run([jfutil.REF_JF, "count", "-m", "21", "-s", "2M", "-t", "4", "-C", "-o", ref, inputs["plain1m.fa"]])
+    h1, b1 = jfutil.split_db(ref)
+    h2, b2 = _count_cli(workdir, inputs, "ours_1m", ["-m", "21", "-s", "2M", "-C"], ["plain1m.fa"])
+    assert jfutil.semantic(h1) == jfutil.semantic(h2)
+    assert b1 == b2
+    # and the reference's own tools read our file
+    ours = os.path.join(workdir, "gpu_ours_1m.jf")
+    assert jfutil.run([jfutil.REF_JF, "stats", ours]).stdout == jfutil.run([jfutil.REF_JF, "stats", ref]).stdout
+    assert jfutil.run([jfutil.REF_JF, "histo", ours]).stdout == jfutil.run([jfutil.REF_JF, "histo", ref]).stdout
+
+
+def test_python_api_chunked_feeds(built, workdir, inputs):
+    """Feeding a file in arbitrary pieces (state carried on the device) and with tiny device
+    batches gives the same database as one feed."""
+    from jellyfish_b200 import HashCounter
+    data = open(inputs["multi.fa"], "rb").read() + b""
+    g = GOLDEN["multi"]
+    rng = random.Random(3)
+    for batch in (0, 4096 + 16, 70000):
+        with HashCounter(1000000, 7, k=17, canonical=True, max_batch_bytes=batch) as hc:
+            if batch == 0:
+                hc.add_text(data)
+            else:
+                off, first = 0, True
+                while off < len(data):
+                    n = rng.choice([1, 3, 17, 100, 5000, 33333, 200000])
+                    hc.add_text(data[off:off + n], begin=first, end=off + n >= len(data))
+                    first = False
+                    off += n
+            st = hc.done()
+            body = hc.dump_records()
+            assert jfutil.md5(body) == g["body_md5"], batch
+            hdr = hc.header()
+            assert {k: hdr[k] for k in jfutil.SEMANTIC_KEYS} == g["header"]
+            assert st["kmers"] == st["inserted"] and st["distinct"] * (3 + 4) <= len(body) + 7 * st["distinct"]
+
+
+def test_split_anywhere_including_cr(built, inputs):
+    """Every split point of a small DOS/CR-laden file, two feeds each."""
+    from jellyfish_b200 import HashCounter
+    data = open(inputs["cr_mid.fa"], "rb").read()
+    g = GOLDEN["cr_mid"]
+    for cut in range(1, len(data)):
+        if data[cut - 1:cut] == b"\r":
+            continue   # contract of jfgpu_feed: the host never ends a non-final piece on '\r'
+        with HashCounter(1000, 7, k=4, canonical=True) as hc:
+            hc.add_text(data[:cut], begin=True, end=False)
+            hc.add_text(data[cut:], begin=False, end=True)
+            hc.done()
+            assert jfutil.md5(hc.dump_records()) == g["body_md5"], cut
+
+
+def test_lookup_histogram_and_stats(built, inputs):
+    from jellyfish_b200 import HashCounter, ReadMerFile, mer_to_int
+    import tempfile
+    with HashCounter(20000, 7, k=21, canonical=True) as hc:
+        hc.add_files([inputs["repeat.fa"], inputs["polya.fa"]])
+        st = hc.done()
+        assert st["kmers"] == (500 * 400 - 20) + (100000 - 20)
+        assert st["overflowed"] > 0            # counts far beyond the in-slot counter field
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "x.jf")
+            nrec = hc.dump(p)
+            recs = list(ReadMerFile(p))
+        assert nrec == len(recs) == st["distinct"]
+        assert sum(c for _, c in recs) == st["kmers"]
+        mers = [m for m, _ in recs[:100]] + ["A" * 21, "ACGTACGTACGTACGTACGTA"]
+        vals = hc.get_many(mers)
+        want = dict(recs)
+        assert vals == [want.get(m, 0) for m in mers]
+        assert hc.get("T" * 21) == want["A" * 21] == 100000 - 20       # canonical lookup
+        assert hc["ACGTACGTACGTACGTACGTA"] is None
+        hist = hc.histogram(200)
+        for c in range(1, 199):
+            assert hist[c] == sum(1 for _, v in recs if v == c)
+        assert hist[199] == sum(1 for _, v in recs if v >= 199)
+
+
+def test_non_canonical_and_filters_via_api(built, inputs):
+    from jellyfish_b200 import HashCounter
+    with HashCounter(600000, 7, k=21, canonical=False) as hc:
+        hc.add_files([inputs["plain.fa"]])
+        hc.done()
+        assert jfutil.md5(hc.dump_records()) == GOLDEN["k21"]["body_md5"]
+    with HashCounter(10000, 7, k=21, canonical=True) as hc:
+        hc.add_files([inputs["repeat.fa"]])
+        hc.done()
+        assert jfutil.md5(hc.dump_records(out_counter_len=1)) == GOLDEN["repeat_ocl1"]["body_md5"]
+        assert jfutil.md5(hc.dump_records(lower=300, upper=400)) == GOLDEN["repeat_LU"]["body_md5"]
+
+
+def test_errors(built, workdir, inputs):
+    import subprocess
+    from jellyfish_b200 import HashCounter, JellyfishError
+    bad = os.path.join(workdir, "bad.txt")
+    open(bad, "w").write("hello\nACGT\n")
+    r = subprocess.run([jfutil.OUR_JF, "count", "-m", "5", "-s", "1k", "-o", os.path.join(workdir, "x.jf"), bad], stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Unsupported format" in r.stderr
+    r = subprocess.run([jfutil.OUR_JF, "count", "-m", "5", "-s", "1k", "-o", os.path.join(workdir, "x.jf"), "/nonexistent.fa"], stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Can't open file" in r.stderr
+    # table full and doubling disabled -> "Hash full" (hash_counter.hpp:194-195)
+    with HashCounter(1000, 7, k=21, canonical=True, allow_regrow=False) as hc:
+        with pytest.raises(JellyfishError) as ei:
+            hc.add_files([inputs["plain.fa"]])
+            hc.done()
+        assert "Hash full" in str(ei.value)
+
+
+def test_large_scale_properties(built):
+    """At a size the CPU reference does not finish in seconds: device-generated FASTA,
+    size-independent properties (total = number of windows, idempotence of a second pass
+    doubling every count, stats consistency)."""
+    import torch
+    from jellyfish_b200 import HashCounter, _lib
+    lib = _lib.load()
+    n_bases = 200_000_000
+    nbytes = lib.jfgpu_synth_fasta_bytes(n_bases)
+    buf = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+    import ctypes as C
+    got = C.c_uint64(0)
+    assert lib.jfgpu_synth_fasta_device(0, C.c_void_p(buf.data_ptr()), nbytes + 64, n_bases, 42, C.byref(got), None) == 0
+    torch.cuda.synchronize()
+    with HashCounter(400_000_000, 7, k=21, canonical=True) as hc:
+        hc.add_device_text(buf.data_ptr(), got.value)
+        st1 = hc.done()
+        assert st1["kmers"] == n_bases - 20 == st1["inserted"]
+        h1 = hc.histogram(64)
+        assert sum(i * h for i, h in enumerate(h1)) == st1["kmers"]
+        assert sum(h1) == st1["distinct"]
+        hc.add_device_text(buf.data_ptr(), got.value)
+        st2 = hc.done()
+        assert st2["kmers"] == 2 * st1["kmers"] and st2["distinct"] == st1["distinct"]
+        h2 = hc.histogram(64)
+        assert all(h2[2 * i] == h1[i] for i in range(1, 31)) and all(h2[2 * i + 1] == 0 for i in range(0, 31))
