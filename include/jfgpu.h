@@ -97,7 +97,10 @@ typedef struct {
   uint64_t overflowed;     /* counter-field wrap events (exact: carried to side table)*/
   uint64_t regrows;        /* table doublings                                         */
   uint64_t bytes;          /* input bytes consumed                                    */
-  double   seconds_count;  /* device time spent in counting kernels (CUDA events)     */
+  double   seconds_count;  /* device time of whole feeds: copies + all kernels (CUDA events) */
+  double   seconds_count_kernel; /* device time inside the fused count kernel alone,
+                              summed over its launches (CUDA events on the launch stream) */
+  uint64_t count_kernel_launches;
 } jfgpu_stats;
 
 /* -- life cycle: hash_counter ctor / dtor (hash_counter.hpp:50-68) ------------------ */
@@ -127,6 +130,10 @@ int  jfgpu_extract_route(jfgpu_handle h, const void* dev_bytes, size_t n, uint32
 /* Insert n packed keys (as produced by jfgpu_extract_route) that this shard owns:
  * hash_counter::add for each (hash_counter.hpp:91-115). */
 int  jfgpu_insert_keys(jfgpu_handle h, const void* dev_keys, uint64_t n, void* stream);
+
+/* -- zero the table and the statistics, keep geometry and hash matrix: what the dumper's
+ *    zero_blocks leaves behind (sorted_dumper.hpp:67-68,98-99) so the counter can be reused. */
+int  jfgpu_clear(jfgpu_handle h);
 
 /* -- hash_counter::done (hash_counter.hpp:169-172): drain all device work ------------ */
 int  jfgpu_finish(jfgpu_handle h, jfgpu_stats* stats /* may be NULL */);

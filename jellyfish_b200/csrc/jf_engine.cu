@@ -95,6 +95,9 @@ struct jfgpu_engine {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   std::string err;
   std::vector<uint64_t> matrix_cols_host;   // for jfgpu_table_info_get
+  std::vector<cudaEvent_t> kev;             // event pairs around count_kernel launches
+  size_t kev_used = 0;
+  double kernel_ms = 0; uint64_t kernel_launches = 0;
   int count_smem = 0;
 };
 
@@ -240,7 +243,11 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     int per_sm = 1;
     if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * per_sm);
+    if(e->kev_used + 2 > e->kev.size()) { cudaEvent_t a0, a1; cudaEventCreate(&a0); cudaEventCreate(&a1); e->kev.push_back(a0); e->kev.push_back(a1); }
+    cudaEventRecord(e->kev[e->kev_used], stream);
     kern<<<grid, NT, smem, stream>>>(a);
+    cudaEventRecord(e->kev[e->kev_used + 1], stream);
+    e->kev_used += 2;
     return JFGPU_OK;
   });
   if(rc) return rc;
@@ -369,7 +376,7 @@ int rebuild_table(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int ol
   CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_REPROBES, 0, 8, e->cs));
   SegScratch s;
   const uint64_t seg = pick_segment(e->tab);
-  rc = seg_alloc(e, s, seg, false, 0);
+  rc = seg_alloc(e, s, seg + e->tab.margin + 8, false, 0);
   for(uint64_t lo = 0; lo < e->tab.local_size && !rc; lo += seg) {
     uint64_t n = 0;
     rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, false, &n);
@@ -446,6 +453,16 @@ int direct_index_fixup(jfgpu_engine* e) {
     }
   }
   return JFGPU_OK;
+}
+
+// fold the per-launch event pairs into kernel_ms (the stream must be idle)
+void resolve_kernel_events(jfgpu_engine* e) {
+  for(size_t i = 0; i + 1 < e->kev_used; i += 2) {
+    float ms = 0;
+    if(cudaEventElapsedTime(&ms, e->kev[i], e->kev[i + 1]) == cudaSuccess) { e->kernel_ms += ms; e->kernel_launches++; }
+    else cudaGetLastError();
+  }
+  e->kev_used = 0;
 }
 
 int check_after_batches(jfgpu_engine* e) {
@@ -562,6 +579,7 @@ void jfgpu_destroy(jfgpu_handle e) {
   if(e->h_stats) cudaFreeHost(e->h_stats);
   if(e->ev_t0) cudaEventDestroy(e->ev_t0);
   if(e->ev_t1) cudaEventDestroy(e->ev_t1);
+  for(cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
   if(e->cs) cudaStreamDestroy(e->cs);
   if(e->hs) cudaStreamDestroy(e->hs);
   delete e;
@@ -621,6 +639,7 @@ int jfgpu_feed_device(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t 
   cudaEventRecord(e->ev_t1, st);
   CUDA_OK(e, cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms;
+  resolve_kernel_events(e);
   e->bytes_fed += n;
   return end_feed(e, flags, st);
 }
@@ -659,6 +678,7 @@ int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
   e->bytes_fed += n;
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
   { float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms; }
+  resolve_kernel_events(e);
   rc = check_after_batches(e);
   if(rc) return rc;
   return end_feed(e, flags, e->cs);
@@ -709,6 +729,21 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
   return JFGPU_OK;
 }
 
+int jfgpu_clear(jfgpu_handle e) {
+  if(!e) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  CUDA_OK(e, cudaStreamSynchronize(e->hs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  resolve_kernel_events(e);
+  CUDA_OK(e, cudaMemsetAsync(e->tab.slots.p, 0, e->tab.bytes(), e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_keys.p, 0, e->ovf_size * 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_vals.p, 0, e->ovf_size * 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->stats.p, 0, STAT_N * 8, e->cs));
+  e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0;
+  e->eff_val_len = e->p.counter_len;
+  return reset_carry(e, e->cs);
+}
+
 int jfgpu_get_stats(jfgpu_handle e, jfgpu_stats* s) {
   if(!e || !s) return JFGPU_ERR_ARG;
   cudaSetDevice(e->device);
@@ -722,6 +757,9 @@ int jfgpu_get_stats(jfgpu_handle e, jfgpu_stats* s) {
   s->regrows = e->regrows;
   s->bytes = e->bytes_fed;
   s->seconds_count = e->count_ms * 1e-3;
+  resolve_kernel_events(e);
+  s->seconds_count_kernel = e->kernel_ms * 1e-3;
+  s->count_kernel_launches = e->kernel_launches;
   return JFGPU_OK;
 }
 
@@ -763,11 +801,11 @@ int jfgpu_dump(jfgpu_handle e, uint64_t lower, uint64_t upper, uint32_t ocl, jfg
   const unsigned key_bytes = e->nbytes, rec = key_bytes + ocl;
   const uint64_t seg = pick_segment(t);
   SegScratch s;
-  rc = seg_alloc(e, s, seg, true, rec);
+  rc = seg_alloc(e, s, seg + t.margin + 8, true, rec);
   uint8_t* hbuf = nullptr;
-  if(!rc && cudaHostAlloc((void**)&hbuf, seg * rec + 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "pinned host allocation failed"); }
+  if(!rc && cudaHostAlloc((void**)&hbuf, (seg + t.margin + 8) * rec + 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "pinned host allocation failed"); }
   uint64_t total = 0;
-  const uint64_t relbits = ceil_log2(seg);
+  const uint64_t relbits = ceil_log2(seg);   // original positions relative to the segment start are < seg
   for(uint64_t lo = 0; lo < t.local_size && !rc; lo += seg) {
     uint64_t n = 0;
     rc = collect_segment(e, t, s, lo, std::min(lo + seg, t.local_size), lower, upper, true, &n);

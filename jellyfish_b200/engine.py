@@ -151,6 +151,10 @@ class HashCounter(object):
     def insert_keys(self, keys_ptr, n, stream=None):
         self._check(self._lib.jfgpu_insert_keys(self._h, C.c_void_p(keys_ptr), n, C.c_void_p(stream or 0)))
 
+    def clear(self):
+        """Zero the table and statistics (same geometry and hash matrix)."""
+        self._check(self._lib.jfgpu_clear(self._h))
+
     def done(self):
         """hash_counter::done -- drain the device, returns the statistics."""
         st = L.Stats()

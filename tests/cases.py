@@ -38,6 +38,10 @@ CASES = {
     "repeat":       (["-m", "21", "-s", "10k", "-C"], ["repeat.fa"]),
     "repeat_ocl1":  (["-m", "21", "-s", "10k", "-C", "--out-counter-len", "1"], ["repeat.fa"]),
     "repeat_LU":    (["-m", "21", "-s", "10k", "-C", "-L", "300", "-U", "400"], ["repeat.fa"]),
+    # counter-field carries in each slot width (14-, 8- and 15-bit in-slot counters)
+    "ovf32":        (["-m", "14", "-s", "100k", "-C"], ["polya.fa", "repeat.fa"]),
+    "ovf64":        (["-m", "32", "-s", "30k", "-C"], ["polya.fa", "repeat.fa"]),
+    "ovf128":       (["-m", "63", "-s", "700k", "-C"], ["polya.fa", "repeat.fa"]),
     "c3":           (["-m", "12", "-s", "300k", "-C", "-c", "3"], ["plain.fa"]),
     # size doubling with new matrix draws (hash_counter.hpp:200-238)
     "grow2":        (["-m", "21", "-s", "100k", "-C"], ["plain.fa"]),

@@ -92,10 +92,10 @@ def test_split_anywhere_including_cr(built, inputs):
 def test_lookup_histogram_and_stats(built, inputs):
     from jellyfish_b200 import HashCounter, ReadMerFile, mer_to_int
     import tempfile
-    with HashCounter(20000, 7, k=21, canonical=True) as hc:
+    with HashCounter(100000, 7, k=14, canonical=True) as hc:
         hc.add_files([inputs["repeat.fa"], inputs["polya.fa"]])
         st = hc.done()
-        assert st["kmers"] == (500 * 400 - 20) + (100000 - 20)
+        assert st["kmers"] == (500 * 400 - 13) + (100000 - 13)
         assert st["overflowed"] > 0            # counts far beyond the in-slot counter field
         with tempfile.TemporaryDirectory() as d:
             p = os.path.join(d, "x.jf")
@@ -103,12 +103,12 @@ def test_lookup_histogram_and_stats(built, inputs):
             recs = list(ReadMerFile(p))
         assert nrec == len(recs) == st["distinct"]
         assert sum(c for _, c in recs) == st["kmers"]
-        mers = [m for m, _ in recs[:100]] + ["A" * 21, "ACGTACGTACGTACGTACGTA"]
+        mers = [m for m, _ in recs[:100]] + ["A" * 14, "ACGTACGTACGTAC"]
         vals = hc.get_many(mers)
         want = dict(recs)
         assert vals == [want.get(m, 0) for m in mers]
-        assert hc.get("T" * 21) == want["A" * 21] == 100000 - 20       # canonical lookup
-        assert hc["ACGTACGTACGTACGTACGTA"] is None
+        assert hc.get("T" * 14) == want["A" * 14] == 100000 - 13       # canonical lookup
+        assert hc["ACGTACGTACGTAC"] is None
         hist = hc.histogram(200)
         for c in range(1, 199):
             assert hist[c] == sum(1 for _, v in recs if v == c)
