@@ -239,6 +239,7 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     auto kern = count_kernel<decltype(KW)::value, decltype(SB)::value>;
     cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(c));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // persistent CTAs: exactly as many as are resident at once (a multiple of the SM count)
     int per_sm = 1;
     if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }

@@ -217,7 +217,7 @@ struct __align__(16) CountSmem {
 };
 
 template<int KW, int SB>
-__global__ void __launch_bounds__(NT, 1) count_kernel(const CountArgs a) {
+__global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   CountSmem& sm = *reinterpret_cast<CountSmem*>(smem_raw);
   uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(CountSmem) + 15) & ~(size_t)15));
