@@ -69,7 +69,12 @@ typedef struct {
   uint64_t bf_size;        /* --bf-size : expected number of k-mers, 0 = no filter     */
   double   bf_fp;          /* --bf-fp                                                 */
   uint64_t max_batch_bytes;/* device staging buffer size for jfgpu_feed (0 = default) */
-  uint64_t reserved[6];
+  uint64_t pool_bytes;     /* HBM set aside for the k-mer record pool of the region-by-region
+                              insertion (0 = 60% of the free memory, at most 64 GB)      */
+  uint32_t no_partition;   /* 1: always insert straight into the table (random HBM access) */
+  uint32_t part_min_mb;    /* tables of at least this many MB are filled region by region
+                              (0 = default 256); tests use 1 to exercise that path on small tables */
+  uint64_t reserved[4];
 } jfgpu_params;
 
 /* What file_header::update_from_ary records (file_header.hpp:26-33). */
@@ -101,6 +106,7 @@ typedef struct {
   double   seconds_count_kernel; /* device time inside the fused count kernel alone,
                               summed over its launches (CUDA events on the launch stream) */
   uint64_t count_kernel_launches;
+  double   seconds_drain;  /* device time of the region-by-region insertion passes (CUDA events) */
 } jfgpu_stats;
 
 /* -- life cycle: hash_counter ctor / dtor (hash_counter.hpp:50-68) ------------------ */

@@ -29,7 +29,8 @@ class Params(C.Structure):
         ("counter_len", C.c_uint32), ("max_reprobe", C.c_uint32), ("canonical", C.c_uint32),
         ("allow_regrow", C.c_uint32), ("device", C.c_int32), ("shard_index", C.c_uint32),
         ("n_shards", C.c_uint32), ("matrix_skip", C.c_uint32), ("bf_size", C.c_uint64),
-        ("bf_fp", C.c_double), ("max_batch_bytes", C.c_uint64), ("reserved", C.c_uint64 * 6),
+        ("bf_fp", C.c_double), ("max_batch_bytes", C.c_uint64), ("pool_bytes", C.c_uint64),
+        ("no_partition", C.c_uint32), ("part_min_mb", C.c_uint32), ("reserved", C.c_uint64 * 4),
     ]
 
 
@@ -47,7 +48,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("kmers", C.c_uint64), ("inserted", C.c_uint64), ("distinct", C.c_uint64), ("reprobes", C.c_uint64),
         ("overflowed", C.c_uint64), ("regrows", C.c_uint64), ("bytes", C.c_uint64), ("seconds_count", C.c_double),
-        ("seconds_count_kernel", C.c_double), ("count_kernel_launches", C.c_uint64),
+        ("seconds_count_kernel", C.c_double), ("count_kernel_launches", C.c_uint64), ("seconds_drain", C.c_double),
     ]
 
 

@@ -17,21 +17,16 @@
 
 namespace jfk {
 
-constexpr int NT    = 512;          // threads per CTA of the counting kernel
-constexpr int BPT   = 32;           // input bytes classified per thread
-constexpr int WIN   = NT * BPT;     // 16384 bytes staged per window
-constexpr int HALO  = 256;          // bytes re-read from the previous tile
-constexpr int TILE  = WIN - HALO;   // 16128 new bytes per tile (multiple of 16)
+constexpr int HALO  = 256;          // bytes of the previous tile staged again in front of a tile
 constexpr int PRE   = 64;           // symbol slots kept in front of a window (>= k-1)
 constexpr int QSYM  = 36;           // symbols rolled per thread chunk (QSYM/4 odd: no bank conflicts)
-constexpr int NWARP = NT / 32;
 
 enum { ST_H = 0, ST_S = 1, ST_L = 2 };   // inside header line / inside sequence line / at line start
 constexpr uint32_t SYM_BREAK = 4;        // symbols 0..3 = A,C,G,T ; 4 = window reset
 
 // stats block indices
 enum { STAT_KMERS = 0, STAT_INSERTED, STAT_DISTINCT, STAT_REPROBES, STAT_OVERFLOWED,
-       STAT_FAILED, STAT_FAIL_DROPPED, STAT_OVF_FULL, STAT_ROUTE_DROPPED, STAT_MAXCOUNT, STAT_N };
+       STAT_FAILED, STAT_FAIL_DROPPED, STAT_OVF_FULL, STAT_ROUTE_DROPPED, STAT_MAXCOUNT, STAT_POOL_FULL, STAT_N };
 
 struct Carry {               // parser state handed from one batch to the next (device resident)
   uint32_t state;            // ST_* after the last byte of the previous batch
@@ -196,13 +191,11 @@ __device__ __forceinline__ uint64_t ovf_get(const TableDev& T, uint64_t slot_idx
 // ---------------------------------------------------------------------------------------
 struct LocalStats { uint32_t kmers, inserted, distinct, reprobes, failed; };
 
-template<int KW, int SB>
-__device__ __forceinline__ bool table_add(const TableDev& T, const uint64_t (&key)[KW], uint64_t pos_global,
-                                          uint64_t count, LocalStats& ls) {
-  const uint64_t base = pos_global & T.local_mask;
-  const u128 high = key_high<KW>(key, T.lsize);
+template<int SB>
+__device__ __forceinline__ bool table_add_hp(const TableDev& T, const uint64_t base, const u128 high,
+                                             uint64_t count, LocalStats& ls, const uint32_t first_probe = 0) {
   const uint32_t rb = T.rbits, fb = T.fbits;
-  uint64_t idx = base;
+  uint64_t idx = base + (first_probe ? tri(first_probe) : 0);
 
   if(SB == 32) {
     const uint32_t cb = 32 - fb;
@@ -211,7 +204,7 @@ __device__ __forceinline__ bool table_add(const TableDev& T, const uint64_t (&ke
     const uint64_t c_hi = count >> cb;
     uint32_t* tab = (uint32_t*)T.slots;
     const uint32_t kf0 = (uint32_t)(high.lo << rb);
-    for(uint32_t i = 0; i <= T.max_reprobe; ++i) {
+    for(uint32_t i = first_probe; i <= T.max_reprobe; ++i) {
       const uint32_t kf = kf0 | (i + 1);
       uint32_t old = atomicCAS(&tab[idx], 0u, kf | (c_lo << fb));
       if(old == 0u) { ls.distinct++; ls.reprobes += i; if(c_hi) ovf_add(T, idx, c_hi); return true; }
@@ -232,7 +225,7 @@ __device__ __forceinline__ bool table_add(const TableDev& T, const uint64_t (&ke
     const uint64_t c_hi = cb >= 64 ? 0 : (count >> cb);
     unsigned long long* tab = (unsigned long long*)T.slots;
     const uint64_t kf0 = high.lo << rb;
-    for(uint32_t i = 0; i <= T.max_reprobe; ++i) {
+    for(uint32_t i = first_probe; i <= T.max_reprobe; ++i) {
       const uint64_t kf = kf0 | (i + 1);
       unsigned long long old = atomicCAS(&tab[idx], 0ull, (unsigned long long)(kf | (c_lo << fb)));
       if(old == 0ull) { ls.distinct++; ls.reprobes += i; if(c_hi) ovf_add(T, idx, c_hi); return true; }
@@ -258,7 +251,7 @@ __device__ __forceinline__ bool table_add(const TableDev& T, const uint64_t (&ke
     // key field = (high << rb) | (i+1)  as a 128-bit value
     const uint64_t kf_lo0 = high.lo << rb;
     const uint64_t kf_hi  = rb ? ((high.hi << rb) | (high.lo >> (64 - rb))) : high.hi;
-    for(uint32_t i = 0; i <= T.max_reprobe; ++i) {
+    for(uint32_t i = first_probe; i <= T.max_reprobe; ++i) {
       const uint64_t kf_lo = kf_lo0 | (i + 1);
       u128 want; want.lo = kf_lo; want.hi = kf_hi | (c_lo << fhi);
       u128 zero; zero.lo = 0; zero.hi = 0;
@@ -277,6 +270,56 @@ __device__ __forceinline__ bool table_add(const TableDev& T, const uint64_t (&ke
     }
     return false;
   }
+}
+
+// R insertions of count 1 with the R first probes issued back to back, so that R L2/HBM
+// round trips overlap instead of running one after the other.  ok[r] = false -> hash full.
+template<int SB, int R>
+__device__ __forceinline__ void table_add_batch(const TableDev& T, const uint64_t (&base)[R], const u128 (&high)[R],
+                                                const bool (&valid)[R], bool (&ok)[R], LocalStats& ls) {
+  const uint32_t rb = T.rbits, fb = T.fbits;
+  if(SB == 32) {
+    uint32_t* tab = (uint32_t*)T.slots;
+    const uint32_t fmask = (1u << fb) - 1u, one = 1u << fb, cb = 32 - fb;
+    uint32_t old[R], kf[R];
+#pragma unroll
+    for(int r = 0; r < R; ++r) { kf[r] = (uint32_t)(high[r].lo << rb) | 1u; old[r] = valid[r] ? atomicCAS(&tab[base[r]], 0u, kf[r] | one) : 1u; }
+#pragma unroll
+    for(int r = 0; r < R; ++r) {
+      ok[r] = true;
+      if(!valid[r]) continue;
+      if(old[r] == 0u) ls.distinct++;
+      else if((old[r] & fmask) == kf[r]) {
+        uint32_t o2 = atomicAdd(&tab[base[r]], one);
+        if((((uint64_t)(o2 >> fb) + 1) >> cb) != 0) ovf_add(T, base[r], 1);
+      } else ok[r] = table_add_hp<SB>(T, base[r], high[r], 1, ls, 1);
+    }
+  } else if(SB == 64) {
+    unsigned long long* tab = (unsigned long long*)T.slots;
+    const uint64_t fmask = (1ull << fb) - 1ull, one = 1ull << fb; const uint32_t cb = 64 - fb;
+    unsigned long long old[R]; uint64_t kf[R];
+#pragma unroll
+    for(int r = 0; r < R; ++r) { kf[r] = (high[r].lo << rb) | 1ull; old[r] = valid[r] ? atomicCAS(&tab[base[r]], 0ull, (unsigned long long)(kf[r] | one)) : 1ull; }
+#pragma unroll
+    for(int r = 0; r < R; ++r) {
+      ok[r] = true;
+      if(!valid[r]) continue;
+      if(old[r] == 0ull) ls.distinct++;
+      else if((old[r] & fmask) == kf[r]) {
+        unsigned long long o2 = atomicAdd(&tab[base[r]], (unsigned long long)one);
+        if((((o2 >> fb) + 1) >> cb) != 0) ovf_add(T, base[r], 1);
+      } else ok[r] = table_add_hp<SB>(T, base[r], high[r], 1, ls, 1);
+    }
+  } else {
+#pragma unroll
+    for(int r = 0; r < R; ++r) ok[r] = valid[r] ? table_add_hp<SB>(T, base[r], high[r], 1, ls) : true;
+  }
+}
+
+template<int KW, int SB>
+__device__ __forceinline__ bool table_add(const TableDev& T, const uint64_t (&key)[KW], uint64_t pos_global,
+                                          uint64_t count, LocalStats& ls) {
+  return table_add_hp<SB>(T, pos_global & T.local_mask, key_high<KW>(key, T.lsize), count, ls);
 }
 
 template<int KW>

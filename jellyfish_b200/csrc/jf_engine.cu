@@ -69,8 +69,17 @@ struct Table {
 
 }  // namespace
 
+struct PartState {
+  uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0;
+  DevBuf pool, dir, order, pool_next, cta_chunk, cta_fill, spill_keys, spill_counts, spill_n, hist, start, cursor, unit_cursor;
+  uint64_t spill_cap = 0;
+  uint64_t bound_chunks = 0;     // host-side upper bound of chunks in use
+  bool pending = false;          // records sit in the pool
+};
+
 struct jfgpu_engine {
   jfgpu_params p;
+  PartState part;
   int device = 0;
   unsigned k = 0, kw = 1, nbytes = 0, shard_bits = 0;
   cudaStream_t cs = nullptr, hs = nullptr;
@@ -98,6 +107,7 @@ struct jfgpu_engine {
   std::vector<cudaEvent_t> kev;             // event pairs around count_kernel launches
   size_t kev_used = 0;
   double kernel_ms = 0; uint64_t kernel_launches = 0;
+  double drain_ms = 0; cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
   int count_smem = 0;
 };
 
@@ -198,7 +208,10 @@ int dispatch(jfgpu_engine* e, unsigned kw, unsigned sb, F&& f) {
   return fail(e, JFGPU_ERR_ARG, "unsupported key/slot combination");
 }
 
-size_t count_smem_bytes(unsigned nbytes) { return ((sizeof(CountSmem) + 15) & ~(size_t)15) + (size_t)nbytes * 256 * 8; }
+template<int NTH>
+size_t count_smem_bytes(unsigned nbytes, size_t stage_bytes) {
+  return ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15) + (size_t)nbytes * 256 * 8 + (stage_bytes ? PMAX * 4 + stage_bytes : 0);
+}
 
 int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
   if(n_tiles <= e->scratch_tiles) return JFGPU_OK;
@@ -211,17 +224,205 @@ int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
   return JFGPU_OK;
 }
 
+// ---- partitioned insertion: geometry, pool, drain --------------------------------------
+PartDev part_dev(const jfgpu_engine* e) {
+  PartDev d;
+  memset(&d, 0, sizeof(d));
+  const PartState& ps = e->part;
+  d.P = ps.P; d.region_bits = ps.region_bits; d.rec_bytes = ps.rec_bytes; d.cap = ps.cap; d.flush_min = ps.flush_min;
+  d.chunk_recs = CHUNK_BYTES / std::max(1u, ps.rec_bytes); d.n_chunks = ps.n_chunks; d.stage_bytes = ps.stage_bytes;
+  d.row_words = ps.cap * ps.rec_bytes / 4 + 1;
+  d.pool = ps.pool.as<uint8_t>(); d.pool_next = ps.pool_next.as<unsigned int>(); d.dir = ps.dir.as<uint2>();
+  d.cta_chunk = ps.cta_chunk.as<uint32_t>(); d.cta_fill = ps.cta_fill.as<uint32_t>();
+  d.spill_keys = ps.spill_keys.as<uint64_t>(); d.spill_counts = ps.spill_counts.as<uint64_t>();
+  d.spill_n = ps.spill_n.as<unsigned long long>(); d.spill_cap = ps.spill_cap;
+  return d;
+}
+
+// Decide whether (and how) the current table is filled region by region.
+void part_configure(jfgpu_engine* e) {
+  PartState& ps = e->part;
+  const Table& t = e->tab;
+  ps.P = 0;
+  if(e->p.no_partition || t.bytes() < ((size_t)(e->p.part_min_mb ? e->p.part_min_mb : 256) << 20)) return;       // small tables live in L2 anyway
+  uint32_t P = 256;
+  const size_t region_target = (size_t)(getenv("JFGPU_REGION_MB") ? atoi(getenv("JFGPU_REGION_MB")) : 32) << 20;
+  while(P < (uint32_t)PMAX && (t.bytes() / P) > region_target) P <<= 1;
+  const uint32_t stage_bytes = e->kw == 1 ? (128u << 10) : (64u << 10);
+  for(;; P >>= 1) {
+    if(P < 64 || t.local_lsize < 8 || (1u << (t.local_lsize - 8)) < P) return;
+    const uint32_t region_bits = t.local_lsize - ceil_log2(P);
+    const uint32_t bits = region_bits + t.hb;
+    const uint32_t rec = bits <= 32 ? 4 : bits <= 64 ? 8 : bits <= 128 ? 16 : 0;
+    if(!rec) return;
+    const uint32_t cap = stage_bytes / P / rec;
+    if(cap < 8) continue;
+    ps.P = P; ps.region_bits = region_bits; ps.rec_bytes = rec; ps.cap = cap; ps.flush_min = std::max(1u, cap / 4);
+    ps.stage_bytes = P * (cap * rec + 4);      // rows padded by one word
+    return;
+  }
+}
+
+int part_alloc(jfgpu_engine* e) {
+  PartState& ps = e->part;
+  if(ps.pool.p) return JFGPU_OK;
+  size_t free_b = 0, total_b = 0;
+  CUDA_OK(e, cudaMemGetInfo(&free_b, &total_b));
+  size_t want = e->p.pool_bytes ? (size_t)e->p.pool_bytes : std::min<size_t>((size_t)(free_b * 0.6), (size_t)64 << 30);
+  const size_t floor_b = (size_t)e->n_sm * ps.P * CHUNK_BYTES * 2;        // every CTA keeps one open chunk per region
+  if(want < floor_b) want = floor_b;
+  ps.n_chunks = (uint32_t)std::min<size_t>(want / CHUNK_BYTES, 0xFFFFFFF0u);
+  ps.spill_cap = (uint64_t)16 << 20;
+  bool ok = ps.pool.alloc((size_t)ps.n_chunks * CHUNK_BYTES) == cudaSuccess && ps.dir.alloc((size_t)ps.n_chunks * 8) == cudaSuccess &&
+            ps.order.alloc((size_t)ps.n_chunks * 4) == cudaSuccess && ps.pool_next.alloc(8) == cudaSuccess &&
+            ps.cta_chunk.alloc((size_t)e->n_sm * PMAX * 4) == cudaSuccess && ps.cta_fill.alloc((size_t)e->n_sm * PMAX * 4) == cudaSuccess &&
+            ps.spill_keys.alloc(ps.spill_cap * 8 * e->kw) == cudaSuccess && ps.spill_counts.alloc(ps.spill_cap * 8) == cudaSuccess &&
+            ps.spill_n.alloc(8) == cudaSuccess && ps.hist.alloc(PMAX * 4) == cudaSuccess && ps.start.alloc(PMAX * 4) == cudaSuccess &&
+            ps.cursor.alloc(PMAX * 4) == cudaSuccess && ps.unit_cursor.alloc(8) == cudaSuccess;
+  if(!ok) { cudaGetLastError(); return fail(e, JFGPU_ERR_NOMEM, "device allocation of the record pool failed"); }
+  CUDA_OK(e, cudaMemsetAsync(ps.pool_next.p, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(ps.spill_n.p, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(ps.cta_chunk.p, 0xFF, ps.cta_chunk.bytes, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(ps.cta_fill.p, 0, ps.cta_fill.bytes, e->cs));
+  ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
+  ps.pending = false;
+  return JFGPU_OK;
+}
+
+void part_release(jfgpu_engine* e) {
+  PartState& ps = e->part;
+  ps.pool.free(); ps.dir.free(); ps.order.free(); ps.pool_next.free(); ps.cta_chunk.free(); ps.cta_fill.free();
+  ps.spill_keys.free(); ps.spill_counts.free(); ps.spill_n.free(); ps.hist.free(); ps.start.free(); ps.cursor.free(); ps.unit_cursor.free();
+  ps.n_chunks = 0; ps.pending = false;
+}
+
+int regrow(jfgpu_engine* e);
+int read_stats(jfgpu_engine* e);
+
+// Insert everything that sits in the record pool (K1b), region by region, then the spill list.
+// With regrow enabled the chunks go in groups small enough for the failure list, and the
+// failure counter is checked after each group (hash_counter::add -> handle_full_ary).
+int part_drain(jfgpu_engine* e, cudaStream_t st) {
+  PartState& ps = e->part;
+  if(!ps.P || !ps.pool.p || !ps.pending) return JFGPU_OK;
+  PartDev pd = part_dev(e);
+  const int g = e->n_sm * 4;
+  if(!e->ev_d0) { cudaEventCreate(&e->ev_d0); cudaEventCreate(&e->ev_d1); }
+  cudaEventRecord(e->ev_d0, st);
+  close_chunks_kernel<<<g, 256, 0, st>>>(pd, (uint32_t)e->n_sm); JF_LAUNCHED();
+  CUDA_OK(e, cudaMemsetAsync(ps.hist.p, 0, PMAX * 4, st));
+  chunk_hist_kernel<<<g, 256, 0, st>>>(pd, ps.hist.as<uint32_t>()); JF_LAUNCHED();
+  chunk_scan_kernel<<<1, 1024, 0, st>>>(pd.P, ps.hist.as<uint32_t>(), ps.start.as<uint32_t>(), ps.cursor.as<uint32_t>()); JF_LAUNCHED();
+  chunk_scatter_kernel<<<g, 256, 0, st>>>(pd, ps.cursor.as<uint32_t>(), ps.order.as<uint32_t>()); JF_LAUNCHED();
+  CUDA_OK(e, cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st));
+  // geometry the records were written with (a regrow in the middle changes e->tab)
+  const TableDev T0 = table_dev(e, e->tab);
+  const unsigned sb0 = e->tab.slot_bits;
+  const bool careful = e->p.allow_regrow != 0;
+  unsigned int n_units = 0;
+  if(careful) {
+    CUDA_OK(e, cudaMemcpyAsync(&n_units, ps.pool_next.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(e, cudaStreamSynchronize(st));
+    n_units = std::min(n_units, ps.n_chunks);
+  }
+  const unsigned group = careful ? (unsigned)std::max<uint64_t>(1, e->fail_cap / 2 / pd.chunk_recs) : 0xFFFFFFFFu;
+  int rc = JFGPU_OK;
+  DevBuf old_inv;     // inverse tables of the geometry the records belong to, once the table has been rebuilt
+  unsigned done = 0;
+  bool rebuilt = false;
+  do {
+    const unsigned upto = careful ? (unsigned)std::min<uint64_t>((uint64_t)done + group, n_units) : 0xFFFFFFFFu;
+    cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st);
+    TableDev T = table_dev(e, e->tab);
+    if(!rebuilt) {
+      rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
+        insert_chunks_kernel<decltype(KW)::value, decltype(SB)::value><<<e->n_sm * 2, 512, 0, st>>>(
+            T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
+        return JFGPU_OK;
+      });
+    } else {
+      const size_t smem = (size_t)e->nbytes * 256 * 8 * 2;
+      rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
+        auto kern = rehash_chunks_kernel<decltype(KW)::value, decltype(SB)::value>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<e->n_sm, 512, smem, st>>>(T, T0, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto,
+                                            old_inv.as<uint64_t>(), e->tab.lut.as<uint64_t>(), e->nbytes);
+        return JFGPU_OK;
+      });
+    }
+    if(rc) break;
+    JF_LAUNCHED();
+    if(!careful) break;
+    done = upto;
+    if(st != e->cs) cudaStreamSynchronize(st);
+    rc = read_stats(e);
+    if(rc) break;
+    if(e->h_stats[STAT_FAILED]) {
+      if(!rebuilt) {            // keep a copy of the inverse tables the pending records were written against
+        if(old_inv.alloc(e->tab.inv_lut.bytes) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "device allocation failed"); break; }
+        cudaMemcpyAsync(old_inv.p, e->tab.inv_lut.p, e->tab.inv_lut.bytes, cudaMemcpyDeviceToDevice, e->cs);
+        cudaStreamSynchronize(e->cs);
+        rebuilt = true;
+      }
+      rc = regrow(e);
+      if(rc) break;
+    }
+  } while(done < n_units);
+  (void)sb0;
+  if(!rc) {
+    // the spilled keys carry full keys: plain insertion into whatever the table is now
+    TableDev T = table_dev(e, e->tab);
+    const size_t smem = (size_t)e->nbytes * 256 * 8;
+    rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
+      auto kern = insert_spill_kernel<decltype(KW)::value, decltype(SB)::value>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<e->n_sm * 2, 256, smem, st>>>(T, e->tab.lut.as<uint64_t>(), e->nbytes, pd);
+      return JFGPU_OK;
+    });
+    if(!rc) JF_LAUNCHED();
+  }
+  cudaMemsetAsync(ps.pool_next.p, 0, 8, st);
+  cudaMemsetAsync(ps.spill_n.p, 0, 8, st);
+  cudaEventRecord(e->ev_d1, st);
+  cudaStreamSynchronize(st);
+  { float ms = 0; if(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1) == cudaSuccess) e->drain_ms += ms; else cudaGetLastError(); }
+  ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
+  ps.pending = false;
+  if(rebuilt) { cudaStreamSynchronize(st); old_inv.free(); part_configure(e); if(!e->part.P) part_release(e); }
+  if(rc) return rc;
+  CUDA_OK(e, cudaGetLastError());
+  return JFGPU_OK;
+}
+
 // One batch of device-resident text through K0a, K0b, K1 on `stream`.
 int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, cudaStream_t stream,
               int mode, uint64_t* route_keys, unsigned long long* route_counts, uint64_t route_cap) {
   if(n == 0) return JFGPU_OK;
-  const uint64_t n_tiles = (n + TILE - 1) / TILE;
-  int rc = ensure_scratch(e, n_tiles);
+  PartState& ps = e->part;
+  const bool part = mode == 0 && ps.P != 0;
+  int rc;
+  if(part) {
+    rc = part_alloc(e);
+    if(rc) return rc;
+    // conservative host-side bound on pool usage: one record per input byte at most
+    const uint64_t need = (n * ps.rec_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES + 1;
+    if(ps.bound_chunks + need > ps.n_chunks) {
+      rc = part_drain(e, stream);
+      if(rc) return rc;
+      if(!e->part.P) return run_batch(e, dev, n, n_look, stream, mode, route_keys, route_counts, route_cap);
+    }
+    if(ps.bound_chunks + need > ps.n_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch");
+    ps.bound_chunks += need;
+    ps.pending = true;
+  }
+  const uint32_t tile = (part ? 1024 : 512) * 32 - HALO;
+  const uint64_t n_tiles = (n + tile - 1) / tile;
+  rc = ensure_scratch(e, n_tiles);
   if(rc) return rc;
   const int g0 = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 8);
-  nl_scan_kernel<<<g0, 256, 0, stream>>>(dev, n, n_tiles, e->nlA.as<long long>(), e->nlB.as<long long>());
+  nl_scan_kernel<<<g0, 256, 0, stream>>>(dev, n, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>());
   JF_LAUNCHED();
-  tile_state_kernel<<<1, 1024, 0, stream>>>(dev, n_tiles, e->nlA.as<long long>(), e->nlB.as<long long>(),
+  tile_state_kernel<<<1, 1024, 0, stream>>>(dev, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>(),
                                             e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
   JF_LAUNCHED();
   CountArgs a;
@@ -234,22 +435,27 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode;
   a.T = table_dev(e, e->tab);
   a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
-  const size_t smem = count_smem_bytes(e->nbytes);
-  rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
-    auto kern = count_kernel<decltype(KW)::value, decltype(SB)::value>;
+  PartDev pd = part_dev(e);
+  auto launch = [&](auto kern, int nth, size_t smem, bool one_per_sm) -> int {
     cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(c));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // persistent CTAs: exactly as many as are resident at once (a multiple of the SM count)
     int per_sm = 1;
-    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    if(!one_per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nth, smem) != cudaSuccess || per_sm < 1)) { cudaGetLastError(); per_sm = 1; }
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * per_sm);
     if(e->kev_used + 2 > e->kev.size()) { cudaEvent_t a0, a1; cudaEventCreate(&a0); cudaEventCreate(&a1); e->kev.push_back(a0); e->kev.push_back(a1); }
     cudaEventRecord(e->kev[e->kev_used], stream);
-    kern<<<grid, NT, smem, stream>>>(a);
+    kern<<<grid, nth, smem, stream>>>(a, pd);
     cudaEventRecord(e->kev[e->kev_used + 1], stream);
     e->kev_used += 2;
     return JFGPU_OK;
+  };
+  rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
+    constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
+    if(part)      return launch(count_kernel<kw, sb, 2, 1024>, 1024, count_smem_bytes<1024>(e->nbytes, ps.stage_bytes), true);
+    if(mode == 1) return launch(count_kernel<kw, sb, 1, 512>, 512, count_smem_bytes<512>(e->nbytes, 0), false);
+    return launch(count_kernel<kw, sb, 0, 512>, 512, count_smem_bytes<512>(e->nbytes, 0), false);
   });
   if(rc) return rc;
   JF_LAUNCHED();
@@ -383,16 +589,21 @@ int rebuild_table(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int ol
     rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, false, &n);
     if(!rc) rc = insert_keys_into(e, nt, s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), n, e->cs);
   }
-  if(!rc && n_failed)
-    rc = insert_keys_into(e, nt, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
   cudaStreamSynchronize(e->cs);
   s.free_all();
   if(rc) { nt.release(); return rc; }
+  // the moved entries are not new k-mer occurrences; the failed ones (below) are
+  CUDA_OK(e, cudaMemcpyAsync(e->stats.as<unsigned long long>() + STAT_INSERTED, &inserted_before, 8, cudaMemcpyHostToDevice, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  if(n_failed) {
+    rc = insert_keys_into(e, nt, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
+    cudaStreamSynchronize(e->cs);
+    if(rc) { nt.release(); return rc; }
+  }
   // (each table owns its counter-carry side table: the old one dies with the old slots)
   e->tab.release();
   e->tab = nt;
-  CUDA_OK(e, cudaMemcpyAsync(e->stats.as<unsigned long long>() + STAT_INSERTED, &inserted_before, 8, cudaMemcpyHostToDevice, e->cs));
-  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  if(!e->part.pending) { part_configure(e); if(!e->part.P) part_release(e); }
   return JFGPU_OK;
 }
 
@@ -558,6 +769,7 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   memset(e->h_stats, 0, STAT_N * 8);
   int rc = table_setup(e, e->tab, lsize, M);
   if(rc) return bail(rc);
+  part_configure(e);
   rc = reset_carry(e, e->cs);
   if(rc) return bail(rc);
   *out = e;
@@ -570,6 +782,7 @@ void jfgpu_destroy(jfgpu_handle e) {
   if(e->cs) cudaStreamSynchronize(e->cs);
   if(e->hs) cudaStreamSynchronize(e->hs);
   e->tab.release();
+  part_release(e);
   e->stats.free();
   for(int i = 0; i < 2; ++i) {
     e->carry[i].free(); e->fail_keys[i].free(); e->fail_counts[i].free(); e->stage[i].free();
@@ -627,11 +840,11 @@ int jfgpu_feed_device(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t 
   const uint8_t* p = (const uint8_t*)dev_bytes;
   cudaEventRecord(e->ev_t0, st);
   for(size_t off = 0; off < n; ) {
-    size_t len = std::min(e->batch_bytes, n - off);
+    size_t len = std::min(e->part.P ? std::max<size_t>(e->batch_bytes, (size_t)512 << 20) : e->batch_bytes, n - off);
     rc = run_batch(e, p + off, len, n - off, st, 0, nullptr, nullptr, 0);
     if(rc) return rc;
     off += len;
-    if(e->p.allow_regrow) {          // the failure list only holds two batches
+    if(e->p.allow_regrow && !e->part.P) {          // the failure list only holds two batches
       if(st != e->cs) CUDA_OK(e, cudaStreamSynchronize(st));
       rc = check_after_batches(e);
       if(rc) return rc;
@@ -740,7 +953,15 @@ int jfgpu_clear(jfgpu_handle e) {
   CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_keys.p, 0, e->ovf_size * 8, e->cs));
   CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_vals.p, 0, e->ovf_size * 8, e->cs));
   CUDA_OK(e, cudaMemsetAsync(e->stats.p, 0, STAT_N * 8, e->cs));
-  e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0;
+  if(e->part.pool.p) {
+    CUDA_OK(e, cudaMemsetAsync(e->part.pool_next.p, 0, 8, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->part.spill_n.p, 0, 8, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->part.cta_chunk.p, 0xFF, e->part.cta_chunk.bytes, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->part.cta_fill.p, 0, e->part.cta_fill.bytes, e->cs));
+    e->part.bound_chunks = (uint64_t)e->n_sm * e->part.P;
+    e->part.pending = false;
+  }
+  e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0; e->drain_ms = 0;
   e->eff_val_len = e->p.counter_len;
   return reset_carry(e, e->cs);
 }
@@ -761,6 +982,7 @@ int jfgpu_get_stats(jfgpu_handle e, jfgpu_stats* s) {
   resolve_kernel_events(e);
   s->seconds_count_kernel = e->kernel_ms * 1e-3;
   s->count_kernel_launches = e->kernel_launches;
+  s->seconds_drain = e->drain_ms * 1e-3;
   return JFGPU_OK;
 }
 
@@ -768,10 +990,13 @@ int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
   if(!e) return JFGPU_ERR_ARG;
   cudaSetDevice(e->device);
   CUDA_OK(e, cudaStreamSynchronize(e->hs));
+  int rc = part_drain(e, e->cs);
+  if(rc) return rc;
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
   CUDA_OK(e, cudaGetLastError());
-  int rc = check_after_batches(e);
+  rc = check_after_batches(e);
   if(rc) return rc;
+  if(e->h_stats[STAT_POOL_FULL]) return fail(e, JFGPU_ERR_NOMEM, "internal: k-mer record pool overflow");
   rc = direct_index_fixup(e);
   if(rc) return rc;
   if(s) return jfgpu_get_stats(e, s);
@@ -853,6 +1078,7 @@ int jfgpu_lookup(jfgpu_handle e, const uint64_t* keys, size_t n, uint64_t* vals)
   if(!e || (n && (!keys || !vals))) return JFGPU_ERR_ARG;
   if(n == 0) return JFGPU_OK;
   cudaSetDevice(e->device);
+  { int rc0 = jfgpu_finish(e, nullptr); if(rc0) return rc0; }
   DevBuf dk, dv;
   CUDA_OK(e, dk.alloc(n * 8 * e->kw));
   CUDA_OK(e, dv.alloc(n * 8));

@@ -19,7 +19,7 @@ namespace jfk {
 // K0a: per tile t (bytes [t*TILE, (t+1)*TILE)), position of the last '\n' in
 //      A = [start, start+TILE-HALO) and in B = [start+TILE-HALO, start+TILE); -1 if none.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) nl_scan_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t n_tiles,
+__global__ void __launch_bounds__(256) nl_scan_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t n_tiles, uint32_t TILE,
                                                       long long* __restrict__ nlA, long long* __restrict__ nlB) {
   __shared__ long long sA[8], sB[8];
   for(uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t line_start_state(const uint8_t* in, uint64_t
 //      before h_t:  max(nlA[t-1], max_{u<t-1} max(nlA[u], nlB[u])).  One CTA, chunked scan:
 //      the thread that owns tile u produces the state of window u+1.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tile_state_kernel(const uint8_t* __restrict__ in, uint64_t n_tiles,
+__global__ void __launch_bounds__(1024) tile_state_kernel(const uint8_t* __restrict__ in, uint64_t n_tiles, uint32_t TILE,
                                                           const long long* __restrict__ nlA, const long long* __restrict__ nlB,
                                                           const Carry* __restrict__ carry_in, uint8_t* __restrict__ tile_state) {
   __shared__ long long part[1024];
@@ -204,90 +204,171 @@ __device__ void backfill_symbols(const uint8_t* in, uint64_t n, const Carry* cin
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: the fused counting kernel.  Persistent CTAs, double-buffered TMA windows.
+// K1: the fused counting kernel.  Persistent CTAs; one TMA bulk copy stages a window of
+//     NTH*32 bytes (HALO bytes of the previous tile + the tile); the copy of the NEXT window is
+//     issued as soon as every thread holds its 32 bytes in registers, so it overlaps the rest.
+//
+//     MODE 0  insert/increment straight into the table (random HBM access)
+//     MODE 1  bucket keys by owning shard for the multi-GPU all-to-all
+//     MODE 2  PARTITION: turn every k-mer into a compact record (position-in-region : explicit
+//             key bits), stage records per table region in shared memory and append them to
+//             per-CTA chunk lists in HBM.  K1b (insert_chunks_kernel) then fills the table one
+//             L2-sized region at a time, so the atomics hit L2 instead of random DRAM pages.
 // ---------------------------------------------------------------------------------------
-struct __align__(16) CountSmem {
-  uint8_t  win[2][WIN];            // TMA destinations
-  uint8_t  sym[PRE + WIN + 16];    // carried prefix + compacted symbols of the window
-  uint64_t bar[2];
-  uint32_t warp_fn[NWARP];
-  uint32_t warp_cnt[NWARP];
-  uint32_t idx0, nsym, halo_break, total_state;
-  unsigned long long red[8];
+constexpr int PMAX        = 2048;          // partitions (table regions) at most
+constexpr int CHUNK_BYTES = 8192;          // granule of the record pool
+constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
+constexpr int SUBROUNDS   = 4;             // staging flushes per rolled chunk of QSYM symbols
+
+struct PartDev {
+  uint32_t  P;              // number of regions (power of two)
+  uint32_t  region_bits;    // log2(slots per region)
+  uint32_t  rec_bytes;      // 4, 8 or 16
+  uint32_t  cap;            // staging capacity per region, records
+  uint32_t  flush_min;      // flush a staging buffer holding at least this many records
+  uint32_t  chunk_recs;     // records per chunk
+  uint32_t  n_chunks;       // chunks in the pool
+  uint32_t  stage_bytes;    // shared-memory staging bytes per CTA
+  uint32_t  row_words;      // 32-bit words per staging row = cap * rec_bytes / 4 + 1 (odd: no bank conflicts)
+  uint8_t*  pool;
+  unsigned int* pool_next;  // allocation cursor
+  uint2*    dir;            // per chunk: { region, records } written when the chunk is closed
+  uint32_t* cta_chunk;      // [grid][P] open chunk of each CTA for each region
+  uint32_t* cta_fill;       // [grid][P] records already in it
+  uint64_t* spill_keys;     // records that found their staging buffer full: inserted directly later
+  uint64_t* spill_counts;
+  unsigned long long* spill_n;
+  uint64_t  spill_cap;
 };
 
-template<int KW, int SB>
-__global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
+template<int NTH>
+struct __align__(16) CountSmemT {
+  uint8_t  win[NTH * 32];            // TMA destination
+  uint8_t  sym[PRE + NTH * 32 + 16]; // carried prefix + compacted symbols of the window
+  uint64_t bar;
+  uint32_t warp_fn[NTH / 32];
+  uint32_t warp_cnt[NTH / 32];
+  uint32_t idx0, nsym, halo_break, total_state;
+  unsigned long long part[NTH / 32][4];
+};
+
+__device__ __forceinline__ void store_rec(uint8_t* base, uint32_t rec_bytes, uint64_t idx, u128 r) {
+  if(rec_bytes == 4) reinterpret_cast<uint32_t*>(base)[idx] = (uint32_t)r.lo;
+  else if(rec_bytes == 8) reinterpret_cast<uint64_t*>(base)[idx] = r.lo;
+  else { reinterpret_cast<uint64_t*>(base)[2 * idx] = r.lo; reinterpret_cast<uint64_t*>(base)[2 * idx + 1] = r.hi; }
+}
+__device__ __forceinline__ u128 load_rec(const uint8_t* base, uint32_t rec_bytes, uint64_t idx) {
+  u128 r; r.hi = 0;
+  if(rec_bytes == 4) r.lo = reinterpret_cast<const uint32_t*>(base)[idx];
+  else if(rec_bytes == 8) r.lo = reinterpret_cast<const uint64_t*>(base)[idx];
+  else { r.lo = reinterpret_cast<const uint64_t*>(base)[2 * idx]; r.hi = reinterpret_cast<const uint64_t*>(base)[2 * idx + 1]; }
+  return r;
+}
+
+// Append n staged records (32-bit words at `stage`) of region p to this CTA's chunk list (one thread).
+__device__ __forceinline__ void flush_region(const PartDev& pd, uint32_t p, const uint32_t* stage, uint32_t n,
+                                             uint32_t* my_chunk, uint32_t* my_fill, unsigned long long* stats) {
+  uint32_t chunk = my_chunk[p], fill = my_fill[p];
+  const uint32_t rw = pd.rec_bytes >> 2;
+  uint32_t done = 0;
+  while(done < n) {
+    if(chunk == NO_CHUNK || fill == pd.chunk_recs) {
+      if(chunk != NO_CHUNK) pd.dir[chunk] = make_uint2(p, fill);          // close the full chunk
+      uint32_t c = atomicAdd(pd.pool_next, 1u);
+      if(c >= pd.n_chunks) { atomicAdd(&stats[STAT_POOL_FULL], 1ull); chunk = NO_CHUNK; fill = 0; break; }
+      chunk = c; fill = 0;
+    }
+    const uint32_t take = min(n - done, pd.chunk_recs - fill);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(pd.pool + (size_t)chunk * CHUNK_BYTES) + (size_t)fill * rw;
+    const uint32_t* src = stage + done * rw;
+    const uint32_t nw = take * rw;
+    for(uint32_t j = 0; j < nw; ++j) dst[j] = src[j];
+    fill += take; done += take;
+  }
+  my_chunk[p] = chunk; my_fill[p] = fill;
+}
+
+template<int KW, int SB, int MODE, int NTH>
+__global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const CountArgs a, const PartDev pd) {
+  constexpr int WINB = NTH * 32;
+  constexpr int TILEB = WINB - HALO;
+  constexpr int NW = NTH / 32;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  CountSmem& sm = *reinterpret_cast<CountSmem*>(smem_raw);
-  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(CountSmem) + 15) & ~(size_t)15));
+  CountSmemT<NTH>& sm = *reinterpret_cast<CountSmemT<NTH>*>(smem_raw);
+  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15));
+  // MODE 2 only: staging counters and buffers behind the hash tables
+  uint32_t* st_cnt = reinterpret_cast<uint32_t*>(lut + a.nbytes * 256);
+  uint32_t* st_buf = st_cnt + PMAX;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t k = a.k;
   const uint64_t n = a.n;
 
-  // hash tables -> shared memory
-  for(uint32_t i = tid; i < a.nbytes * 256u; i += NT) lut[i] = a.lut[i];
-  if(tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
+  for(uint32_t i = tid; i < a.nbytes * 256u; i += NTH) lut[i] = a.lut[i];
+  if(MODE == 2) for(uint32_t p = tid; p < pd.P; p += NTH) st_cnt[p] = 0;
+  if(tid == 0) mbar_init(&sm.bar, 1);
   __syncthreads();
+  uint32_t* my_chunk = MODE == 2 ? pd.cta_chunk + (size_t)blockIdx.x * pd.P : nullptr;
+  uint32_t* my_fill  = MODE == 2 ? pd.cta_fill + (size_t)blockIdx.x * pd.P : nullptr;
 
-  // issue the TMA copy of window t into buffer b (thread 0 only)
-  auto issue = [&](uint64_t t, int b) {
-    long long h = (long long)(t * (uint64_t)TILE) - HALO;
+  auto issue = [&](uint64_t t) {       // TMA copy of window t (thread 0 only)
+    long long h = (long long)(t * (uint64_t)TILEB) - HALO;
     long long from = h < 0 ? 0 : h;
     uint64_t avail = n - (uint64_t)from;
-    uint64_t want = (uint64_t)((h + WIN) - from);
+    uint64_t want = (uint64_t)((h + WINB) - from);
     uint32_t bytes = (uint32_t)((avail < want ? avail : want) & ~(uint64_t)15);
-    if(bytes) {
-      mbar_expect_tx(&sm.bar[b], bytes);
-      tma_load_1d(&sm.win[b][from - h], a.in + from, bytes, &sm.bar[b]);
-    } else {
-      mbar_arrive(&sm.bar[b]);
+    if(bytes) { mbar_expect_tx(&sm.bar, bytes); tma_load_1d(&sm.win[from - h], a.in + from, bytes, &sm.bar); }
+    else mbar_arrive(&sm.bar);
+  };
+  // staging flush (MODE 2): every region holding >= flush_min records (or all when `all`)
+  auto flush_pass = [&](bool all) {
+    __syncthreads();
+    for(uint32_t p = tid; p < pd.P; p += NTH) {
+      const uint32_t c = min(st_cnt[p], pd.cap);
+      if(c && (all || c >= pd.flush_min)) {
+        flush_region(pd, p, st_buf + (size_t)p * pd.row_words, c, my_chunk, my_fill, a.T.stats);
+        st_cnt[p] = 0;
+      } else if(st_cnt[p] > pd.cap) st_cnt[p] = pd.cap;
     }
+    __syncthreads();
   };
 
   LocalStats ls = { 0, 0, 0, 0, 0 };
-  uint32_t phase_bits = 0;          // bit b = parity to wait for on buffer b
-  int buf = 0;
+  uint32_t phase = 0;
   uint64_t t = blockIdx.x;
-  if(t < a.n_tiles && tid == 0) issue(t, 0);
+  if(t < a.n_tiles && tid == 0) issue(t);
 
   const uint64_t kmask_hi = (k * 2) % 64 ? ((1ull << ((k * 2) % 64)) - 1ull) : ~0ull;   // mask of the top key word
-  for(; t < a.n_tiles; t += gridDim.x, buf ^= 1) {
-    const uint64_t tn = t + gridDim.x;
-    if(tn < a.n_tiles && tid == 0) issue(tn, buf ^ 1);
-
-    const long long h = (long long)(t * (uint64_t)TILE) - HALO;      // global position of window byte 0
-    const long long wend_ll = (long long)n < h + WIN ? (long long)n : h + WIN;
-    // tail bytes that the 16-byte granular TMA copy left out
-    {
+  for(; t < a.n_tiles; t += gridDim.x) {
+    const long long h = (long long)(t * (uint64_t)TILEB) - HALO;      // global position of window byte 0
+    const long long wend_ll = (long long)n < h + WINB ? (long long)n : h + WINB;
+    {   // tail bytes that the 16-byte granular TMA copy left out
       long long from = h < 0 ? 0 : h;
       long long copied = ((wend_ll - from) & ~15ll);
       long long g = from + copied + tid;
-      if(tid < 16 && g < wend_ll) sm.win[buf][g - h] = a.in[g];
+      if(tid < 16 && g < wend_ll) sm.win[g - h] = a.in[g];
     }
-    mbar_wait(&sm.bar[buf], (phase_bits >> buf) & 1u);
-    phase_bits ^= 1u << buf;
+    mbar_wait(&sm.bar, phase);
+    phase ^= 1;
     __syncthreads();
 
-    // ---- phase B: classify 32 bytes per thread, build the state transition function ----
-    const uint8_t* wb = sm.win[buf];
+    // ---- phase B: 32 bytes per thread into registers, state transition function ----
     uint32_t w[8];
     {
-      const uint4* p4 = reinterpret_cast<const uint4*>(wb + tid * BPT);
+      const uint4* p4 = reinterpret_cast<const uint4*>(sm.win + tid * 32);
       uint4 x0 = p4[0], x1 = p4[1];
       w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
     }
-    const long long g0 = h + (long long)tid * BPT;      // global position of this thread's first byte
-    int vlo = g0 < 0 ? (int)(-g0 < BPT ? -g0 : BPT) : 0;
-    int vhi = (wend_ll - g0) < 0 ? 0 : ((wend_ll - g0) > BPT ? BPT : (int)(wend_ll - g0));
+    const long long g0 = h + (long long)tid * 32;       // global position of this thread's first byte
+    int vlo = g0 < 0 ? (int)(-g0 < 32 ? -g0 : 32) : 0;
+    int vhi = (wend_ll - g0) < 0 ? 0 : ((wend_ll - g0) > 32 ? 32 : (int)(wend_ll - g0));
     if(vhi < vlo) vhi = vlo;
 
     uint32_t f;
     {
       uint32_t st = ST_L; bool seen_nl = false;
 #pragma unroll
-      for(int i = 0; i < BPT; ++i) {
+      for(int i = 0; i < 32; ++i) {
         if(i >= vlo && i < vhi) {
           uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
           if(b == '\n') { st = ST_L; seen_nl = true; }
@@ -297,7 +378,6 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
       f = seen_nl ? fn_const(st) : ((uint32_t)ST_H | ((uint32_t)ST_S << 2) | (st << 4));
       if(vhi == vlo) f = FN_ID;
     }
-    // block-wide exclusive scan of the transition functions
     uint32_t inc = f;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1) {
@@ -306,13 +386,15 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
     }
     if(lane == 31) sm.warp_fn[warp] = inc;
     __syncthreads();
+    // every thread holds its bytes: the window buffer is free, fetch the next window now
+    { const uint64_t tn = t + gridDim.x; if(tn < a.n_tiles && tid == 0) issue(tn); }
     uint32_t entry = (t == 0) ? a.carry_in->state : (uint32_t)a.tile_state[t];
     uint32_t wpre = FN_ID;
     for(int i = 0; i < warp; ++i) wpre = fn_compose(wpre, sm.warp_fn[i]);
     uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
     if(lane == 0) excl = FN_ID;
     uint32_t st_in = fn_apply(fn_compose(wpre, excl), entry);
-    if(tid == NT - 1) sm.total_state = fn_apply(fn_compose(wpre, inc), entry);
+    if(tid == NTH - 1) sm.total_state = fn_apply(fn_compose(wpre, inc), entry);
 
     // ---- phase C: emit symbols (4 bits each, 32 max) ----
     uint64_t pk0 = 0, pk1 = 0;
@@ -320,7 +402,7 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
     {
       uint32_t st = st_in;
 #pragma unroll
-      for(int i = 0; i < BPT; ++i) {
+      for(int i = 0; i < 32; ++i) {
         if(i >= vlo && i < vhi) {
           uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
           uint32_t sy = 8;   // 8 = nothing
@@ -342,7 +424,6 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
         }
       }
     }
-    // block-wide exclusive scan of counts
     uint32_t cinc = cnt;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1) {
@@ -355,9 +436,9 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
     uint32_t woff = 0;
     for(int i = 0; i < warp; ++i) woff += sm.warp_cnt[i];
     const uint32_t off = woff + cinc - cnt;
-    if(tid == HALO / BPT) sm.idx0 = off;               // symbols emitted by the halo bytes
-    if(tid == NT - 1) sm.nsym = off + cnt;
-    if(tid < HALO / BPT && brk) sm.halo_break = 1;
+    if(tid == HALO / 32) sm.idx0 = off;                // symbols emitted by the halo bytes
+    if(tid == NTH - 1) sm.nsym = off + cnt;
+    if(tid < HALO / 32 && brk) sm.halo_break = 1;
     {
       uint8_t* dst = sm.sym + PRE + off;
       for(uint32_t j = 0; j < cnt; ++j) {
@@ -385,7 +466,6 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
 
     // hand the parser state to the next batch
     if(t == a.n_tiles - 1 && warp == 1) {
-      // (need at least PRE symbols of history: if this window is short, look further back)
       uint8_t* cs = a.carry_out->sym;
       if(nsym >= (uint32_t)PRE || t == 0 || sm.halo_break || a.tile_state[t] == ST_H) {
         cs[lane] = sm.sym[nsym + lane]; cs[lane + 32] = sm.sym[nsym + lane + 32];
@@ -395,19 +475,25 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
       if(lane == 0) a.carry_out->state = sm.total_state;
     }
 
-    // ---- phase E: roll canonical k-mers over the compacted symbols, hash, insert ----
-    if(nsym > idx0) {
-      const uint32_t n_chunks = (nsym - idx0 + QSYM - 1) / QSYM;
-      for(uint32_t c = tid; c < n_chunks; c += NT) {
-        const uint32_t j0 = idx0 + c * QSYM;
-        const uint32_t j1 = min(nsym, j0 + (uint32_t)QSYM);
-        uint64_t m[KW], rc[KW];
+    // ---- phase E: roll canonical k-mers over the compacted symbols, hash, insert / stage ----
+    const uint32_t n_chunks = nsym > idx0 ? (nsym - idx0 + QSYM - 1) / QSYM : 0;
+    const uint32_t iters = (n_chunks + NTH - 1) / NTH;      // identical for every thread (block-wide flushes)
+    for(uint32_t it = 0; it < iters; ++it) {
+      const uint32_t c = it * NTH + tid;
+      const bool active = c < n_chunks;
+      const uint32_t j0 = idx0 + c * QSYM;
+      const uint32_t j1 = active ? min(nsym, j0 + (uint32_t)QSYM) : j0;
+      uint64_t m[KW], rc[KW];
 #pragma unroll
-        for(int q = 0; q < KW; ++q) { m[q] = 0; rc[q] = 0; }
-        uint32_t run = 0;
-        const uint8_t* sp = sm.sym + PRE + j0 - (k - 1);
-        const uint32_t total = (k - 1) + (j1 - j0);
-        for(uint32_t j = 0; j < total; ++j) {
+      for(int q = 0; q < KW; ++q) { m[q] = 0; rc[q] = 0; }
+      uint32_t run = 0;
+      const uint8_t* sp = sm.sym + PRE + j0 - (k - 1);
+      const uint32_t total = active ? (k - 1) + (j1 - j0) : 0;
+      uint32_t j = 0;
+#pragma unroll 1
+      for(int round = 0; round < (MODE == 2 ? SUBROUNDS : 1); ++round) {
+        const uint32_t stop = (MODE == 2 && round < SUBROUNDS - 1) ? min(total, (k - 1) + (round + 1) * (QSYM / SUBROUNDS)) : total;
+        for(; j < stop; ++j) {
           const uint32_t sy = sp[j];
           if(sy < 4) {
             // m = (m << 2 | sy) & mask ; rc = rc >> 2 | (3 - sy) << (2k - 2)   (mer_dna.hpp:322-370)
@@ -433,23 +519,52 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
             for(int q = 0; q < KW; ++q) key[q] = use_rc ? rc[q] : m[q];
             ls.kmers++;
             const uint64_t pos = gf2_hash<KW>(lut, key, (int)a.nbytes);
-            if(a.mode == 0) {
+            if(MODE == 0) {
               if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;
               else { ls.failed++; record_failure<KW>(a.T, key, 1); }
-            } else {
+            } else if(MODE == 1) {
               const uint32_t owner = a.shard_bits ? (uint32_t)(pos >> (a.T.lsize - a.shard_bits)) : 0u;
               unsigned long long at = atomicAdd(&a.route_counts[owner], 1ull);
               if(at < a.route_cap) {
 #pragma unroll
                 for(int q = 0; q < KW; ++q) a.route_keys[((uint64_t)owner * a.route_cap + at) * KW + q] = key[q];
               } else atomicAdd(&a.T.stats[STAT_ROUTE_DROPPED], 1ull);
+            } else {
+              // record = (position inside the region << hb) | explicit key bits
+              const uint64_t lpos = pos & a.T.local_mask;
+              const uint32_t p = (uint32_t)(lpos >> pd.region_bits);
+              const uint64_t rel = lpos & ((1ull << pd.region_bits) - 1ull);
+              const u128 high = key_high<KW>(key, a.T.lsize);
+              const uint32_t hb = a.T.fbits - a.T.rbits;
+              u128 rec;
+              if(hb == 0)       { rec.lo = rel; rec.hi = 0; }
+              else if(hb < 64)  { rec.lo = high.lo | (rel << hb); rec.hi = high.hi | (rel >> (64 - hb)); }
+              else              { rec.lo = high.lo; rec.hi = high.hi | (rel << (hb - 64)); }
+              const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
+              if(slot < pd.cap) {
+                uint32_t* row = st_buf + (size_t)p * pd.row_words;
+                if(pd.rec_bytes == 4) row[slot] = (uint32_t)rec.lo;
+                else if(pd.rec_bytes == 8) { row[2 * slot] = (uint32_t)rec.lo; row[2 * slot + 1] = (uint32_t)(rec.lo >> 32); }
+                else { row[4 * slot] = (uint32_t)rec.lo; row[4 * slot + 1] = (uint32_t)(rec.lo >> 32); row[4 * slot + 2] = (uint32_t)rec.hi; row[4 * slot + 3] = (uint32_t)(rec.hi >> 32); }
+              }
+              else {           // staging buffer of this region is full (skewed input): direct insertion later
+                unsigned long long at = atomicAdd(pd.spill_n, 1ull);
+                if(at < pd.spill_cap) {
+#pragma unroll
+                  for(int q = 0; q < KW; ++q) pd.spill_keys[at * KW + q] = key[q];
+                  pd.spill_counts[at] = 1;
+                } else if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;   // spill list full too: insert right here
+                else { ls.failed++; record_failure<KW>(a.T, key, 1); }
+              }
             }
           }
         }
+        if(MODE == 2) flush_pass(false);
       }
     }
-    __syncthreads();     // all reads of win[buf] and sym[] done before they are overwritten
+    __syncthreads();     // all reads of sym[] done before the next window overwrites it
   }
+  if(MODE == 2) flush_pass(true);
 
   // ---- statistics: one atomic per counter per CTA ----
   unsigned long long v[4] = { ls.kmers, ls.inserted, ls.distinct, ls.reprobes };
@@ -458,14 +573,210 @@ __global__ void __launch_bounds__(NT, 2) count_kernel(const CountArgs a) {
 #pragma unroll
     for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
   }
-  __shared__ unsigned long long part[NWARP][4];
-  if(lane == 0) { part[warp][0] = v[0]; part[warp][1] = v[1]; part[warp][2] = v[2]; part[warp][3] = v[3]; }
+  if(lane == 0) { sm.part[warp][0] = v[0]; sm.part[warp][1] = v[1]; sm.part[warp][2] = v[2]; sm.part[warp][3] = v[3]; }
   __syncthreads();
   if(tid < 4) {
     unsigned long long s = 0;
-    for(int i = 0; i < NWARP; ++i) s += part[i][tid];
-    const int which[4] = { STAT_KMERS, STAT_INSERTED, STAT_DISTINCT, STAT_REPROBES };
-    if(s) atomicAdd(&a.T.stats[which[tid]], s);
+    for(int i = 0; i < NW; ++i) s += sm.part[i][tid];
+    const int which = tid == 0 ? STAT_KMERS : tid == 1 ? STAT_INSERTED : tid == 2 ? STAT_DISTINCT : STAT_REPROBES;
+    if(s) atomicAdd(&a.T.stats[which], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1b: partitioned insertion.  Chunks are visited region by region (order[] lists the chunk
+//      ids sorted by region), every CTA pulling the next chunk from a shared cursor, so that at
+//      any moment the whole GPU works on one or two adjacent table regions that sit in L2.
+// ---------------------------------------------------------------------------------------
+__global__ void close_chunks_kernel(PartDev pd, uint32_t n_cta) {
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)n_cta * pd.P; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = pd.cta_chunk[i];
+    if(c != NO_CHUNK) { pd.dir[c] = make_uint2((uint32_t)(i % pd.P), pd.cta_fill[i]); pd.cta_chunk[i] = NO_CHUNK; pd.cta_fill[i] = 0; }
+  }
+}
+__global__ void chunk_hist_kernel(PartDev pd, uint32_t* __restrict__ hist) {
+  const uint32_t n = min(*pd.pool_next, pd.n_chunks);
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&hist[pd.dir[i].x], 1u);
+}
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(uint32_t P, const uint32_t* __restrict__ hist, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t s[PMAX];
+  for(uint32_t p = threadIdx.x; p < P; p += blockDim.x) s[p] = hist[p];
+  __syncthreads();
+  if(threadIdx.x == 0) { uint32_t run = 0; for(uint32_t p = 0; p < P; ++p) { uint32_t x = s[p]; s[p] = run; run += x; } }
+  __syncthreads();
+  for(uint32_t p = threadIdx.x; p < P; p += blockDim.x) { start[p] = s[p]; cursor[p] = s[p]; }
+}
+__global__ void chunk_scatter_kernel(PartDev pd, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+  const uint32_t n = min(*pd.pool_next, pd.n_chunks);
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) order[atomicAdd(&cursor[pd.dir[i].x], 1u)] = i;
+}
+
+template<int KW, int SB>
+__global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartDev pd, const uint32_t* __restrict__ order,
+                                                                unsigned int* __restrict__ unit_cursor, uint32_t from, uint32_t upto,
+                                                                const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
+  const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
+  const uint32_t hb = T.fbits - T.rbits;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t per16 = 16 / pd.rec_bytes;                         // records per 16 bytes: 4, 2 or 1
+  LocalStats ls = { 0, 0, 0, 0, 0 };
+  for(;;) {
+    // a warp takes the next chunk; chunks are handed out in region order, so all warps of the GPU
+    // work on the same one or two L2-resident table regions
+    uint32_t u = 0;
+    if(lane == 0) u = from + atomicAdd(unit_cursor, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if(u >= n_units) break;
+    const uint32_t chunk = order[u];
+    const uint2 d = pd.dir[chunk];
+    const uint4* src = reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk * CHUNK_BYTES);
+    const uint64_t region_base = (uint64_t)d.x << pd.region_bits;
+    const uint32_t n16 = (d.y + per16 - 1) / per16;                 // 16-byte pieces holding records
+    uint4 raw = lane < n16 ? __ldcs(src + lane) : make_uint4(0, 0, 0, 0);
+    for(uint32_t v0 = lane; v0 < n16; v0 += 32) {
+      const uint4 cur = raw;
+      if(v0 + 32 < n16) raw = __ldcs(src + v0 + 32);                // next piece in flight while this one is inserted
+      u128 recs[4]; bool valid[4]; uint64_t base[4]; u128 high[4]; bool ok[4];
+      if(pd.rec_bytes == 4) {
+        recs[0].lo = cur.x; recs[1].lo = cur.y; recs[2].lo = cur.z; recs[3].lo = cur.w;
+        recs[0].hi = recs[1].hi = recs[2].hi = recs[3].hi = 0;
+      } else if(pd.rec_bytes == 8) {
+        recs[0].lo = (uint64_t)cur.x | ((uint64_t)cur.y << 32); recs[1].lo = (uint64_t)cur.z | ((uint64_t)cur.w << 32);
+        recs[0].hi = recs[1].hi = 0; recs[2].lo = recs[2].hi = recs[3].lo = recs[3].hi = 0;
+      } else {
+        recs[0].lo = (uint64_t)cur.x | ((uint64_t)cur.y << 32); recs[0].hi = (uint64_t)cur.z | ((uint64_t)cur.w << 32);
+        recs[1].lo = recs[1].hi = recs[2].lo = recs[2].hi = recs[3].lo = recs[3].hi = 0;
+      }
+#pragma unroll
+      for(int r = 0; r < 4; ++r) {
+        valid[r] = (uint32_t)r < per16 && v0 * per16 + r < d.y;
+        const u128 rec = recs[r];
+        uint64_t rel;
+        if(hb == 0)      { rel = rec.lo; high[r].lo = 0; high[r].hi = 0; }
+        else if(hb < 64) { high[r].lo = rec.lo & ((1ull << hb) - 1ull); high[r].hi = 0; rel = (rec.lo >> hb) | (rec.hi << (64 - hb)); }
+        else             { high[r].lo = rec.lo; high[r].hi = hb == 64 ? 0 : (rec.hi & ((1ull << (hb - 64)) - 1ull)); rel = hb == 64 ? rec.hi : (rec.hi >> (hb - 64)); }
+        base[r] = region_base + rel;
+      }
+      table_add_batch<SB, 4>(T, base, high, valid, ok, ls);
+#pragma unroll
+      for(int r = 0; r < 4; ++r) {
+        if(!valid[r]) continue;
+        if(ok[r]) { ls.inserted++; continue; }
+        // hash full: rebuild the key (low bits = inverse matrix * [explicit bits : position]) for the failure list
+        uint64_t v[KW], key[KW];
+        const uint64_t gpos = ((uint64_t)T.shard_index << T.local_lsize) | base[r];
+        v[0] = (T.lsize >= 64 ? 0 : (high[r].lo << T.lsize)) | gpos;
+        if(KW == 2) v[KW - 1] = T.lsize ? ((high[r].hi << T.lsize) | (high[r].lo >> (64 - T.lsize))) : high[r].hi;
+        const uint64_t low = gf2_hash<KW>(inv_lut_g, v, (int)nbytes);
+        const uint64_t lmask = T.lsize >= 64 ? ~0ull : ((1ull << T.lsize) - 1ull);
+#pragma unroll
+        for(int q = 0; q < KW; ++q) key[q] = v[q];
+        key[0] = (key[0] & ~lmask) | (low & lmask);
+        record_failure<KW>(T, key, 1);
+      }
+    }
+  }
+  unsigned long long v[3] = { ls.inserted, ls.distinct, ls.reprobes };
+#pragma unroll
+  for(int q = 0; q < 3; ++q) {
+#pragma unroll
+    for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+  if(lane == 0) {
+    if(v[0]) atomicAdd(&T.stats[STAT_INSERTED], v[0]);
+    if(v[1]) atomicAdd(&T.stats[STAT_DISTINCT], v[1]);
+    if(v[2]) atomicAdd(&T.stats[STAT_REPROBES], v[2]);
+  }
+}
+
+// After a regrow in the middle of a drain: the remaining records still describe positions of
+// the OLD table (T0).  Rebuild each key with the old inverse matrix, hash it with the new one
+// and insert it into the new table.
+template<int KW, int SB>
+__global__ void __launch_bounds__(512, 1) rehash_chunks_kernel(TableDev T, TableDev T0, PartDev pd, const uint32_t* __restrict__ order,
+                                                               unsigned int* __restrict__ unit_cursor, uint32_t from, uint32_t upto,
+                                                               const uint64_t* __restrict__ old_inv_g, const uint64_t* __restrict__ new_lut_g,
+                                                               uint32_t nbytes) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* inv = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* lut = inv + nbytes * 256;
+  for(uint32_t i = threadIdx.x; i < nbytes * 256u; i += blockDim.x) { inv[i] = old_inv_g[i]; lut[i] = new_lut_g[i]; }
+  __shared__ uint32_t s_unit;
+  __syncthreads();
+  const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
+  const uint32_t hb = T0.fbits - T0.rbits;
+  LocalStats ls = { 0, 0, 0, 0, 0 };
+  for(;;) {
+    if(threadIdx.x == 0) s_unit = from + atomicAdd(unit_cursor, 1u);
+    __syncthreads();
+    const uint32_t u = s_unit;
+    __syncthreads();
+    if(u >= n_units) break;
+    const uint32_t chunk = order[u];
+    const uint2 d = pd.dir[chunk];
+    const uint8_t* src = pd.pool + (size_t)chunk * CHUNK_BYTES;
+    const uint64_t region_base = (uint64_t)d.x << pd.region_bits;
+    for(uint32_t i = threadIdx.x; i < d.y; i += blockDim.x) {
+      const u128 rec = load_rec(src, pd.rec_bytes, i);
+      u128 high; uint64_t rel;
+      if(hb == 0)      { rel = rec.lo; high.lo = 0; high.hi = 0; }
+      else if(hb < 64) { high.lo = rec.lo & ((1ull << hb) - 1ull); high.hi = 0; rel = (rec.lo >> hb) | (rec.hi << (64 - hb)); }
+      else             { high.lo = rec.lo; high.hi = hb == 64 ? 0 : (rec.hi & ((1ull << (hb - 64)) - 1ull)); rel = hb == 64 ? rec.hi : (rec.hi >> (hb - 64)); }
+      const uint64_t gpos = ((uint64_t)T0.shard_index << T0.local_lsize) | (region_base + rel);
+      uint64_t v[KW], key[KW];
+      v[0] = (T0.lsize >= 64 ? 0 : (high.lo << T0.lsize)) | gpos;
+      if(KW == 2) v[KW - 1] = T0.lsize ? ((high.hi << T0.lsize) | (high.lo >> (64 - T0.lsize))) : high.hi;
+      const uint64_t low = gf2_hash<KW>(inv, v, (int)nbytes);
+      const uint64_t lmask = T0.lsize >= 64 ? ~0ull : ((1ull << T0.lsize) - 1ull);
+#pragma unroll
+      for(int q = 0; q < KW; ++q) key[q] = v[q];
+      key[0] = (key[0] & ~lmask) | (low & lmask);
+      const uint64_t pos = gf2_hash<KW>(lut, key, (int)nbytes);
+      if(table_add<KW, SB>(T, key, pos, 1, ls)) ls.inserted++;
+      else record_failure<KW>(T, key, 1);
+    }
+  }
+  unsigned long long v[3] = { ls.inserted, ls.distinct, ls.reprobes };
+#pragma unroll
+  for(int q = 0; q < 3; ++q) {
+#pragma unroll
+    for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+  if((threadIdx.x & 31) == 0) {
+    if(v[0]) atomicAdd(&T.stats[STAT_INSERTED], v[0]);
+    if(v[1]) atomicAdd(&T.stats[STAT_DISTINCT], v[1]);
+    if(v[2]) atomicAdd(&T.stats[STAT_REPROBES], v[2]);
+  }
+}
+
+// insert the spilled keys (count taken from device memory so that no host round trip is needed)
+template<int KW, int SB>
+__global__ void __launch_bounds__(256) insert_spill_kernel(TableDev T, const uint64_t* __restrict__ lut_g, uint32_t nbytes, PartDev pd) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw);
+  for(uint32_t i = threadIdx.x; i < nbytes * 256u; i += blockDim.x) lut[i] = lut_g[i];
+  __syncthreads();
+  const uint64_t n = min((uint64_t)*pd.spill_n, pd.spill_cap);
+  LocalStats ls = { 0, 0, 0, 0, 0 };
+  unsigned long long occ = 0;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key[KW];
+#pragma unroll
+    for(int q = 0; q < KW; ++q) key[q] = pd.spill_keys[i * KW + q];
+    const uint64_t pos = gf2_hash<KW>(lut, key, (int)nbytes);
+    if(table_add<KW, SB>(T, key, pos, pd.spill_counts[i], ls)) occ += pd.spill_counts[i];
+    else record_failure<KW>(T, key, pd.spill_counts[i]);
+  }
+  unsigned long long v[3] = { occ, ls.distinct, ls.reprobes };
+#pragma unroll
+  for(int q = 0; q < 3; ++q) {
+#pragma unroll
+    for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+  if((threadIdx.x & 31) == 0) {
+    if(v[0]) atomicAdd(&T.stats[STAT_INSERTED], v[0]);
+    if(v[1]) atomicAdd(&T.stats[STAT_DISTINCT], v[1]);
+    if(v[2]) atomicAdd(&T.stats[STAT_REPROBES], v[2]);
   }
 }
 
@@ -481,16 +792,17 @@ __global__ void __launch_bounds__(256) insert_keys_kernel(TableDev T, const uint
   for(uint32_t i = threadIdx.x; i < nbytes * 256u; i += blockDim.x) lut[i] = lut_g[i];
   __syncthreads();
   LocalStats ls = { 0, 0, 0, 0, 0 };
+  unsigned long long occ = 0;
   for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t key[KW];
 #pragma unroll
     for(int q = 0; q < KW; ++q) key[q] = keys[i * KW + q];
     const uint64_t cnt = counts ? counts[i] : 1;
     const uint64_t pos = gf2_hash<KW>(lut, key, (int)nbytes);
-    if(table_add<KW, SB>(T, key, pos, cnt, ls)) ls.inserted++;
+    if(table_add<KW, SB>(T, key, pos, cnt, ls)) occ += cnt;
     else { ls.failed++; record_failure<KW>(T, key, cnt); }
   }
-  unsigned long long v[3] = { ls.inserted, ls.distinct, ls.reprobes };
+  unsigned long long v[3] = { occ, ls.distinct, ls.reprobes };
 #pragma unroll
   for(int q = 0; q < 3; ++q) {
 #pragma unroll
