@@ -92,6 +92,8 @@ typedef struct {
   const uint64_t* matrix_columns; /* matrix_c columns (NULL when identity); owned by
                                      the engine, valid until the next regrow/destroy  */
   const uint64_t* reprobes;       /* max_reprobe+1 offsets (lib/storage.cc:13-41)      */
+  uint32_t part_regions;   /* table regions of the region-by-region insertion (0 = direct insertion) */
+  uint32_t part_rec_bytes; /* bytes of one staged k-mer record                                  */
 } jfgpu_table_info;
 
 typedef struct {

@@ -40,7 +40,7 @@ class TableInfo(C.Structure):
         ("max_reprobe", C.c_uint32), ("matrix_r", C.c_uint32), ("matrix_c", C.c_uint32),
         ("matrix_identity", C.c_uint32), ("slot_bits", C.c_uint32), ("local_slots", C.c_uint64),
         ("table_bytes", C.c_uint64), ("matrix_columns", C.POINTER(C.c_uint64)),
-        ("reprobes", C.POINTER(C.c_uint64)),
+        ("reprobes", C.POINTER(C.c_uint64)), ("part_regions", C.c_uint32), ("part_rec_bytes", C.c_uint32),
     ]
 
 

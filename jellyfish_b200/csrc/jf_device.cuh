@@ -14,6 +14,7 @@
 #define JF_DEVICE_CUH
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace jfk {
 
@@ -272,43 +273,74 @@ __device__ __forceinline__ bool table_add_hp(const TableDev& T, const uint64_t b
   }
 }
 
-// R insertions of count 1 with the R first probes issued back to back, so that R L2/HBM
-// round trips overlap instead of running one after the other.  ok[r] = false -> hash full.
+// R insertions of count 1.  Round 1: the R first probes (CAS) are issued back to back so the
+// R L2 round trips overlap.  Keys that lost their first slot then LOOK AHEAD: the next LOOK probe
+// slots (offsets 1,3,6,10 -- at most 40 bytes away, i.e. the same or the next 32-byte sector)
+// are read with plain L2 loads, all in flight together, and only the first slot that is empty or
+// already holds the key is CASed.  A dependent chain of p CAS round trips becomes ~2.
+// ok[r] = false -> hash full.
+template<typename W>
+__device__ __forceinline__ W ld_slot(const W* p) { return __ldcg(p); }
+
 template<int SB, int R>
 __device__ __forceinline__ void table_add_batch(const TableDev& T, const uint64_t (&base)[R], const u128 (&high)[R],
                                                 const bool (&valid)[R], bool (&ok)[R], LocalStats& ls) {
+  constexpr uint32_t LOOK = 4;
   const uint32_t rb = T.rbits, fb = T.fbits;
-  if(SB == 32) {
-    uint32_t* tab = (uint32_t*)T.slots;
-    const uint32_t fmask = (1u << fb) - 1u, one = 1u << fb, cb = 32 - fb;
-    uint32_t old[R], kf[R];
-#pragma unroll
-    for(int r = 0; r < R; ++r) { kf[r] = (uint32_t)(high[r].lo << rb) | 1u; old[r] = valid[r] ? atomicCAS(&tab[base[r]], 0u, kf[r] | one) : 1u; }
+  if(SB == 32 || SB == 64) {
+    typedef typename std::conditional<SB == 32, uint32_t, unsigned long long>::type W;
+    W* tab = (W*)T.slots;
+    const W fmask = (W)(((W)1 << fb) - 1), one = (W)1 << fb;
+    const uint32_t cb = SB - fb;
+    W old[R], kf0[R];
 #pragma unroll
     for(int r = 0; r < R; ++r) {
-      ok[r] = true;
-      if(!valid[r]) continue;
-      if(old[r] == 0u) ls.distinct++;
-      else if((old[r] & fmask) == kf[r]) {
-        uint32_t o2 = atomicAdd(&tab[base[r]], one);
-        if((((uint64_t)(o2 >> fb) + 1) >> cb) != 0) ovf_add(T, base[r], 1);
-      } else ok[r] = table_add_hp<SB>(T, base[r], high[r], 1, ls, 1);
+      kf0[r] = (W)((W)high[r].lo << rb);
+      old[r] = valid[r] ? atomicCAS(&tab[base[r]], (W)0, (W)(kf0[r] | 1u | one)) : (W)1;
     }
-  } else if(SB == 64) {
-    unsigned long long* tab = (unsigned long long*)T.slots;
-    const uint64_t fmask = (1ull << fb) - 1ull, one = 1ull << fb; const uint32_t cb = 64 - fb;
-    unsigned long long old[R]; uint64_t kf[R];
-#pragma unroll
-    for(int r = 0; r < R; ++r) { kf[r] = (high[r].lo << rb) | 1ull; old[r] = valid[r] ? atomicCAS(&tab[base[r]], 0ull, (unsigned long long)(kf[r] | one)) : 1ull; }
+    uint32_t pending = 0;
 #pragma unroll
     for(int r = 0; r < R; ++r) {
       ok[r] = true;
       if(!valid[r]) continue;
-      if(old[r] == 0ull) ls.distinct++;
-      else if((old[r] & fmask) == kf[r]) {
-        unsigned long long o2 = atomicAdd(&tab[base[r]], (unsigned long long)one);
-        if((((o2 >> fb) + 1) >> cb) != 0) ovf_add(T, base[r], 1);
-      } else ok[r] = table_add_hp<SB>(T, base[r], high[r], 1, ls, 1);
+      if(old[r] == 0) ls.distinct++;
+      else if((old[r] & fmask) == (W)(kf0[r] | 1u)) {
+        W o2 = atomicAdd(&tab[base[r]], one);
+        if(((((uint64_t)(o2 >> fb)) + 1) >> cb) != 0) ovf_add(T, base[r], 1);
+      } else pending |= 1u << r;
+    }
+#pragma unroll
+    for(int r = 0; r < R; ++r) {
+      if(!((pending >> r) & 1u)) continue;
+      bool done = false;
+      for(uint32_t nxt = 1; !done; nxt += LOOK) {
+        if(nxt > T.max_reprobe) { ok[r] = false; break; }
+        // look ahead: LOOK probe slots, loads all in flight
+        W seen[LOOK];
+#pragma unroll
+        for(uint32_t j = 0; j < LOOK; ++j) {
+          const uint32_t i = nxt + j;
+          seen[j] = i <= T.max_reprobe ? ld_slot(&tab[base[r] + tri(i)]) : (W)~(W)0;
+        }
+#pragma unroll
+        for(uint32_t j = 0; j < LOOK; ++j) {
+          const uint32_t i = nxt + j;
+          if(done || i > T.max_reprobe) continue;
+          const W kf = (W)(kf0[r] | (W)(i + 1));
+          const W v = seen[j];
+          if(v != 0 && (v & fmask) != kf) continue;            // occupied by another key: keep walking
+          const uint64_t idx = base[r] + tri(i);
+          W o = v;
+          if(v == 0) o = atomicCAS(&tab[idx], (W)0, (W)(kf | one));
+          if(o == 0) { ls.distinct++; ls.reprobes += i; done = true; }
+          else if((o & fmask) == kf) {
+            W o2 = atomicAdd(&tab[idx], one);
+            if(((((uint64_t)(o2 >> fb)) + 1) >> cb) != 0) ovf_add(T, idx, 1);
+            ls.reprobes += i; done = true;
+          }
+          // else: another key took this slot in the meantime: keep walking
+        }
+      }
     }
   } else {
 #pragma unroll

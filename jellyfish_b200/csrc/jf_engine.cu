@@ -337,7 +337,8 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     if(!rebuilt) {
       rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
         insert_chunks_kernel<decltype(KW)::value, decltype(SB)::value><<<e->n_sm * 2, 512, 0, st>>>(
-            T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
+            T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes,
+            (uint32_t)std::max(1, std::min(2, getenv("JFGPU_GRAB") ? atoi(getenv("JFGPU_GRAB")) : 2)));
         return JFGPU_OK;
       });
     } else {
@@ -1014,6 +1015,7 @@ int jfgpu_table_info_get(jfgpu_handle e, jfgpu_table_info* info) {
   for(unsigned i = 0; i < t.M.c(); ++i) e->matrix_cols_host[i] = t.M[i];
   info->matrix_columns = t.M.is_identity() ? nullptr : e->matrix_cols_host.data();
   info->reprobes = t.reprobes.data();
+  info->part_regions = e->part.P; info->part_rec_bytes = e->part.rec_bytes;
   return JFGPU_OK;
 }
 

@@ -524,7 +524,12 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
               else { ls.failed++; record_failure<KW>(a.T, key, 1); }
             } else if(MODE == 1) {
               const uint32_t owner = a.shard_bits ? (uint32_t)(pos >> (a.T.lsize - a.shard_bits)) : 0u;
-              unsigned long long at = atomicAdd(&a.route_counts[owner], 1ull);
+              // warp-aggregated reservation: one atomic per (warp, owner) instead of one per k-mer
+              const uint32_t peers = __match_any_sync(__activemask(), owner);
+              const uint32_t leader = __ffs(peers) - 1;
+              unsigned long long at = 0;
+              if((uint32_t)lane == leader) at = atomicAdd(&a.route_counts[owner], (unsigned long long)__popc(peers));
+              at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
               if(at < a.route_cap) {
 #pragma unroll
                 for(int q = 0; q < KW; ++q) a.route_keys[((uint64_t)owner * a.route_cap + at) * KW + q] = key[q];
@@ -611,31 +616,52 @@ __global__ void chunk_scatter_kernel(PartDev pd, uint32_t* __restrict__ cursor, 
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) order[atomicAdd(&cursor[pd.dir[i].x], 1u)] = i;
 }
 
+constexpr int GRAB_MAX = 2;   // chunks a CTA takes per visit of the shared cursor (at most)
+
 template<int KW, int SB>
 __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartDev pd, const uint32_t* __restrict__ order,
                                                                 unsigned int* __restrict__ unit_cursor, uint32_t from, uint32_t upto,
-                                                                const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
+                                                                const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes, uint32_t GRAB) {
+  __shared__ uint32_t s_unit;
+  __shared__ uint32_t s_chunk[GRAB_MAX];
+  __shared__ uint2 s_dir[GRAB_MAX];
   const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
   const uint32_t hb = T.fbits - T.rbits;
-  const uint32_t lane = threadIdx.x & 31;
   const uint32_t per16 = 16 / pd.rec_bytes;                         // records per 16 bytes: 4, 2 or 1
   LocalStats ls = { 0, 0, 0, 0, 0 };
   for(;;) {
-    // a warp takes the next chunk; chunks are handed out in region order, so all warps of the GPU
-    // work on the same one or two L2-resident table regions
-    uint32_t u = 0;
-    if(lane == 0) u = from + atomicAdd(unit_cursor, 1u);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if(u >= n_units) break;
-    const uint32_t chunk = order[u];
-    const uint2 d = pd.dir[chunk];
-    const uint4* src = reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk * CHUNK_BYTES);
-    const uint64_t region_base = (uint64_t)d.x << pd.region_bits;
-    const uint32_t n16 = (d.y + per16 - 1) / per16;                 // 16-byte pieces holding records
-    uint4 raw = lane < n16 ? __ldcs(src + lane) : make_uint4(0, 0, 0, 0);
-    for(uint32_t v0 = lane; v0 < n16; v0 += 32) {
-      const uint4 cur = raw;
-      if(v0 + 32 < n16) raw = __ldcs(src + v0 + 32);                // next piece in flight while this one is inserted
+    // the CTA takes the next GRAB chunks; chunks are handed out in region order, so the whole GPU
+    // works on the same one or two L2-resident table regions at any time
+    if(threadIdx.x == 0) s_unit = from + atomicAdd(unit_cursor, GRAB);
+    __syncthreads();
+    const uint32_t u0 = s_unit;
+    if(u0 >= n_units) break;
+    if(threadIdx.x < GRAB) {
+      const uint32_t u = u0 + threadIdx.x;
+      const uint32_t c = u < n_units ? order[u] : NO_CHUNK;
+      s_chunk[threadIdx.x] = c;
+      s_dir[threadIdx.x] = c != NO_CHUNK ? pd.dir[c] : make_uint2(0, 0);
+    }
+    __syncthreads();
+    // all record loads of the grab first (one coalesced 128-bit streaming load per chunk and
+    // thread), so that their DRAM latency overlaps the probing of the earlier chunks
+    uint4 raws[GRAB_MAX];
+#pragma unroll
+    for(uint32_t g = 0; g < GRAB_MAX; ++g) {
+      raws[g] = make_uint4(0, 0, 0, 0);
+      if(g < GRAB && s_chunk[g] != NO_CHUNK && threadIdx.x * per16 < s_dir[g].y)
+        raws[g] = __ldcs(reinterpret_cast<const uint4*>(pd.pool + (size_t)s_chunk[g] * CHUNK_BYTES) + threadIdx.x);
+    }
+#pragma unroll
+    for(uint32_t g = 0; g < GRAB_MAX; ++g) {
+      if(g >= GRAB) break;
+      const uint32_t chunk = s_chunk[g];
+      if(chunk == NO_CHUNK) break;
+      const uint2 d = s_dir[g];
+      const uint64_t region_base = (uint64_t)d.x << pd.region_bits;
+      const uint32_t v0 = threadIdx.x;
+      if(v0 * per16 >= d.y) continue;
+      const uint4 cur = raws[g];
       u128 recs[4]; bool valid[4]; uint64_t base[4]; u128 high[4]; bool ok[4];
       if(pd.rec_bytes == 4) {
         recs[0].lo = cur.x; recs[1].lo = cur.y; recs[2].lo = cur.z; recs[3].lo = cur.w;
@@ -675,6 +701,7 @@ __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartD
         record_failure<KW>(T, key, 1);
       }
     }
+    __syncthreads();       // s_unit / s_chunk are rewritten next
   }
   unsigned long long v[3] = { ls.inserted, ls.distinct, ls.reprobes };
 #pragma unroll
@@ -682,7 +709,7 @@ __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartD
 #pragma unroll
     for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
   }
-  if(lane == 0) {
+  if((threadIdx.x & 31) == 0) {
     if(v[0]) atomicAdd(&T.stats[STAT_INSERTED], v[0]);
     if(v[1]) atomicAdd(&T.stats[STAT_DISTINCT], v[1]);
     if(v[2]) atomicAdd(&T.stats[STAT_REPROBES], v[2]);

@@ -1,0 +1,157 @@
+"""One process per GPU: the hash table sharded by the top bits of the hash position.
+
+The reference is a single process; this module is the multi-GPU form of
+`hash_counter`: every rank parses its own part of the input, the canonical k-mers are bucketed
+by the rank that owns their table position (device kernel, `jfgpu_extract_route`), exchanged
+with one NCCL all-to-all per batch, and inserted by their owner (`jfgpu_insert_keys`).  All
+ranks draw the same hash matrix (the reference's deterministic random stream), and shard r owns
+the positions whose top log2(world) bits equal r, so the rank-ordered concatenation of the
+shard dumps is byte-identical to the single-GPU dump.
+
+The exchange logic (bucket capacities, count exchange, uneven all-to-all, ordering of the shard
+files) is plain torch.distributed code and is exercised on CPU with the gloo backend in
+tests/test_distributed_cpu.py through the `RouteBackend` seam below.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class RouteBackend(object):
+    """What the exchange needs from the engine; the CUDA engine implements it with kernels."""
+
+    key_words = 1
+
+    def extract_route(self, text, begin, end, keys, capacity, counts):
+        raise NotImplementedError
+
+    def insert_keys(self, keys, n):
+        raise NotImplementedError
+
+
+class EngineBackend(RouteBackend):
+    """libjfgpu.so (sm_100a kernels) behind the seam."""
+
+    def __init__(self, hc):
+        self.hc = hc
+        self.key_words = hc.key_words
+
+    def extract_route(self, text, begin, end, keys, capacity, counts):
+        ptr, n = text
+        self.hc.extract_route(ptr, n, keys.data_ptr(), capacity, counts.data_ptr(), begin=begin, end=end)
+
+    def insert_keys(self, keys, n):
+        if n:
+            self.hc.insert_keys(keys.data_ptr(), n)
+
+
+def exchange_and_insert(backend, world, send, counts, capacity, recv):
+    """Uneven all-to-all of the bucketed keys, then insertion on the owner.
+
+    send:   int64 tensor [world, capacity * key_words]; bucket d holds counts[d] keys for rank d
+    counts: int64 tensor [world] (device of `send`)
+    recv:   int64 tensor [world, capacity * key_words] scratch
+    Returns the number of keys this rank received."""
+    kw = backend.key_words
+    if world == 1:
+        n = int(counts[0].item())
+        backend.insert_keys(send[0], n)
+        return n
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts)
+    sc = counts.tolist()
+    rc = recv_counts.tolist()
+    if max(sc) > capacity or max(rc) > capacity:
+        raise RuntimeError("route bucket capacity exceeded (%d > %d)" % (max(max(sc), max(rc)), capacity))
+    # uneven all-to-all: buckets compacted into one contiguous send tensor, one contiguous receive
+    flat_in = torch.cat([send[d, :sc[d] * kw] for d in range(world)])
+    flat_out = recv.view(-1)[:sum(rc) * kw]
+    dist.all_to_all_single(flat_out, flat_in, output_split_sizes=[c * kw for c in rc], input_split_sizes=[c * kw for c in sc])
+    total = sum(rc)
+    backend.insert_keys(flat_out, total)
+    return total
+
+
+class ShardedCounter(object):
+    """hash_counter over `world` GPUs.  `size` is the GLOBAL table size (jellyfish count -s)."""
+
+    def __init__(self, size, val_len=7, k=None, canonical=False, rank=0, world=1, device=0, reprobes=126,
+                 batch_bytes=256 << 20, slack=1.25):
+        from .engine import HashCounter
+        self.rank, self.world = rank, world
+        self.hc = HashCounter(size, val_len, k=k, canonical=canonical, reprobes=reprobes, device=device,
+                              shard_index=rank, n_shards=world, allow_regrow=(world == 1), max_batch_bytes=batch_bytes)
+        self.backend = EngineBackend(self.hc)
+        self.batch_bytes = batch_bytes
+        self.dev = torch.device("cuda", device)
+        if world > 1:
+            kw = self.hc.key_words
+            # a batch of B bytes yields at most B k-mers, spread evenly over the owners by the hash
+            self.capacity = int(batch_bytes / world * slack) + 65536
+            self.send = torch.empty((world, self.capacity * kw), dtype=torch.int64, device=self.dev)
+            self.recv = torch.empty((world, self.capacity * kw), dtype=torch.int64, device=self.dev)
+            self.counts = torch.zeros(world, dtype=torch.int64, device=self.dev)
+        self._host_stage = None
+
+    def add_device_text(self, ptr, n, begin=True, end=True):
+        if self.world == 1:
+            self.hc.add_device_text(ptr, n, begin=begin, end=end)
+            return
+        off = 0
+        # every rank must take part in every exchange: the number of rounds is agreed on first
+        rounds = (n + self.batch_bytes - 1) // self.batch_bytes
+        t = torch.tensor([rounds], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for i in range(int(t.item())):
+            ln = max(0, min(self.batch_bytes, n - off))
+            self.counts.zero_()
+            if ln:
+                self.backend.extract_route((ptr + off, ln), begin and off == 0, end and off + ln >= n,
+                                           self.send, self.capacity, self.counts)
+            exchange_and_insert(self.backend, self.world, self.send, self.counts, self.capacity, self.recv)
+            off += ln
+
+    def add_host_text(self, hptr, n, begin=True, end=True):
+        """Host memory (pinned) -> staged through a device buffer batch by batch."""
+        if self.world == 1:
+            import ctypes as C
+            self.hc.add_text((C.c_void_p(hptr), n), begin=begin, end=end)
+            return
+        import ctypes as C
+        if self._host_stage is None:
+            self._host_stage = torch.empty(self.batch_bytes + 256, dtype=torch.uint8, device=self.dev)
+        cudart = torch.cuda.cudart()
+        off = 0
+        rounds = (n + self.batch_bytes - 1) // self.batch_bytes
+        t = torch.tensor([rounds], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for i in range(int(t.item())):
+            ln = max(0, min(self.batch_bytes, n - off))
+            self.counts.zero_()
+            if ln:
+                cudart.cudaMemcpy(self._host_stage.data_ptr(), hptr + off, ln, 1)   # cudaMemcpyHostToDevice
+                self.backend.extract_route((self._host_stage.data_ptr(), ln), begin and off == 0, end and off + ln >= n,
+                                           self.send, self.capacity, self.counts)
+            exchange_and_insert(self.backend, self.world, self.send, self.counts, self.capacity, self.recv)
+            off += ln
+
+    def done(self):
+        return self.hc.done()
+
+    def dump_shard(self, path, **kw):
+        """Every rank writes `path.<rank>`: header (global size/matrix) + its sorted records."""
+        return self.hc.dump("%s.%d" % (path, self.rank), **kw)
+
+
+def concat_shards(path, world, out=None):
+    """Rank-ordered concatenation of the shard files = the single-GPU database
+    (positions of shard r all precede those of shard r+1)."""
+    out = out or path
+    with open(out, "wb") as fo:
+        for r in range(world):
+            with open("%s.%d" % (path, r), "rb") as fi:
+                data = fi.read()
+            hlen = int(data[:9])
+            fo.write(data if r == 0 else data[9 + hlen:])
+    return out

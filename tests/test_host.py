@@ -33,7 +33,7 @@ def test_struct_layouts_match_header(built):
     # sizes computed by hand from include/jfgpu.h
     assert ctypes.sizeof(_lib.Params) == 4 * 2 + 8 + 4 * 8 + 8 + 8 + 8 + 6 * 8
     assert ctypes.sizeof(_lib.Stats) == 11 * 8
-    assert ctypes.sizeof(_lib.TableInfo) == 8 + 4 * 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.TableInfo) == 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
 
 
 def test_reference_matrix_stream(built):
