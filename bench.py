@@ -281,7 +281,11 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = lib.jfgpu_kernel_launches() - launches0
-    assert st["kmers"] == kmers_per_step == st["inserted"], (st, kmers_per_step)
+    tot = torch.tensor([st["kmers"], st["inserted"], st["distinct"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)          # keys are inserted by their owner: only the sums must agree
+    assert st["kmers"] == kmers_per_step and tot[0].item() == tot[1].item() == kmers_per_step * world, (st, tot.tolist())
+    distinct_total = int(tot[2].item())
     t = torch.tensor([dev_secs, wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -390,7 +394,7 @@ def main():
                        "parallelism": "1 GPU" if world == 1 else "table sharded by top hash bits over %d GPUs, NCCL all-to-all" % world},
             "device_seconds_per_step": dev_secs / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "distinct": st["distinct"], "load_factor": st["distinct"] / float(info["size"]) * world if world > 1 else st["distinct"] / float(info["size"]),
+            "distinct": distinct_total, "load_factor": distinct_total / float(info["size"]),
         }
         print(json.dumps(line))
     if world > 1:

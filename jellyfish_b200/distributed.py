@@ -38,12 +38,15 @@ class EngineBackend(RouteBackend):
         self.key_words = hc.key_words
 
     def extract_route(self, text, begin, end, keys, capacity, counts):
+        # the engine works on torch's current stream, so its kernels are ordered with the NCCL
+        # collectives and the tensor ops around them
         ptr, n = text
-        self.hc.extract_route(ptr, n, keys.data_ptr(), capacity, counts.data_ptr(), begin=begin, end=end)
+        self.hc.extract_route(ptr, n, keys.data_ptr(), capacity, counts.data_ptr(), begin=begin, end=end,
+                              stream=torch.cuda.current_stream().cuda_stream)
 
     def insert_keys(self, keys, n):
         if n:
-            self.hc.insert_keys(keys.data_ptr(), n)
+            self.hc.insert_keys(keys.data_ptr(), n, stream=torch.cuda.current_stream().cuda_stream)
 
 
 def exchange_and_insert(backend, world, send, counts, capacity, recv):
@@ -93,11 +96,20 @@ class ShardedCounter(object):
             self.recv = torch.empty((world, self.capacity * kw), dtype=torch.int64, device=self.dev)
             self.counts = torch.zeros(world, dtype=torch.int64, device=self.dev)
         self._host_stage = None
+        # a dedicated (non-default) stream: its handle is passed to the engine so that kernels, tensor
+        # ops and NCCL collectives are ordered on one stream (handle 0 would mean "engine stream")
+        self.stream = torch.cuda.Stream(device=self.dev)
 
     def add_device_text(self, ptr, n, begin=True, end=True):
         if self.world == 1:
             self.hc.add_device_text(ptr, n, begin=begin, end=end)
             return
+        torch.cuda.current_stream(self.dev).synchronize()     # the caller's text is complete
+        with torch.cuda.stream(self.stream):
+            self._add_device_text(ptr, n, begin, end)
+        self.stream.synchronize()
+
+    def _add_device_text(self, ptr, n, begin, end):
         off = 0
         # every rank must take part in every exchange: the number of rounds is agreed on first
         rounds = (n + self.batch_bytes - 1) // self.batch_bytes
@@ -118,7 +130,11 @@ class ShardedCounter(object):
             import ctypes as C
             self.hc.add_text((C.c_void_p(hptr), n), begin=begin, end=end)
             return
-        import ctypes as C
+        with torch.cuda.stream(self.stream):
+            self._add_host_text(hptr, n, begin, end)
+        self.stream.synchronize()
+
+    def _add_host_text(self, hptr, n, begin, end):
         if self._host_stage is None:
             self._host_stage = torch.empty(self.batch_bytes + 256, dtype=torch.uint8, device=self.dev)
         cudart = torch.cuda.cudart()
@@ -130,7 +146,8 @@ class ShardedCounter(object):
             ln = max(0, min(self.batch_bytes, n - off))
             self.counts.zero_()
             if ln:
-                cudart.cudaMemcpy(self._host_stage.data_ptr(), hptr + off, ln, 1)   # cudaMemcpyHostToDevice
+                self.stream.synchronize()
+                cudart.cudaMemcpy(self._host_stage.data_ptr(), hptr + off, ln, 1)   # cudaMemcpyHostToDevice (synchronous)
                 self.backend.extract_route((self._host_stage.data_ptr(), ln), begin and off == 0, end and off + ln >= n,
                                            self.send, self.capacity, self.counts)
             exchange_and_insert(self.backend, self.world, self.send, self.counts, self.capacity, self.recv)

@@ -204,3 +204,55 @@ def test_partitioned_insertion_matches_golden(name, built, inputs):
             hdr = hc.header(ocl)
             assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == g["header"], (name, pool)
             assert jfutil.md5(body) == g["body_md5"], (name, pool)
+
+
+@pytest.mark.parametrize("name,world", [("k21C", 2), ("multi_files", 4), ("k63_multi", 2), ("k31C", 8)])
+def test_route_and_shards_on_one_gpu(name, world, built, workdir, inputs):
+    """The multi-GPU data path without NCCL: one engine per shard on the same device; keys bucketed
+    by `jfgpu_extract_route`, handed to their owner's `jfgpu_insert_keys`, shard dumps concatenated."""
+    import torch
+    from jellyfish_b200 import HashCounter
+    from jellyfish_b200.distributed import concat_shards
+    args, ins = CASES[name]
+    k = int(args[args.index("-m") + 1])
+    v = args[args.index("-s") + 1]
+    size = int(v[:-1]) * {"k": 10**3, "M": 10**6, "G": 10**9}[v[-1]] if v[-1] in "kMG" else int(v)
+    shards = [HashCounter(size, 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world, allow_regrow=False, max_batch_bytes=200000)
+              for r in range(world)]
+    kw = shards[0].key_words
+    cap = 400000
+    keys = torch.zeros((world, cap * kw), dtype=torch.int64, device="cuda")
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    total = 0
+    for i, f in enumerate(ins):
+        data = open(inputs[f], "rb").read()
+        buf = torch.zeros(len(data) + 256, dtype=torch.uint8, device="cuda")
+        if data:
+            buf[:len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        router = shards[i % world]            # any shard can do the routing: same matrix everywhere
+        off = 0
+        while True:
+            ln = min(150000, len(data) - off)
+            counts.zero_()
+            torch.cuda.synchronize()
+            router.extract_route(buf.data_ptr() + off, ln, keys.data_ptr(), cap, counts.data_ptr(), begin=off == 0, end=off + ln >= len(data))
+            c = counts.tolist()
+            assert max(c) <= cap
+            for d in range(world):
+                shards[d].insert_keys(keys[d].data_ptr(), c[d])
+            total += sum(c)
+            off += ln
+            if off >= len(data):
+                break
+    out = os.path.join(workdir, "route1_%s_%d" % (name, world))
+    n_ins = 0
+    for r, hc in enumerate(shards):
+        st = hc.done()
+        n_ins += st["inserted"]
+        hc.dump("%s.%d" % (out, r))
+        hc.close()
+    assert n_ins == total
+    h, b = jfutil.split_db(concat_shards(out, world, out + ".jf"))
+    g = GOLDEN[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert jfutil.md5(b) == g["body_md5"]
