@@ -70,7 +70,7 @@ struct Table {
 }  // namespace
 
 struct PartState {
-  uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0;
+  uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0, margin = 0;
   DevBuf pool, dir, order, pool_next, cta_chunk, cta_fill, spill_keys, spill_counts, spill_n, hist, start, cursor, unit_cursor;
   uint64_t spill_cap = 0;
   uint64_t bound_chunks = 0;     // host-side upper bound of chunks in use
@@ -231,7 +231,7 @@ PartDev part_dev(const jfgpu_engine* e) {
   const PartState& ps = e->part;
   d.P = ps.P; d.region_bits = ps.region_bits; d.rec_bytes = ps.rec_bytes; d.cap = ps.cap; d.flush_min = ps.flush_min;
   d.chunk_recs = CHUNK_BYTES / std::max(1u, ps.rec_bytes); d.n_chunks = ps.n_chunks; d.stage_bytes = ps.stage_bytes;
-  d.row_words = ps.cap * ps.rec_bytes / 4 + 1;
+  d.margin = ps.margin;
   d.pool = ps.pool.as<uint8_t>(); d.pool_next = ps.pool_next.as<unsigned int>(); d.dir = ps.dir.as<uint2>();
   d.cta_chunk = ps.cta_chunk.as<uint32_t>(); d.cta_fill = ps.cta_fill.as<uint32_t>();
   d.spill_keys = ps.spill_keys.as<uint64_t>(); d.spill_counts = ps.spill_counts.as<uint64_t>();
@@ -248,17 +248,18 @@ void part_configure(jfgpu_engine* e) {
   uint32_t P = 256;
   const size_t region_target = (size_t)(getenv("JFGPU_REGION_MB") ? atoi(getenv("JFGPU_REGION_MB")) : 32) << 20;
   while(P < (uint32_t)PMAX && (t.bytes() / P) > region_target) P <<= 1;
-  const uint32_t stage_bytes = e->kw == 1 ? (128u << 10) : (64u << 10);
   for(;; P >>= 1) {
     if(P < 64 || t.local_lsize < 8 || (1u << (t.local_lsize - 8)) < P) return;
     const uint32_t region_bits = t.local_lsize - ceil_log2(P);
     const uint32_t bits = region_bits + t.hb;
     const uint32_t rec = bits <= 32 ? 4 : bits <= 64 ? 8 : bits <= 128 ? 16 : 0;
     if(!rec) return;
-    const uint32_t cap = stage_bytes / P / rec;
-    if(cap < 8) continue;
-    ps.P = P; ps.region_bits = region_bits; ps.rec_bytes = rec; ps.cap = cap; ps.flush_min = std::max(1u, cap / 4);
-    ps.stage_bytes = P * (cap * rec + 4);      // rows padded by one word
+    // records arriving per region between two roll-over passes: 1024 threads x QSYM symbols / P
+    const double mean = 1024.0 * QSYM / P;
+    const uint32_t margin = (uint32_t)(mean + 6.0 * sqrt(mean) + 8.0);
+    if(margin * 2 > CHUNK_BYTES / rec) return;               // chunks would be closed half empty: insert directly
+    ps.P = P; ps.region_bits = region_bits; ps.rec_bytes = rec; ps.cap = 0; ps.flush_min = 0; ps.margin = margin;
+    ps.stage_bytes = PMAX * 4;                               // the open-chunk ids (the counters are accounted separately)
     return;
   }
 }
@@ -337,8 +338,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     if(!rebuilt) {
       rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
         insert_chunks_kernel<decltype(KW)::value, decltype(SB)::value><<<e->n_sm * 2, 512, 0, st>>>(
-            T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes,
-            (uint32_t)std::max(1, std::min(2, getenv("JFGPU_GRAB") ? atoi(getenv("JFGPU_GRAB")) : 2)));
+            T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
         return JFGPU_OK;
       });
     } else {
@@ -406,7 +406,8 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     rc = part_alloc(e);
     if(rc) return rc;
     // conservative host-side bound on pool usage: one record per input byte at most
-    const uint64_t need = (n * ps.rec_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES + 1;
+    const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;         // records a closed chunk holds at least
+    const uint64_t need = n / usable + 2;
     if(ps.bound_chunks + need > ps.n_chunks) {
       rc = part_drain(e, stream);
       if(rc) return rc;

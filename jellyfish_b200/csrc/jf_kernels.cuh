@@ -218,7 +218,7 @@ __device__ void backfill_symbols(const uint8_t* in, uint64_t n, const Carry* cin
 constexpr int PMAX        = 2048;          // partitions (table regions) at most
 constexpr int CHUNK_BYTES = 8192;          // granule of the record pool
 constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
-constexpr int SUBROUNDS   = 4;             // staging flushes per rolled chunk of QSYM symbols
+constexpr int SUBROUNDS   = 1;
 
 struct PartDev {
   uint32_t  P;              // number of regions (power of two)
@@ -229,7 +229,7 @@ struct PartDev {
   uint32_t  chunk_recs;     // records per chunk
   uint32_t  n_chunks;       // chunks in the pool
   uint32_t  stage_bytes;    // shared-memory staging bytes per CTA
-  uint32_t  row_words;      // 32-bit words per staging row = cap * rec_bytes / 4 + 1 (odd: no bank conflicts)
+  uint32_t  margin;         // a chunk is closed once fewer than `margin` free records remain
   uint8_t*  pool;
   unsigned int* pool_next;  // allocation cursor
   uint2*    dir;            // per chunk: { region, records } written when the chunk is closed
@@ -265,29 +265,6 @@ __device__ __forceinline__ u128 load_rec(const uint8_t* base, uint32_t rec_bytes
   return r;
 }
 
-// Append n staged records (32-bit words at `stage`) of region p to this CTA's chunk list (one thread).
-__device__ __forceinline__ void flush_region(const PartDev& pd, uint32_t p, const uint32_t* stage, uint32_t n,
-                                             uint32_t* my_chunk, uint32_t* my_fill, unsigned long long* stats) {
-  uint32_t chunk = my_chunk[p], fill = my_fill[p];
-  const uint32_t rw = pd.rec_bytes >> 2;
-  uint32_t done = 0;
-  while(done < n) {
-    if(chunk == NO_CHUNK || fill == pd.chunk_recs) {
-      if(chunk != NO_CHUNK) pd.dir[chunk] = make_uint2(p, fill);          // close the full chunk
-      uint32_t c = atomicAdd(pd.pool_next, 1u);
-      if(c >= pd.n_chunks) { atomicAdd(&stats[STAT_POOL_FULL], 1ull); chunk = NO_CHUNK; fill = 0; break; }
-      chunk = c; fill = 0;
-    }
-    const uint32_t take = min(n - done, pd.chunk_recs - fill);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(pd.pool + (size_t)chunk * CHUNK_BYTES) + (size_t)fill * rw;
-    const uint32_t* src = stage + done * rw;
-    const uint32_t nw = take * rw;
-    for(uint32_t j = 0; j < nw; ++j) dst[j] = src[j];
-    fill += take; done += take;
-  }
-  my_chunk[p] = chunk; my_fill[p] = fill;
-}
-
 template<int KW, int SB, int MODE, int NTH>
 __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const CountArgs a, const PartDev pd) {
   constexpr int WINB = NTH * 32;
@@ -296,20 +273,31 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   CountSmemT<NTH>& sm = *reinterpret_cast<CountSmemT<NTH>*>(smem_raw);
   uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15));
-  // MODE 2 only: staging counters and buffers behind the hash tables
+  // MODE 2 only, behind the hash tables: per region, fill count and id of this CTA's open chunk
   uint32_t* st_cnt = reinterpret_cast<uint32_t*>(lut + a.nbytes * 256);
-  uint32_t* st_buf = st_cnt + PMAX;
+  uint32_t* st_chunk = st_cnt + PMAX;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t k = a.k;
   const uint64_t n = a.n;
 
   for(uint32_t i = tid; i < a.nbytes * 256u; i += NTH) lut[i] = a.lut[i];
-  if(MODE == 2) for(uint32_t p = tid; p < pd.P; p += NTH) st_cnt[p] = 0;
-  if(tid == 0) mbar_init(&sm.bar, 1);
-  __syncthreads();
   uint32_t* my_chunk = MODE == 2 ? pd.cta_chunk + (size_t)blockIdx.x * pd.P : nullptr;
   uint32_t* my_fill  = MODE == 2 ? pd.cta_fill + (size_t)blockIdx.x * pd.P : nullptr;
+  if(MODE == 2) {
+    // every (CTA, region) pair always owns an open chunk: records are appended to it straight
+    // from the k-mer threads (a shared-memory counter hands out the slots)
+    for(uint32_t p = tid; p < pd.P; p += NTH) {
+      uint32_t c = my_chunk[p], f = my_fill[p];
+      if(c == NO_CHUNK) {
+        c = atomicAdd(pd.pool_next, 1u); f = 0;
+        if(c >= pd.n_chunks) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); c = NO_CHUNK; f = pd.chunk_recs; }
+      }
+      st_chunk[p] = c; st_cnt[p] = f;
+    }
+  }
+  if(tid == 0) mbar_init(&sm.bar, 1);
+  __syncthreads();
 
   auto issue = [&](uint64_t t) {       // TMA copy of window t (thread 0 only)
     long long h = (long long)(t * (uint64_t)TILEB) - HALO;
@@ -320,15 +308,19 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
     if(bytes) { mbar_expect_tx(&sm.bar, bytes); tma_load_1d(&sm.win[from - h], a.in + from, bytes, &sm.bar); }
     else mbar_arrive(&sm.bar);
   };
-  // staging flush (MODE 2): every region holding >= flush_min records (or all when `all`)
-  auto flush_pass = [&](bool all) {
+  // chunk roll-over (MODE 2): a chunk that may overflow during the next iteration is closed
+  // (its record count goes to the directory) and a fresh one is taken from the pool
+  auto rollover_pass = [&]() {
     __syncthreads();
     for(uint32_t p = tid; p < pd.P; p += NTH) {
-      const uint32_t c = min(st_cnt[p], pd.cap);
-      if(c && (all || c >= pd.flush_min)) {
-        flush_region(pd, p, st_buf + (size_t)p * pd.row_words, c, my_chunk, my_fill, a.T.stats);
-        st_cnt[p] = 0;
-      } else if(st_cnt[p] > pd.cap) st_cnt[p] = pd.cap;
+      const uint32_t c = st_cnt[p];
+      if(c + pd.margin > pd.chunk_recs) {
+        const uint32_t old = st_chunk[p];
+        if(old != NO_CHUNK) pd.dir[old] = make_uint2(p, min(c, pd.chunk_recs));
+        uint32_t nc = atomicAdd(pd.pool_next, 1u);
+        if(nc >= pd.n_chunks) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
+        else { st_chunk[p] = nc; st_cnt[p] = 0; }
+      }
     }
     __syncthreads();
   };
@@ -546,13 +538,13 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
               else if(hb < 64)  { rec.lo = high.lo | (rel << hb); rec.hi = high.hi | (rel >> (64 - hb)); }
               else              { rec.lo = high.lo; rec.hi = high.hi | (rel << (hb - 64)); }
               const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
-              if(slot < pd.cap) {
-                uint32_t* row = st_buf + (size_t)p * pd.row_words;
-                if(pd.rec_bytes == 4) row[slot] = (uint32_t)rec.lo;
-                else if(pd.rec_bytes == 8) { row[2 * slot] = (uint32_t)rec.lo; row[2 * slot + 1] = (uint32_t)(rec.lo >> 32); }
-                else { row[4 * slot] = (uint32_t)rec.lo; row[4 * slot + 1] = (uint32_t)(rec.lo >> 32); row[4 * slot + 2] = (uint32_t)rec.hi; row[4 * slot + 3] = (uint32_t)(rec.hi >> 32); }
+              if(slot < pd.chunk_recs) {
+                uint8_t* dst = pd.pool + (size_t)st_chunk[p] * CHUNK_BYTES;
+                if(pd.rec_bytes == 4) reinterpret_cast<uint32_t*>(dst)[slot] = (uint32_t)rec.lo;
+                else if(pd.rec_bytes == 8) reinterpret_cast<uint64_t*>(dst)[slot] = rec.lo;
+                else { reinterpret_cast<uint64_t*>(dst)[2 * slot] = rec.lo; reinterpret_cast<uint64_t*>(dst)[2 * slot + 1] = rec.hi; }
               }
-              else {           // staging buffer of this region is full (skewed input): direct insertion later
+              else {           // this region's chunk filled up within one iteration (skewed input): direct insertion later
                 unsigned long long at = atomicAdd(pd.spill_n, 1ull);
                 if(at < pd.spill_cap) {
 #pragma unroll
@@ -564,12 +556,15 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
             }
           }
         }
-        if(MODE == 2) flush_pass(false);
       }
+      if(MODE == 2) rollover_pass();
     }
     __syncthreads();     // all reads of sym[] done before the next window overwrites it
   }
-  if(MODE == 2) flush_pass(true);
+  if(MODE == 2) {          // keep the open chunks for the next launch
+    __syncthreads();
+    for(uint32_t p = tid; p < pd.P; p += NTH) { my_chunk[p] = st_chunk[p]; my_fill[p] = min(st_cnt[p], pd.chunk_recs); }
+  }
 
   // ---- statistics: one atomic per counter per CTA ----
   unsigned long long v[4] = { ls.kmers, ls.inserted, ls.distinct, ls.reprobes };
@@ -616,92 +611,93 @@ __global__ void chunk_scatter_kernel(PartDev pd, uint32_t* __restrict__ cursor, 
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) order[atomicAdd(&cursor[pd.dir[i].x], 1u)] = i;
 }
 
-constexpr int GRAB_MAX = 2;   // chunks a CTA takes per visit of the shared cursor (at most)
+// A warp works on one 512-byte piece of a chunk at a time (32 lanes x one 128-bit streaming
+// load = 128 four-byte records) and takes pieces from ONE shared cursor, so that
+//  * the pieces in flight on the whole GPU (~4.7k warps) span only ~300 consecutive chunks of the
+//    region-ordered list: one or two table regions, which stay L2 resident;
+//  * there is no block-wide barrier: a warp whose keys need long probe sequences delays nobody;
+//  * the next piece (cursor, chunk directory, records) is fetched before the current one is
+//    inserted, so HBM latency overlaps the probing.
+constexpr uint32_t PIECES = CHUNK_BYTES / 512;
+constexpr uint32_t PGRAB = 4;      // consecutive pieces a warp takes per visit of the shared cursor
 
 template<int KW, int SB>
 __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartDev pd, const uint32_t* __restrict__ order,
-                                                                unsigned int* __restrict__ unit_cursor, uint32_t from, uint32_t upto,
-                                                                const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes, uint32_t GRAB) {
-  __shared__ uint32_t s_unit;
-  __shared__ uint32_t s_chunk[GRAB_MAX];
-  __shared__ uint2 s_dir[GRAB_MAX];
+                                                                unsigned int* __restrict__ piece_cursor, uint32_t from, uint32_t upto,
+                                                                const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
   const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
   const uint32_t hb = T.fbits - T.rbits;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t per16 = 16 / pd.rec_bytes;                         // records per 16 bytes: 4, 2 or 1
   LocalStats ls = { 0, 0, 0, 0, 0 };
-  for(;;) {
-    // the CTA takes the next GRAB chunks; chunks are handed out in region order, so the whole GPU
-    // works on the same one or two L2-resident table regions at any time
-    if(threadIdx.x == 0) s_unit = from + atomicAdd(unit_cursor, GRAB);
-    __syncthreads();
-    const uint32_t u0 = s_unit;
-    if(u0 >= n_units) break;
-    if(threadIdx.x < GRAB) {
-      const uint32_t u = u0 + threadIdx.x;
-      const uint32_t c = u < n_units ? order[u] : NO_CHUNK;
-      s_chunk[threadIdx.x] = c;
-      s_dir[threadIdx.x] = c != NO_CHUNK ? pd.dir[c] : make_uint2(0, 0);
+
+  struct Piece { uint4 raw; uint64_t region_base; uint32_t n_rec; uint32_t v0; bool ok; };
+  uint32_t g_next = 0, g_left = 0;               // pieces of the current grab still to be fetched
+  auto fetch = [&](Piece& pc) {
+    if(g_left == 0) {
+      uint32_t g0 = 0;
+      if(lane == 0) g0 = atomicAdd(piece_cursor, PGRAB);
+      g_next = __shfl_sync(0xffffffffu, g0, 0);
+      g_left = PGRAB;
     }
-    __syncthreads();
-    // all record loads of the grab first (one coalesced 128-bit streaming load per chunk and
-    // thread), so that their DRAM latency overlaps the probing of the earlier chunks
-    uint4 raws[GRAB_MAX];
-#pragma unroll
-    for(uint32_t g = 0; g < GRAB_MAX; ++g) {
-      raws[g] = make_uint4(0, 0, 0, 0);
-      if(g < GRAB && s_chunk[g] != NO_CHUNK && threadIdx.x * per16 < s_dir[g].y)
-        raws[g] = __ldcs(reinterpret_cast<const uint4*>(pd.pool + (size_t)s_chunk[g] * CHUNK_BYTES) + threadIdx.x);
+    const uint32_t g = g_next++;
+    --g_left;
+    const uint32_t u = from + g / PIECES;
+    pc.ok = u < n_units;
+    pc.raw = make_uint4(0, 0, 0, 0); pc.n_rec = 0; pc.v0 = 0; pc.region_base = 0;
+    if(!pc.ok) return;
+    const uint32_t chunk = order[u];
+    const uint2 d = pd.dir[chunk];
+    pc.region_base = (uint64_t)d.x << pd.region_bits;
+    pc.n_rec = d.y;
+    pc.v0 = (g % PIECES) * 32 + lane;
+    if(pc.v0 * per16 < d.y) pc.raw = __ldcs(reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk * CHUNK_BYTES) + pc.v0);
+  };
+
+  Piece nxt;
+  fetch(nxt);
+  while(nxt.ok) {
+    const Piece cur = nxt;
+    fetch(nxt);                                  // in flight while `cur` is inserted
+    if(cur.v0 * per16 >= cur.n_rec) continue;
+    u128 recs[4]; bool valid[4]; uint64_t base[4]; u128 high[4]; bool ok[4];
+    if(pd.rec_bytes == 4) {
+      recs[0].lo = cur.raw.x; recs[1].lo = cur.raw.y; recs[2].lo = cur.raw.z; recs[3].lo = cur.raw.w;
+      recs[0].hi = recs[1].hi = recs[2].hi = recs[3].hi = 0;
+    } else if(pd.rec_bytes == 8) {
+      recs[0].lo = (uint64_t)cur.raw.x | ((uint64_t)cur.raw.y << 32); recs[1].lo = (uint64_t)cur.raw.z | ((uint64_t)cur.raw.w << 32);
+      recs[0].hi = recs[1].hi = 0; recs[2].lo = recs[2].hi = recs[3].lo = recs[3].hi = 0;
+    } else {
+      recs[0].lo = (uint64_t)cur.raw.x | ((uint64_t)cur.raw.y << 32); recs[0].hi = (uint64_t)cur.raw.z | ((uint64_t)cur.raw.w << 32);
+      recs[1].lo = recs[1].hi = recs[2].lo = recs[2].hi = recs[3].lo = recs[3].hi = 0;
     }
 #pragma unroll
-    for(uint32_t g = 0; g < GRAB_MAX; ++g) {
-      if(g >= GRAB) break;
-      const uint32_t chunk = s_chunk[g];
-      if(chunk == NO_CHUNK) break;
-      const uint2 d = s_dir[g];
-      const uint64_t region_base = (uint64_t)d.x << pd.region_bits;
-      const uint32_t v0 = threadIdx.x;
-      if(v0 * per16 >= d.y) continue;
-      const uint4 cur = raws[g];
-      u128 recs[4]; bool valid[4]; uint64_t base[4]; u128 high[4]; bool ok[4];
-      if(pd.rec_bytes == 4) {
-        recs[0].lo = cur.x; recs[1].lo = cur.y; recs[2].lo = cur.z; recs[3].lo = cur.w;
-        recs[0].hi = recs[1].hi = recs[2].hi = recs[3].hi = 0;
-      } else if(pd.rec_bytes == 8) {
-        recs[0].lo = (uint64_t)cur.x | ((uint64_t)cur.y << 32); recs[1].lo = (uint64_t)cur.z | ((uint64_t)cur.w << 32);
-        recs[0].hi = recs[1].hi = 0; recs[2].lo = recs[2].hi = recs[3].lo = recs[3].hi = 0;
-      } else {
-        recs[0].lo = (uint64_t)cur.x | ((uint64_t)cur.y << 32); recs[0].hi = (uint64_t)cur.z | ((uint64_t)cur.w << 32);
-        recs[1].lo = recs[1].hi = recs[2].lo = recs[2].hi = recs[3].lo = recs[3].hi = 0;
-      }
-#pragma unroll
-      for(int r = 0; r < 4; ++r) {
-        valid[r] = (uint32_t)r < per16 && v0 * per16 + r < d.y;
-        const u128 rec = recs[r];
-        uint64_t rel;
-        if(hb == 0)      { rel = rec.lo; high[r].lo = 0; high[r].hi = 0; }
-        else if(hb < 64) { high[r].lo = rec.lo & ((1ull << hb) - 1ull); high[r].hi = 0; rel = (rec.lo >> hb) | (rec.hi << (64 - hb)); }
-        else             { high[r].lo = rec.lo; high[r].hi = hb == 64 ? 0 : (rec.hi & ((1ull << (hb - 64)) - 1ull)); rel = hb == 64 ? rec.hi : (rec.hi >> (hb - 64)); }
-        base[r] = region_base + rel;
-      }
-      table_add_batch<SB, 4>(T, base, high, valid, ok, ls);
-#pragma unroll
-      for(int r = 0; r < 4; ++r) {
-        if(!valid[r]) continue;
-        if(ok[r]) { ls.inserted++; continue; }
-        // hash full: rebuild the key (low bits = inverse matrix * [explicit bits : position]) for the failure list
-        uint64_t v[KW], key[KW];
-        const uint64_t gpos = ((uint64_t)T.shard_index << T.local_lsize) | base[r];
-        v[0] = (T.lsize >= 64 ? 0 : (high[r].lo << T.lsize)) | gpos;
-        if(KW == 2) v[KW - 1] = T.lsize ? ((high[r].hi << T.lsize) | (high[r].lo >> (64 - T.lsize))) : high[r].hi;
-        const uint64_t low = gf2_hash<KW>(inv_lut_g, v, (int)nbytes);
-        const uint64_t lmask = T.lsize >= 64 ? ~0ull : ((1ull << T.lsize) - 1ull);
-#pragma unroll
-        for(int q = 0; q < KW; ++q) key[q] = v[q];
-        key[0] = (key[0] & ~lmask) | (low & lmask);
-        record_failure<KW>(T, key, 1);
-      }
+    for(int r = 0; r < 4; ++r) {
+      valid[r] = (uint32_t)r < per16 && cur.v0 * per16 + r < cur.n_rec;
+      const u128 rec = recs[r];
+      uint64_t rel;
+      if(hb == 0)      { rel = rec.lo; high[r].lo = 0; high[r].hi = 0; }
+      else if(hb < 64) { high[r].lo = rec.lo & ((1ull << hb) - 1ull); high[r].hi = 0; rel = (rec.lo >> hb) | (rec.hi << (64 - hb)); }
+      else             { high[r].lo = rec.lo; high[r].hi = hb == 64 ? 0 : (rec.hi & ((1ull << (hb - 64)) - 1ull)); rel = hb == 64 ? rec.hi : (rec.hi >> (hb - 64)); }
+      base[r] = cur.region_base + rel;
     }
-    __syncthreads();       // s_unit / s_chunk are rewritten next
+    table_add_batch<SB, 4>(T, base, high, valid, ok, ls);
+#pragma unroll
+    for(int r = 0; r < 4; ++r) {
+      if(!valid[r]) continue;
+      if(ok[r]) { ls.inserted++; continue; }
+      // hash full: rebuild the key (low bits = inverse matrix * [explicit bits : position]) for the failure list
+      uint64_t v[KW], key[KW];
+      const uint64_t gpos = ((uint64_t)T.shard_index << T.local_lsize) | base[r];
+      v[0] = (T.lsize >= 64 ? 0 : (high[r].lo << T.lsize)) | gpos;
+      if(KW == 2) v[KW - 1] = T.lsize ? ((high[r].hi << T.lsize) | (high[r].lo >> (64 - T.lsize))) : high[r].hi;
+      const uint64_t low = gf2_hash<KW>(inv_lut_g, v, (int)nbytes);
+      const uint64_t lmask = T.lsize >= 64 ? ~0ull : ((1ull << T.lsize) - 1ull);
+#pragma unroll
+      for(int q = 0; q < KW; ++q) key[q] = v[q];
+      key[0] = (key[0] & ~lmask) | (low & lmask);
+      record_failure<KW>(T, key, 1);
+    }
   }
   unsigned long long v[3] = { ls.inserted, ls.distinct, ls.reprobes };
 #pragma unroll
@@ -709,7 +705,7 @@ __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartD
 #pragma unroll
     for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
   }
-  if((threadIdx.x & 31) == 0) {
+  if(lane == 0) {
     if(v[0]) atomicAdd(&T.stats[STAT_INSERTED], v[0]);
     if(v[1]) atomicAdd(&T.stats[STAT_DISTINCT], v[1]);
     if(v[2]) atomicAdd(&T.stats[STAT_REPROBES], v[2]);

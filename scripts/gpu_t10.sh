@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "partitioned or chunked or lookup or large" 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+echo "=== full bench"; timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tee gpurun_out/bench_full10.json | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('VALUE', d['value']/1e9, 'ms', d['ms_per_step'], 'feed', d['device_seconds_per_step'], [ (k['kernel'][:20], k['seconds']) for k in d['roofline']['kernels']])"
+B="python bench.py --bases 2000000000 --size 4G --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+ncu --set full --clock-control none --import-source on -k regex:"insert_chunks" -s 40 -c 1 -o gpurun_out/prof_part_insert_r01c $B > gpurun_out/ncu_full.log 2>&1
