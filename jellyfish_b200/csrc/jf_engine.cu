@@ -336,6 +336,12 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st);
     TableDev T = table_dev(e, e->tab);
     if(!rebuilt) {
+      if(e->tab.slot_bits == 32 && pd.rec_bytes == 4 && !getenv("JFGPU_K2_GENERIC")) {
+        // lean 32-bit specialisation: 2 CTAs x 1024 threads per SM
+        if(e->kw == 1) insert_chunks32_kernel<1><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
+        else           insert_chunks32_kernel<2><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
+        rc = JFGPU_OK;
+      } else
       rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
         insert_chunks_kernel<decltype(KW)::value, decltype(SB)::value><<<e->n_sm * 2, 512, 0, st>>>(
             T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);

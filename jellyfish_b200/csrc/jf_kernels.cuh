@@ -712,6 +712,142 @@ __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartD
   }
 }
 
+// ---- lean specialisation of K2 for the common geometry: 32-bit slots and 4-byte records ----
+// Everything is 32-bit arithmetic except the slot index; rare paths (counter carry, hash full)
+// are kept out of line so that the kernel runs with 32 registers, i.e. 2048 threads per SM: the
+// kernel is bound by L2 atomic latency, and twice the threads means twice the atomics in flight.
+template<int KW>
+__device__ __noinline__ void k2_fail(uint32_t shard_index, uint32_t local_lsize, uint32_t lsize, unsigned long long* stats,
+                                     uint64_t* fail_keys, uint64_t* fail_counts, uint64_t fail_cap,
+                                     uint64_t base, uint32_t high, const uint64_t* inv_lut_g, uint32_t nbytes) {
+  uint64_t v[KW], key[KW];
+  const uint64_t gpos = ((uint64_t)shard_index << local_lsize) | base;
+  v[0] = (lsize >= 64 ? 0 : ((uint64_t)high << lsize)) | gpos;
+  if(KW == 2) v[KW - 1] = lsize ? ((uint64_t)high >> (64 - lsize)) : 0;
+  const uint64_t low = gf2_hash<KW>(inv_lut_g, v, (int)nbytes);
+  const uint64_t lmask = lsize >= 64 ? ~0ull : ((1ull << lsize) - 1ull);
+#pragma unroll
+  for(int q = 0; q < KW; ++q) key[q] = v[q];
+  key[0] = (key[0] & ~lmask) | (low & lmask);
+  unsigned long long at = atomicAdd(&stats[STAT_FAILED], 1ull);
+  if(at < fail_cap) {
+#pragma unroll
+    for(int w = 0; w < KW; ++w) fail_keys[at * KW + w] = key[w];
+    fail_counts[at] = 1;
+  } else atomicAdd(&stats[STAT_FAIL_DROPPED], 1ull);
+}
+__device__ __noinline__ void k2_carry(unsigned long long* ovf_keys, unsigned long long* ovf_vals, uint64_t ovf_mask, unsigned long long* stats, uint64_t idx) {
+  TableDev T; T.ovf_keys = ovf_keys; T.ovf_vals = ovf_vals; T.ovf_mask = ovf_mask; T.stats = stats;
+  ovf_add(T, idx, 1);
+}
+
+// continue the probe sequence of one key from probe 1 (look-ahead of 4 slots at a time); returns
+// false when the reprobe limit is exhausted
+// returns 0 = hash full, else 1 + probe index used | (new slot claimed ? 0x10000 : 0) | (counter carry ? 0x20000 : 0)
+__device__ __noinline__ uint32_t k2_walk(uint32_t* tab, uint64_t base, uint32_t kf0, uint32_t fb, uint32_t max_reprobe) {
+  const uint32_t fmask = (1u << fb) - 1u, one = 1u << fb, cb = 32 - fb;
+  for(uint32_t nxt = 1; nxt <= max_reprobe; nxt += 4) {
+    uint32_t seen[4];
+#pragma unroll
+    for(uint32_t j = 0; j < 4; ++j) seen[j] = nxt + j <= max_reprobe ? __ldcg(&tab[base + tri(nxt + j)]) : 0xFFFFFFFFu;
+#pragma unroll
+    for(uint32_t j = 0; j < 4; ++j) {
+      const uint32_t i = nxt + j;
+      if(i > max_reprobe) return 0;
+      const uint32_t kf = kf0 | (i + 1);
+      const uint32_t v = seen[j];
+      if(v != 0 && (v & fmask) != kf) continue;
+      const uint64_t idx = base + tri(i);
+      uint32_t o = v;
+      if(v == 0) o = atomicCAS(&tab[idx], 0u, kf | one);
+      if(o == 0) return (1 + i) | 0x10000u;
+      if((o & fmask) == kf) {
+        const uint32_t o2 = atomicAdd(&tab[idx], one);
+        return (1 + i) | ((((o2 >> fb) + 1) >> cb) != 0 ? 0x20000u : 0u);
+      }
+    }
+  }
+  return 0;
+}
+
+template<int KW>
+__global__ void __launch_bounds__(768, 2) insert_chunks32_kernel(TableDev T, PartDev pd, const uint32_t* __restrict__ order,
+                                                                   unsigned int* __restrict__ piece_cursor, uint32_t from, uint32_t upto,
+                                                                   const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
+  const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
+  const uint32_t fb = T.fbits, rb = T.rbits, hb = fb - rb;
+  const uint32_t fmask = (1u << fb) - 1u, one = 1u << fb, cb = 32 - fb;
+  const uint32_t hmask = hb ? ((1u << hb) - 1u) : 0u;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t* tab = (uint32_t*)T.slots;
+  uint32_t n_ins = 0, n_new = 0, n_rep = 0;
+  uint32_t g_next = 0, g_left = 0;
+  uint4 nraw = make_uint4(0, 0, 0, 0); uint64_t nbase = 0; uint32_t nvalid = 0; bool nok = false;
+  auto fetch = [&]() {
+    if(g_left == 0) {
+      uint32_t g0 = 0;
+      if(lane == 0) g0 = atomicAdd(piece_cursor, PGRAB);
+      g_next = __shfl_sync(0xffffffffu, g0, 0);
+      g_left = PGRAB;
+    }
+    const uint32_t g = g_next++;
+    --g_left;
+    const uint32_t u = from + g / PIECES;
+    nok = u < n_units; nvalid = 0;
+    if(!nok) return;
+    const uint32_t chunk = order[u];
+    const uint2 d = pd.dir[chunk];
+    nbase = (uint64_t)d.x << pd.region_bits;
+    const uint32_t v0 = (g % PIECES) * 32 + lane;
+    nvalid = v0 * 4 >= d.y ? 0u : min(4u, d.y - v0 * 4);
+    if(nvalid) nraw = __ldcs(reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk * CHUNK_BYTES) + v0);
+  };
+  fetch();
+  while(nok) {
+    const uint4 raw = nraw; const uint64_t rbase = nbase; const uint32_t nv = nvalid;
+    fetch();                                     // next piece in flight while this one is inserted
+    if(!nv) continue;
+    const uint32_t rec[4] = { raw.x, raw.y, raw.z, raw.w };
+    uint32_t old[4];
+#pragma unroll
+    for(int r = 0; r < 4; ++r)
+      old[r] = (uint32_t)r < nv ? atomicCAS(&tab[rbase + (hb < 32 ? rec[r] >> hb : 0u)], 0u, (((rec[r] & hmask) << rb) | 1u) | one) : 1u;
+#pragma unroll
+    for(int r = 0; r < 4; ++r) {
+      if((uint32_t)r >= nv) continue;
+      const uint32_t kf0 = (rec[r] & hmask) << rb;
+      const uint64_t base = rbase + (hb < 32 ? rec[r] >> hb : 0u);
+      bool ok = true;
+      if(old[r] == 0u) n_new++;
+      else if((old[r] & fmask) == (kf0 | 1u)) {
+        const uint32_t o2 = atomicAdd(&tab[base], one);
+        if((((o2 >> fb) + 1) >> cb) != 0) k2_carry(T.ovf_keys, T.ovf_vals, T.ovf_mask, T.stats, base);
+      } else {
+        const uint32_t w = k2_walk(tab, base, kf0, fb, T.max_reprobe);
+        ok = w != 0;
+        if(ok) {
+          const uint32_t i = (w & 0xFFFFu) - 1;
+          n_rep += i; if(w & 0x10000u) n_new++;
+          if(w & 0x20000u) k2_carry(T.ovf_keys, T.ovf_vals, T.ovf_mask, T.stats, base + tri(i));
+        }
+      }
+      if(ok) n_ins++;
+      else k2_fail<KW>(T.shard_index, T.local_lsize, T.lsize, T.stats, T.fail_keys, T.fail_counts, T.fail_cap, base, rec[r] & hmask, inv_lut_g, nbytes);
+    }
+  }
+  unsigned long long v[3] = { n_ins, n_new, n_rep };
+#pragma unroll
+  for(int q = 0; q < 3; ++q) {
+#pragma unroll
+    for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+  if(lane == 0) {
+    if(v[0]) atomicAdd(&T.stats[STAT_INSERTED], v[0]);
+    if(v[1]) atomicAdd(&T.stats[STAT_DISTINCT], v[1]);
+    if(v[2]) atomicAdd(&T.stats[STAT_REPROBES], v[2]);
+  }
+}
+
 // After a regrow in the middle of a drain: the remaining records still describe positions of
 // the OLD table (T0).  Rebuild each key with the old inverse matrix, hash it with the new one
 // and insert it into the new table.
