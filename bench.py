@@ -329,8 +329,20 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": (dom["achieved"] / peak) if dom["achieved"] else None, "traffic": dom.get("traffic"), "peak_source": peak_src,
                 "alg_bytes_per_kmer": dom["alg_bytes_per_kmer"], "mean_probes": p_mean, "avg_seconds_per_step": dom["seconds"],
-                "note": "HBM traffic of the region-by-region pipeline is at its algorithmic minimum (ncu); the kernels are bound by "
-                        "instruction issue (K1) and L2 atomic latency (K2), see profiles/", "kernels": kernels}
+                "note": "HBM traffic of the region-by-region pipeline is near its algorithmic minimum (ncu, profiles/traffic.json); the "
+                        "kernels are bound by instruction issue (K1) and by L2 atomic/load throughput (K2), not by HBM", "kernels": kernels}
+    # the north star's own yardstick: k-mers/s x (71/70 + 32 p + 32) bytes against the HBM peak, i.e. what a
+    # table filled by random HBM accesses would have to move; and the measured random-atomic ceiling of this
+    # GPU (scripts/micro/atomics.cu: 20.5 G random 32-bit atomics/s over a 32 GB region)
+    b_rand = 71.0 / 70.0 + 32.0 * p_mean + 32.0
+    roofline["random_access_model"] = {
+        "alg_bytes_per_kmer": b_rand, "achieved": value / world * b_rand / 1e9, "unit": "GB/s", "frac_of_hbm_peak": value / world * b_rand / 1e9 / peak,
+        "measured_random_atomic_ceiling_gops": 20.5, "ceiling_kmers_per_s": 20.5e9 / p_mean,
+        "vs_random_atomic_ceiling": (value / world) / (20.5e9 / p_mean)}
+    if info["part_regions"] and drain_secs:
+        # K2 against the measured L2 ceiling for its operation mix (scripts/micro/mix.cu: ~50 G keys/s at load 0.58)
+        roofline["l2_op_mix"] = {"achieved_gkeys_per_s": nk / drain_secs / 1e9, "measured_ceiling_gkeys_per_s": 50.0,
+                                 "frac": nk / drain_secs / 1e9 / 50.0}
 
     # ---- e2e: the public host API with pinned HOST buffers, copies inside the timed region ----
     e2e = None
