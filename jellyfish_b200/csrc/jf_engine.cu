@@ -942,9 +942,40 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
   if(!e) return JFGPU_ERR_ARG;
   cudaSetDevice(e->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  if(n == 0) return JFGPU_OK;
   cudaEventRecord(e->ev_t0, st);
-  int rc = insert_keys_into(e, e->tab, (const uint64_t*)dev_keys, nullptr, n, st);
-  if(rc) return rc;
+  int rc = JFGPU_OK;
+  PartState& ps = e->part;
+  if(ps.P) {
+    // region-by-region mode: turn the keys into records of the pool (K1c); K2 inserts them at the next drain
+    rc = part_alloc(e);
+    if(rc) return rc;
+    const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
+    const uint64_t need = n / usable + 2;
+    if(ps.bound_chunks + need > ps.n_chunks) { rc = part_drain(e, st); if(rc) return rc; }
+    if(ps.P && ps.bound_chunks + need > ps.n_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch of keys");
+  }
+  if(ps.P) {
+    const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
+    ps.bound_chunks += n / usable + 2;
+    ps.pending = true;
+    PartDev pd = part_dev(e);
+    TableDev T = table_dev(e, e->tab);
+    const size_t smem = (size_t)e->nbytes * 256 * 8 + PMAX * 8;
+    const int grid = (int)std::min<uint64_t>((n + 1024ull * QSYM - 1) / (1024ull * QSYM), (uint64_t)e->n_sm);
+    if(e->kw == 1) {
+      cudaFuncSetAttribute(stage_keys_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      stage_keys_kernel<1><<<grid, 1024, smem, st>>>(T, pd, e->tab.lut.as<uint64_t>(), e->nbytes, (const uint64_t*)dev_keys, n, nullptr);
+    } else {
+      cudaFuncSetAttribute(stage_keys_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      stage_keys_kernel<2><<<grid, 1024, smem, st>>>(T, pd, e->tab.lut.as<uint64_t>(), e->nbytes, (const uint64_t*)dev_keys, n, nullptr);
+    }
+    JF_LAUNCHED();
+    CUDA_OK(e, cudaGetLastError());
+  } else {
+    rc = insert_keys_into(e, e->tab, (const uint64_t*)dev_keys, nullptr, n, st);
+    if(rc) return rc;
+  }
   cudaEventRecord(e->ev_t1, st);
   CUDA_OK(e, cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms;

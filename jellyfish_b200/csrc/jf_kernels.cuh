@@ -712,6 +712,82 @@ __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartD
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// K1c: packed keys -> records appended to the per-CTA chunk lists (the receive side of the
+//      multi-GPU all-to-all in region-by-region mode: same record pool, same K2 afterwards).
+// ---------------------------------------------------------------------------------------
+template<int KW>
+__global__ void __launch_bounds__(1024, 1) stage_keys_kernel(TableDev T, PartDev pd, const uint64_t* __restrict__ lut_g, uint32_t nbytes,
+                                                              const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ spill_keys_unused) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* st_cnt = reinterpret_cast<uint32_t*>(lut + nbytes * 256);
+  uint32_t* st_chunk = st_cnt + PMAX;
+  const int tid = threadIdx.x;
+  for(uint32_t i = tid; i < nbytes * 256u; i += blockDim.x) lut[i] = lut_g[i];
+  uint32_t* my_chunk = pd.cta_chunk + (size_t)blockIdx.x * pd.P;
+  uint32_t* my_fill  = pd.cta_fill + (size_t)blockIdx.x * pd.P;
+  for(uint32_t p = tid; p < pd.P; p += blockDim.x) {
+    uint32_t c = my_chunk[p], f = my_fill[p];
+    if(c == NO_CHUNK) {
+      c = atomicAdd(pd.pool_next, 1u); f = 0;
+      if(c >= pd.n_chunks) { atomicAdd(&T.stats[STAT_POOL_FULL], 1ull); c = NO_CHUNK; f = pd.chunk_recs; }
+    }
+    st_chunk[p] = c; st_cnt[p] = f;
+  }
+  __syncthreads();
+  const uint32_t hb = T.fbits - T.rbits;
+  // an iteration = QSYM keys per thread (the arrival rate the roll-over margin was sized for)
+  const uint64_t per_iter = (uint64_t)blockDim.x * QSYM;
+  const uint64_t iters = (n + per_iter * gridDim.x - 1) / (per_iter * gridDim.x);
+  for(uint64_t it = 0; it < iters; ++it) {
+    const uint64_t base_i = (it * gridDim.x + blockIdx.x) * per_iter;
+    for(uint32_t q = 0; q < (uint32_t)QSYM; ++q) {
+      const uint64_t i = base_i + (uint64_t)q * blockDim.x + tid;       // coalesced key loads
+      if(i >= n) break;
+      uint64_t key[KW];
+#pragma unroll
+      for(int w = 0; w < KW; ++w) key[w] = keys[i * KW + w];
+      const uint64_t pos = gf2_hash<KW>(lut, key, (int)nbytes);
+      const uint64_t lpos = pos & T.local_mask;
+      const uint32_t p = (uint32_t)(lpos >> pd.region_bits);
+      const uint64_t rel = lpos & ((1ull << pd.region_bits) - 1ull);
+      const u128 high = key_high<KW>(key, T.lsize);
+      u128 rec;
+      if(hb == 0)       { rec.lo = rel; rec.hi = 0; }
+      else if(hb < 64)  { rec.lo = high.lo | (rel << hb); rec.hi = high.hi | (rel >> (64 - hb)); }
+      else              { rec.lo = high.lo; rec.hi = high.hi | (rel << (hb - 64)); }
+      const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
+      if(slot < pd.chunk_recs) {
+        uint8_t* dst = pd.pool + (size_t)st_chunk[p] * CHUNK_BYTES;
+        if(pd.rec_bytes == 4) reinterpret_cast<uint32_t*>(dst)[slot] = (uint32_t)rec.lo;
+        else if(pd.rec_bytes == 8) reinterpret_cast<uint64_t*>(dst)[slot] = rec.lo;
+        else { reinterpret_cast<uint64_t*>(dst)[2 * slot] = rec.lo; reinterpret_cast<uint64_t*>(dst)[2 * slot + 1] = rec.hi; }
+      } else {
+        unsigned long long at = atomicAdd(pd.spill_n, 1ull);
+        if(at < pd.spill_cap) {
+#pragma unroll
+          for(int w = 0; w < KW; ++w) pd.spill_keys[at * KW + w] = key[w];
+          pd.spill_counts[at] = 1;
+        } else atomicAdd(&T.stats[STAT_POOL_FULL], 1ull);
+      }
+    }
+    __syncthreads();
+    for(uint32_t p = tid; p < pd.P; p += blockDim.x) {
+      const uint32_t c = st_cnt[p];
+      if(c + pd.margin > pd.chunk_recs) {
+        const uint32_t old = st_chunk[p];
+        if(old != NO_CHUNK) pd.dir[old] = make_uint2(p, min(c, pd.chunk_recs));
+        uint32_t nc = atomicAdd(pd.pool_next, 1u);
+        if(nc >= pd.n_chunks) { atomicAdd(&T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
+        else { st_chunk[p] = nc; st_cnt[p] = 0; }
+      }
+    }
+    __syncthreads();
+  }
+  for(uint32_t p = tid; p < pd.P; p += blockDim.x) { my_chunk[p] = st_chunk[p]; my_fill[p] = min(st_cnt[p], pd.chunk_recs); }
+}
+
 // ---- lean specialisation of K2 for the common geometry: 32-bit slots and 4-byte records ----
 // Everything is 32-bit arithmetic except the slot index; rare paths (counter carry, hash full)
 // are kept out of line so that the kernel runs with 32 registers, i.e. 2048 threads per SM: the

@@ -206,8 +206,9 @@ def test_partitioned_insertion_matches_golden(name, built, inputs):
             assert jfutil.md5(body) == g["body_md5"], (name, pool)
 
 
-@pytest.mark.parametrize("name,world", [("k21C", 2), ("multi_files", 4), ("k63_multi", 2), ("k31C", 8)])
-def test_route_and_shards_on_one_gpu(name, world, built, workdir, inputs):
+@pytest.mark.parametrize("name,world,part", [("k21C", 2, 0), ("multi_files", 4, 0), ("k63_multi", 2, 0), ("k31C", 8, 0),
+                                             ("k21C", 2, 1), ("k63_multi", 4, 1), ("multi_files", 2, 1), ("ovf32", 2, 1)])
+def test_route_and_shards_on_one_gpu(name, world, part, built, workdir, inputs):
     """The multi-GPU data path without NCCL: one engine per shard on the same device; keys bucketed
     by `jfgpu_extract_route`, handed to their owner's `jfgpu_insert_keys`, shard dumps concatenated."""
     import torch
@@ -217,7 +218,9 @@ def test_route_and_shards_on_one_gpu(name, world, built, workdir, inputs):
     k = int(args[args.index("-m") + 1])
     v = args[args.index("-s") + 1]
     size = int(v[:-1]) * {"k": 10**3, "M": 10**6, "G": 10**9}[v[-1]] if v[-1] in "kMG" else int(v)
-    shards = [HashCounter(size, 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world, allow_regrow=False, max_batch_bytes=200000)
+    # part=1: the owner turns the received keys into region records (K1c) and inserts them region by region
+    shards = [HashCounter(size, 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world, allow_regrow=False, max_batch_bytes=200000,
+                          part_min_mb=part, pool_bytes=(256 << 20) if part else 0)
               for r in range(world)]
     kw = shards[0].key_words
     cap = 400000
@@ -244,7 +247,7 @@ def test_route_and_shards_on_one_gpu(name, world, built, workdir, inputs):
             off += ln
             if off >= len(data):
                 break
-    out = os.path.join(workdir, "route1_%s_%d" % (name, world))
+    out = os.path.join(workdir, "route1_%s_%d_%d" % (name, world, part))
     n_ins = 0
     for r, hc in enumerate(shards):
         st = hc.done()
