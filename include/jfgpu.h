@@ -183,6 +183,9 @@ int  jfgpu_synth_fasta_device(int device, void* dev_out, uint64_t capacity, uint
 /* Pinned host memory for jfgpu_feed sources and dump sinks. */
 void* jfgpu_host_alloc(size_t bytes);
 void  jfgpu_host_free(void* p);
+/* cudaMemcpyAsync host->device on `stream` (NULL = legacy default stream) for callers that have no
+ * CUDA binding of their own; with memory from jfgpu_host_alloc the copy is asynchronous. */
+int   jfgpu_memcpy_h2d(void* dev_dst, const void* host_src, size_t bytes, void* stream);
 /* Number of engine kernels launched so far by this process (bench "gpu_launches"). */
 uint64_t jfgpu_kernel_launches(void);
 const char* jfgpu_version(void);

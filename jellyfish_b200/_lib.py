@@ -16,7 +16,7 @@ SYMBOLS = [
     "jfgpu_extract_route", "jfgpu_insert_keys", "jfgpu_clear", "jfgpu_finish", "jfgpu_get_stats",
     "jfgpu_table_info_get", "jfgpu_dump", "jfgpu_lookup", "jfgpu_histogram",
     "jfgpu_reference_matrix", "jfgpu_synth_fasta_bytes", "jfgpu_synth_fasta_device",
-    "jfgpu_host_alloc", "jfgpu_host_free", "jfgpu_kernel_launches", "jfgpu_version",
+    "jfgpu_host_alloc", "jfgpu_host_free", "jfgpu_memcpy_h2d", "jfgpu_kernel_launches", "jfgpu_version",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_FULL, ERR_FORMAT, ERR_STATE, ERR_NOMEM, ERR_SINK = range(8)
@@ -105,6 +105,8 @@ def load():
     lib.jfgpu_host_alloc.restype = C.c_void_p
     lib.jfgpu_host_free.argtypes = [C.c_void_p]
     lib.jfgpu_host_free.restype = None
+    lib.jfgpu_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.jfgpu_memcpy_h2d.restype = C.c_int
     lib.jfgpu_kernel_launches.argtypes = []
     lib.jfgpu_kernel_launches.restype = C.c_uint64
     lib.jfgpu_version.argtypes = []

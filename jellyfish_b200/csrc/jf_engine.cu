@@ -61,9 +61,10 @@ struct Table {
   unsigned lsize = 0, local_lsize = 0, max_reprobe = 0, rbits = 1, fbits = 1, slot_bits = 32, hb = 0;
   uint64_t size = 0, local_size = 0, margin = 0, local_slots = 0;
   jfb::gf2_matrix M, Minv;
-  DevBuf slots, lut, inv_lut, ovf_keys, ovf_vals;
+  DevBuf slots, lut, inv_lut, ovf_keys, ovf_vals, lut11;
+  uint64_t prow[8] = {0,0,0,0,0,0,0,0}; unsigned n_prow = 0; bool hash_fast = false;
   std::vector<uint64_t> reprobes;
-  void release() { slots.free(); lut.free(); inv_lut.free(); ovf_keys.free(); ovf_vals.free(); }
+  void release() { slots.free(); lut.free(); inv_lut.free(); ovf_keys.free(); ovf_vals.free(); lut11.free(); }
   size_t bytes() const { return (size_t)local_slots * (slot_bits / 8); }
 };
 
@@ -185,7 +186,33 @@ int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix
   CUDA_OK(e, t.inv_lut.alloc(l2.size() * 8));
   CUDA_OK(e, cudaMemcpyAsync(t.lut.p, l1.data(), l1.size() * 8, cudaMemcpyHostToDevice, e->cs));
   CUDA_OK(e, cudaMemcpyAsync(t.inv_lut.p, l2.data(), l2.size() * 8, cudaMemcpyHostToDevice, e->cs));
-  CUDA_OK(e, cudaStreamSynchronize(e->cs));     // l1/l2 are about to go out of scope
+  // fast hash tables: 2k <= 44 -> four 11-bit chunks; entries = low 32 bits of the partial products,
+  // position bits 32.. come from parity rows
+  t.hash_fast = false; t.n_prow = 0;
+  std::vector<uint32_t> l11;
+  if(e->kw == 1 && kbits <= 44 && lsize <= 40) {
+    l11.assign(4 * 2048, 0);
+    auto colsel = [&](unsigned i) -> uint64_t {       // contribution of key bit i
+      if(i >= t.M.c()) return 0;
+      if(t.M.is_identity()) return i < t.M.r() ? ((uint64_t)1 << i) : 0;
+      return t.M[t.M.c() - 1 - i];
+    };
+    for(unsigned tb = 0; tb < 4; ++tb)
+      for(unsigned v = 0; v < 2048; ++v) {
+        uint64_t x = 0;
+        for(unsigned j = 0; j < 11; ++j) if(v & (1u << j)) x ^= colsel(tb * 11 + j);
+        l11[tb * 2048 + v] = (uint32_t)x;
+      }
+    for(unsigned ob = 32; ob < lsize; ++ob) {
+      uint64_t row = 0;
+      for(unsigned i = 0; i < kbits; ++i) if((colsel(i) >> ob) & 1) row |= (uint64_t)1 << i;
+      t.prow[t.n_prow++] = row;
+    }
+    CUDA_OK(e, t.lut11.alloc(l11.size() * 4));
+    CUDA_OK(e, cudaMemcpyAsync(t.lut11.p, l11.data(), l11.size() * 4, cudaMemcpyHostToDevice, e->cs));
+    t.hash_fast = true;
+  }
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));     // the host vectors are about to go out of scope
   return JFGPU_OK;
 }
 
@@ -209,8 +236,8 @@ int dispatch(jfgpu_engine* e, unsigned kw, unsigned sb, F&& f) {
 }
 
 template<int NTH>
-size_t count_smem_bytes(unsigned nbytes, size_t stage_bytes) {
-  return ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15) + (size_t)nbytes * 256 * 8 + (stage_bytes ? PMAX * 4 + stage_bytes : 0);
+size_t count_smem_bytes(size_t lut_bytes, size_t stage_bytes) {
+  return ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + (stage_bytes ? PMAX * 4 + stage_bytes : 0);
 }
 
 int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
@@ -255,7 +282,7 @@ void part_configure(jfgpu_engine* e) {
     const uint32_t rec = bits <= 32 ? 4 : bits <= 64 ? 8 : bits <= 128 ? 16 : 0;
     if(!rec) return;
     // records arriving per region between two roll-over passes: 1024 threads x QSYM symbols / P
-    const double mean = 1024.0 * QSYM / P;
+    const double mean = 2.0 * 1024.0 * QSYM / P;              // (roll-over runs every second iteration)
     const uint32_t margin = (uint32_t)(mean + 6.0 * sqrt(mean) + 8.0);
     if(margin * 2 > CHUNK_BYTES / rec) return;               // chunks would be closed half empty: insert directly
     ps.P = P; ps.region_bits = region_bits; ps.rec_bytes = rec; ps.cap = 0; ps.flush_min = 0; ps.margin = margin;
@@ -439,7 +466,10 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   a.tile_state = e->tstate.as<uint8_t>();
   a.carry_in = e->carry[e->carry_cur].as<Carry>();
   a.carry_out = e->carry[e->carry_cur ^ 1].as<Carry>();
-  a.lut = e->tab.lut.as<uint64_t>();
+  a.lut = e->tab.hash_fast ? e->tab.lut11.as<uint64_t>() : e->tab.lut.as<uint64_t>();
+  a.hash_fast = e->tab.hash_fast ? 1 : 0; a.n_prow = e->tab.n_prow;
+  a.lut_bytes = e->tab.hash_fast ? 4 * 2048 * 4 : e->nbytes * 256 * 8;
+  for(unsigned i = 0; i < 8; ++i) a.prow[i] = e->tab.prow[i];
   a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode;
   a.T = table_dev(e, e->tab);
   a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
@@ -461,9 +491,9 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   };
   rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
     constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
-    if(part)      return launch(count_kernel<kw, sb, 2, 1024>, 1024, count_smem_bytes<1024>(e->nbytes, ps.stage_bytes), true);
-    if(mode == 1) return launch(count_kernel<kw, sb, 1, 512>, 512, count_smem_bytes<512>(e->nbytes, 0), false);
-    return launch(count_kernel<kw, sb, 0, 512>, 512, count_smem_bytes<512>(e->nbytes, 0), false);
+    if(part)      return launch(count_kernel<kw, sb, 2, 1024>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes), true);
+    if(mode == 1) return launch(count_kernel<kw, sb, 1, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
+    return launch(count_kernel<kw, sb, 0, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
   });
   if(rc) return rc;
   JF_LAUNCHED();
@@ -706,6 +736,10 @@ const char* jfgpu_last_error(jfgpu_handle h) { return h ? h->err.c_str() : g_cre
 
 void* jfgpu_host_alloc(size_t bytes) { void* p = nullptr; if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void jfgpu_host_free(void* p) { if(p) cudaFreeHost(p); }
+int jfgpu_memcpy_h2d(void* dev_dst, const void* host_src, size_t bytes, void* stream) {
+  if(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return JFGPU_ERR_CUDA; }
+  return JFGPU_OK;
+}
 
 int jfgpu_reference_matrix(uint32_t r, uint32_t c, uint32_t skip, uint64_t* cols) {
   if(r == 0 || r > 64 || c == 0 || !cols) return JFGPU_ERR_ARG;

@@ -152,6 +152,13 @@ struct CountArgs {
   unsigned long long* route_counts;
   uint64_t       route_cap;
   uint32_t       shard_bits;
+  // fast hash (2k <= 44): four 11-bit-indexed tables of 32-bit entries give the low 32 position bits,
+  // the few bits above come from parity rows
+  uint32_t       hash_fast;
+  uint32_t       n_prow;
+  uint32_t       lut_bytes;     // bytes of hash tables to stage in shared memory
+  uint32_t       pad1;
+  uint64_t       prow[8];
 };
 
 // Slow path: walk backwards from byte position `end` (exclusive) of the batch collecting
@@ -274,14 +281,15 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
   CountSmemT<NTH>& sm = *reinterpret_cast<CountSmemT<NTH>*>(smem_raw);
   uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15));
   // MODE 2 only, behind the hash tables: per region, fill count and id of this CTA's open chunk
-  uint32_t* st_cnt = reinterpret_cast<uint32_t*>(lut + a.nbytes * 256);
+  uint32_t* st_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes);
   uint32_t* st_chunk = st_cnt + PMAX;
+  const uint32_t* lut32 = reinterpret_cast<const uint32_t*>(lut);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t k = a.k;
   const uint64_t n = a.n;
 
-  for(uint32_t i = tid; i < a.nbytes * 256u; i += NTH) lut[i] = a.lut[i];
+  for(uint32_t i = tid; i < a.lut_bytes / 8; i += NTH) lut[i] = a.lut[i];
   uint32_t* my_chunk = MODE == 2 ? pd.cta_chunk + (size_t)blockIdx.x * pd.P : nullptr;
   uint32_t* my_fill  = MODE == 2 ? pd.cta_fill + (size_t)blockIdx.x * pd.P : nullptr;
   if(MODE == 2) {
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
   };
 
   LocalStats ls = { 0, 0, 0, 0, 0 };
-  uint32_t phase = 0;
+  uint32_t phase = 0, since_roll = 0;
   uint64_t t = blockIdx.x;
   if(t < a.n_tiles && tid == 0) issue(t);
 
@@ -510,7 +518,14 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
 #pragma unroll
             for(int q = 0; q < KW; ++q) key[q] = use_rc ? rc[q] : m[q];
             ls.kmers++;
-            const uint64_t pos = gf2_hash<KW>(lut, key, (int)a.nbytes);
+            uint64_t pos;
+            if(KW == 1 && a.hash_fast) {
+              const uint64_t kk = key[0];
+              uint32_t h32 = lut32[(uint32_t)kk & 2047u] ^ lut32[2048 + ((uint32_t)(kk >> 11) & 2047u)] ^
+                             lut32[4096 + ((uint32_t)(kk >> 22) & 2047u)] ^ lut32[6144 + (uint32_t)(kk >> 33)];
+              pos = h32;
+              for(uint32_t jb = 0; jb < a.n_prow; ++jb) pos |= (uint64_t)(__popcll(kk & a.prow[jb]) & 1) << (32 + jb);
+            } else pos = gf2_hash<KW>(lut, key, (int)a.nbytes);
             if(MODE == 0) {
               if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;
               else { ls.failed++; record_failure<KW>(a.T, key, 1); }
@@ -557,7 +572,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
           }
         }
       }
-      if(MODE == 2) rollover_pass();
+      if(MODE == 2 && ((++since_roll) & 1) == 0) rollover_pass();
     }
     __syncthreads();     // all reads of sym[] done before the next window overwrites it
   }

@@ -137,7 +137,9 @@ class ShardedCounter(object):
     def _add_host_text(self, hptr, n, begin, end):
         if self._host_stage is None:
             self._host_stage = torch.empty(self.batch_bytes + 256, dtype=torch.uint8, device=self.dev)
-        cudart = torch.cuda.cudart()
+        from . import _lib
+        lib = _lib.load()
+        import ctypes as C
         off = 0
         rounds = (n + self.batch_bytes - 1) // self.batch_bytes
         t = torch.tensor([rounds], dtype=torch.int64, device=self.dev)
@@ -146,8 +148,9 @@ class ShardedCounter(object):
             ln = max(0, min(self.batch_bytes, n - off))
             self.counts.zero_()
             if ln:
-                self.stream.synchronize()
-                cudart.cudaMemcpy(self._host_stage.data_ptr(), hptr + off, ln, 1)   # cudaMemcpyHostToDevice (synchronous)
+                # host -> device on the working stream (asynchronous for pinned memory)
+                if lib.jfgpu_memcpy_h2d(C.c_void_p(self._host_stage.data_ptr()), C.c_void_p(hptr + off), ln, C.c_void_p(self.stream.cuda_stream)):
+                    raise RuntimeError("host to device copy failed")
                 self.backend.extract_route((self._host_stage.data_ptr(), ln), begin and off == 0, end and off + ln >= n,
                                            self.send, self.capacity, self.counts)
             exchange_and_insert(self.backend, self.world, self.send, self.counts, self.capacity, self.recv)
