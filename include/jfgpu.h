@@ -132,11 +132,14 @@ int  jfgpu_feed_device(jfgpu_handle h, const void* dev_bytes, size_t n, uint32_t
  * (top bits of the hash position).  dev_keys: n_shards * capacity packed keys
  * (8 bytes each for k<=32, 16 for k<=64), bucket d at offset d*capacity;
  * dev_counts: n_shards uint64 counters (accumulated; caller zeroes).
- * Returns JFGPU_ERR_FULL if a bucket overflowed (counts still exact, keys truncated). */
+ * Returns JFGPU_ERR_FULL if a bucket overflowed (counts still exact, keys truncated).
+ * With a caller stream and neither FILE flag the call is stream-ordered (no host synchronisation;
+ * an overflow is then reported by jfgpu_finish). */
 int  jfgpu_extract_route(jfgpu_handle h, const void* dev_bytes, size_t n, uint32_t flags,
                          void* dev_keys, uint64_t capacity, uint64_t* dev_counts, void* stream);
 /* Insert n packed keys (as produced by jfgpu_extract_route) that this shard owns:
- * hash_counter::add for each (hash_counter.hpp:91-115). */
+ * hash_counter::add for each (hash_counter.hpp:91-115).  With a caller stream the call is
+ * stream-ordered (returns without synchronising). */
 int  jfgpu_insert_keys(jfgpu_handle h, const void* dev_keys, uint64_t n, void* stream);
 
 /* -- zero the table and the statistics, keep geometry and hash matrix: what the dumper's

@@ -314,6 +314,7 @@ int part_alloc(jfgpu_engine* e) {
   CUDA_OK(e, cudaMemsetAsync(ps.cta_fill.p, 0, ps.cta_fill.bytes, e->cs));
   ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
   ps.pending = false;
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));     // callers may continue on another stream
   return JFGPU_OK;
 }
 
@@ -963,6 +964,7 @@ int jfgpu_extract_route(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_
     off += len;
   }
   e->bytes_fed += n;
+  if(stream && !(flags & (JFGPU_FILE_BEGIN | JFGPU_FILE_END))) return JFGPU_OK;   // stream-ordered: the caller synchronises; drops are reported by jfgpu_finish
   CUDA_OK(e, cudaStreamSynchronize(st));
   rc = end_feed(e, flags, st);
   if(rc) return rc;
@@ -977,7 +979,7 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
   cudaSetDevice(e->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
   if(n == 0) return JFGPU_OK;
-  cudaEventRecord(e->ev_t0, st);
+  if(!stream) cudaEventRecord(e->ev_t0, st);
   int rc = JFGPU_OK;
   PartState& ps = e->part;
   if(ps.P) {
@@ -1010,6 +1012,7 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
     rc = insert_keys_into(e, e->tab, (const uint64_t*)dev_keys, nullptr, n, st);
     if(rc) return rc;
   }
+  if(stream) return JFGPU_OK;          // stream-ordered: the caller synchronises
   cudaEventRecord(e->ev_t1, st);
   CUDA_OK(e, cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms;
@@ -1070,6 +1073,7 @@ int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
   rc = check_after_batches(e);
   if(rc) return rc;
   if(e->h_stats[STAT_POOL_FULL]) return fail(e, JFGPU_ERR_NOMEM, "internal: k-mer record pool overflow");
+  if(e->h_stats[STAT_ROUTE_DROPPED]) return fail(e, JFGPU_ERR_FULL, "route bucket capacity exceeded");
   rc = direct_index_fixup(e);
   if(rc) return rc;
   if(s) return jfgpu_get_stats(e, s);

@@ -49,16 +49,21 @@ class EngineBackend(RouteBackend):
             self.hc.insert_keys(keys.data_ptr(), n, stream=torch.cuda.current_stream().cuda_stream)
 
 
-def exchange_and_insert(backend, world, send, counts, capacity, recv):
+def exchange_and_insert(backend, world, send, counts, capacity, recv, before_payload=None):
     """Uneven all-to-all of the bucketed keys, then insertion on the owner.
 
     send:   int64 tensor [world, capacity * key_words]; bucket d holds counts[d] keys for rank d
     counts: int64 tensor [world] (device of `send`)
     recv:   int64 tensor [world, capacity * key_words] scratch
+    before_payload: optional callable run after the (host-synchronising) count exchange and before
+        the payload exchange -- the pipelined caller launches the next batch's extraction there, so
+        that it overlaps the NVLink transfer and the insertion of this batch.
     Returns the number of keys this rank received."""
     kw = backend.key_words
     if world == 1:
         n = int(counts[0].item())
+        if before_payload:
+            before_payload()
         backend.insert_keys(send[0], n)
         return n
     recv_counts = torch.empty_like(counts)
@@ -67,11 +72,20 @@ def exchange_and_insert(backend, world, send, counts, capacity, recv):
     rc = recv_counts.tolist()
     if max(sc) > capacity or max(rc) > capacity:
         raise RuntimeError("route bucket capacity exceeded (%d > %d)" % (max(max(sc), max(rc)), capacity))
-    # uneven all-to-all: buckets compacted into one contiguous send tensor, one contiguous receive
-    flat_in = torch.cat([send[d, :sc[d] * kw] for d in range(world)])
-    flat_out = recv.view(-1)[:sum(rc) * kw]
-    dist.all_to_all_single(flat_out, flat_in, output_split_sizes=[c * kw for c in rc], input_split_sizes=[c * kw for c in sc])
+    if before_payload:
+        before_payload()
     total = sum(rc)
+    flat_out = recv.view(-1)[:total * kw]
+    if dist.get_backend() == "nccl":
+        # list form: the buckets are sent straight from where the kernel wrote them (no packing copy)
+        outs, o = [], 0
+        for s in range(world):
+            outs.append(flat_out[o:o + rc[s] * kw])
+            o += rc[s] * kw
+        dist.all_to_all(outs, [send[d, :sc[d] * kw] for d in range(world)])
+    else:
+        flat_in = torch.cat([send[d, :sc[d] * kw] for d in range(world)])
+        dist.all_to_all_single(flat_out, flat_in, output_split_sizes=[c * kw for c in rc], input_split_sizes=[c * kw for c in sc])
     backend.insert_keys(flat_out, total)
     return total
 
@@ -96,6 +110,7 @@ class ShardedCounter(object):
             self.recv = torch.empty((world, self.capacity * kw), dtype=torch.int64, device=self.dev)
             self.counts = torch.zeros(world, dtype=torch.int64, device=self.dev)
         self._host_stage = None
+        self._send2 = self._counts2 = self._sa = None
         # a dedicated (non-default) stream: its handle is passed to the engine so that kernels, tensor
         # ops and NCCL collectives are ordered on one stream (handle 0 would mean "engine stream")
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -110,19 +125,44 @@ class ShardedCounter(object):
         self.stream.synchronize()
 
     def _add_device_text(self, ptr, n, begin, end):
-        off = 0
-        # every rank must take part in every exchange: the number of rounds is agreed on first
+        """Two-stage software pipeline: the extraction of batch i+1 (stream A) overlaps the NVLink
+        exchange and the owner-side insertion of batch i (stream B).  Two send/count buffer sets."""
         rounds = (n + self.batch_bytes - 1) // self.batch_bytes
         t = torch.tensor([rounds], dtype=torch.int64, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        for i in range(int(t.item())):
+        rounds_all = int(t.item())        # every rank takes part in every exchange
+        if self._send2 is None:
+            self._send2 = torch.empty_like(self.send)
+            self._counts2 = torch.zeros_like(self.counts)
+            self._sa = torch.cuda.Stream(device=self.dev)
+        sends, cnts = (self.send, self._send2), (self.counts, self._counts2)
+        sb = self.stream                    # stream B: exchange + insertion
+        sa = self._sa                       # stream A: extraction
+        sa.wait_stream(sb)
+        done_extract = [torch.cuda.Event(), torch.cuda.Event()]
+        done_use = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in done_use:
+            ev.record(sb)
+
+        def launch_extract(i):
+            off = i * self.batch_bytes
             ln = max(0, min(self.batch_bytes, n - off))
-            self.counts.zero_()
-            if ln:
-                self.backend.extract_route((ptr + off, ln), begin and off == 0, end and off + ln >= n,
-                                           self.send, self.capacity, self.counts)
-            exchange_and_insert(self.backend, self.world, self.send, self.counts, self.capacity, self.recv)
-            off += ln
+            with torch.cuda.stream(sa):
+                sa.wait_event(done_use[i & 1])           # the buffers of batch i-2 have been sent
+                cnts[i & 1].zero_()
+                if ln:
+                    self.backend.extract_route((ptr + off, ln), begin and off == 0, end and off + ln >= n,
+                                               sends[i & 1], self.capacity, cnts[i & 1])
+                done_extract[i & 1].record(sa)
+
+        if rounds_all:
+            launch_extract(0)
+        for i in range(rounds_all):
+            sb.wait_event(done_extract[i & 1])
+            nxt = (lambda j=i + 1: launch_extract(j)) if i + 1 < rounds_all else None
+            exchange_and_insert(self.backend, self.world, sends[i & 1], cnts[i & 1], self.capacity, self.recv, before_payload=nxt)
+            done_use[i & 1].record(sb)
+        sa.synchronize()
 
     def add_host_text(self, hptr, n, begin=True, end=True):
         """Host memory (pinned) -> staged through a device buffer batch by batch."""
