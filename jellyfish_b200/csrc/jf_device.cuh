@@ -27,7 +27,7 @@ constexpr uint32_t SYM_BREAK = 4;        // symbols 0..3 = A,C,G,T ; 4 = window 
 
 // stats block indices
 enum { STAT_KMERS = 0, STAT_INSERTED, STAT_DISTINCT, STAT_REPROBES, STAT_OVERFLOWED,
-       STAT_FAILED, STAT_FAIL_DROPPED, STAT_OVF_FULL, STAT_ROUTE_DROPPED, STAT_MAXCOUNT, STAT_POOL_FULL, STAT_N };
+       STAT_FAILED, STAT_FAIL_DROPPED, STAT_OVF_FULL, STAT_ROUTE_DROPPED, STAT_MAXCOUNT, STAT_POOL_FULL, STAT_FORMAT_ERR, STAT_N };
 
 struct Carry {               // parser state handed from one batch to the next (device resident)
   uint32_t state;            // ST_* after the last byte of the previous batch

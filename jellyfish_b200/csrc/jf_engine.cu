@@ -96,7 +96,8 @@ struct jfgpu_engine {
   DevBuf stage[2]; cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
   int stage_cur = 0;
   // per-batch scratch
-  DevBuf nlA, nlB, tstate; uint64_t scratch_tiles = 0;
+  DevBuf nlA, nlB, cntA, cntB, tstate; uint64_t scratch_tiles = 0;
+  int format = 0;                 // 0 = FASTA, 1 = FASTQ: format of the file being fed
   // bookkeeping
   bool in_file = false;
   uint64_t bytes_fed = 0, regrows = 0;
@@ -246,6 +247,8 @@ int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
   CUDA_OK(e, e->nlA.alloc(want * 8));
   CUDA_OK(e, e->nlB.alloc(want * 8));
+  CUDA_OK(e, e->cntA.alloc(want * 4));
+  CUDA_OK(e, e->cntB.alloc(want * 4));
   CUDA_OK(e, e->tstate.alloc(want));
   e->scratch_tiles = want;
   return JFGPU_OK;
@@ -456,10 +459,13 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   rc = ensure_scratch(e, n_tiles);
   if(rc) return rc;
   const int g0 = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 8);
-  nl_scan_kernel<<<g0, 256, 0, stream>>>(dev, n, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>());
+  nl_scan_kernel<<<g0, 256, 0, stream>>>(dev, n, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>(), e->cntA.as<uint32_t>(), e->cntB.as<uint32_t>());
   JF_LAUNCHED();
-  tile_state_kernel<<<1, 1024, 0, stream>>>(dev, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>(),
-                                            e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
+  if(e->format == 1)
+    tile_state_fastq_kernel<<<1, 1024, 0, stream>>>(n_tiles, e->cntA.as<uint32_t>(), e->cntB.as<uint32_t>(), e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
+  else
+    tile_state_kernel<<<1, 1024, 0, stream>>>(dev, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>(),
+                                              e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
   JF_LAUNCHED();
   CountArgs a;
   memset(&a, 0, sizeof(a));
@@ -471,7 +477,7 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   a.hash_fast = e->tab.hash_fast ? 1 : 0; a.n_prow = e->tab.n_prow;
   a.lut_bytes = e->tab.hash_fast ? 4 * 2048 * 4 : e->nbytes * 256 * 8;
   for(unsigned i = 0; i < 8; ++i) a.prow[i] = e->tab.prow[i];
-  a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode;
+  a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode; a.format = (uint32_t)e->format;
   a.T = table_dev(e, e->tab);
   a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
   PartDev pd = part_dev(e);
@@ -505,7 +511,8 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
 
 int reset_carry(jfgpu_engine* e, cudaStream_t stream) {
   Carry c;
-  c.state = ST_L; c.pad = 0;
+  c.state = e->format == 1 ? (0u | 4u) : (uint32_t)ST_L;    // FASTQ: header line expected, at a line start
+  c.pad = 0;
   memset(c.sym, SYM_BREAK, sizeof(c.sym));
   // (stream ordered; source is copied synchronously into the driver's staging for pageable memory)
   CUDA_OK(e, cudaMemcpyAsync(e->carry[e->carry_cur].p, &c, sizeof(c), cudaMemcpyHostToDevice, stream));
@@ -832,7 +839,7 @@ void jfgpu_destroy(jfgpu_handle e) {
     if(e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
     if(e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
   }
-  e->nlA.free(); e->nlB.free(); e->tstate.free();
+  e->nlA.free(); e->nlB.free(); e->cntA.free(); e->cntB.free(); e->tstate.free();
   if(e->h_stats) cudaFreeHost(e->h_stats);
   if(e->ev_t0) cudaEventDestroy(e->ev_t0);
   if(e->ev_t1) cudaEventDestroy(e->ev_t1);
@@ -845,10 +852,8 @@ void jfgpu_destroy(jfgpu_handle e) {
 static int begin_feed(jfgpu_engine* e, uint32_t flags, int first_byte, cudaStream_t st) {
   if(flags & JFGPU_FILE_BEGIN) {
     // mer_overlap_sequence_parser.hpp:134-148: the first byte selects the format
-    if(first_byte >= 0 && first_byte != '>') {
-      if(first_byte == '@') return fail(e, JFGPU_ERR_FORMAT, "FASTQ input is not supported by the device parser yet");
-      return fail(e, JFGPU_ERR_FORMAT, "Unsupported format");
-    }
+    if(first_byte >= 0 && first_byte != '>' && first_byte != '@') return fail(e, JFGPU_ERR_FORMAT, "Unsupported format");
+    e->format = first_byte == '@' ? 1 : 0;
     int rc = reset_carry(e, st);
     if(rc) return rc;
     e->in_file = true;
@@ -859,6 +864,7 @@ static int begin_feed(jfgpu_engine* e, uint32_t flags, int first_byte, cudaStrea
 static int end_feed(jfgpu_engine* e, uint32_t flags, cudaStream_t st) {
   if(flags & JFGPU_FILE_END) {
     // no k-mer spans two files: mer_overlap_sequence_parser.hpp:111
+    e->format = 0;
     int rc = reset_carry(e, st);
     if(rc) return rc;
     e->in_file = false;
@@ -1072,6 +1078,7 @@ int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
   CUDA_OK(e, cudaGetLastError());
   rc = check_after_batches(e);
   if(rc) return rc;
+  if(e->h_stats[STAT_FORMAT_ERR]) return fail(e, JFGPU_ERR_FORMAT, "Invalid fastq sequence (the device parser reads 4-line FASTQ records: '@' header, sequence, '+', qualities)");
   if(e->h_stats[STAT_POOL_FULL]) return fail(e, JFGPU_ERR_NOMEM, "internal: k-mer record pool overflow");
   if(e->h_stats[STAT_ROUTE_DROPPED]) return fail(e, JFGPU_ERR_FULL, "route bucket capacity exceeded");
   rc = direct_index_fixup(e);

@@ -20,13 +20,16 @@ namespace jfk {
 //      A = [start, start+TILE-HALO) and in B = [start+TILE-HALO, start+TILE); -1 if none.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nl_scan_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t n_tiles, uint32_t TILE,
-                                                      long long* __restrict__ nlA, long long* __restrict__ nlB) {
+                                                      long long* __restrict__ nlA, long long* __restrict__ nlB,
+                                                      uint32_t* __restrict__ cntA, uint32_t* __restrict__ cntB) {
   __shared__ long long sA[8], sB[8];
+  __shared__ uint32_t sCA[8], sCB[8];
   for(uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const uint64_t start = t * (uint64_t)TILE;
     const uint64_t end = min(n, start + (uint64_t)TILE);
     const uint64_t split = start + (uint64_t)(TILE - HALO);
     long long a = -1, b = -1;
+    uint32_t ca = 0, cb = 0;
     // 16-byte vectors; the tile start is 16-byte aligned
     const uint64_t nvec = (end - start) / 16;
     const uint4* v = reinterpret_cast<const uint4*>(in + start);
@@ -41,25 +44,27 @@ __global__ void __launch_bounds__(256) nl_scan_kernel(const uint8_t* __restrict_
           for(int q = 0; q < 4; ++q) {
             if(((w[j] >> (8 * q)) & 0xFFu) == 0x0Au) {
               long long p = (long long)(start + i * 16 + j * 4 + q);
-              if((uint64_t)p < split) a = max(a, p); else b = max(b, p);
+              if((uint64_t)p < split) { a = max(a, p); ++ca; } else { b = max(b, p); ++cb; }
             }
           }
         }
       }
     }
     for(uint64_t p = start + nvec * 16 + threadIdx.x; p < end; p += blockDim.x) {
-      if(in[p] == '\n') { if(p < split) a = max(a, (long long)p); else b = max(b, (long long)p); }
+      if(in[p] == '\n') { if(p < split) { a = max(a, (long long)p); ++ca; } else { b = max(b, (long long)p); ++cb; } }
     }
 #pragma unroll
     for(int o = 16; o; o >>= 1) {
       a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
       b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+      ca += __shfl_xor_sync(0xffffffffu, ca, o);
+      cb += __shfl_xor_sync(0xffffffffu, cb, o);
     }
-    if((threadIdx.x & 31) == 0) { sA[threadIdx.x >> 5] = a; sB[threadIdx.x >> 5] = b; }
+    if((threadIdx.x & 31) == 0) { sA[threadIdx.x >> 5] = a; sB[threadIdx.x >> 5] = b; sCA[threadIdx.x >> 5] = ca; sCB[threadIdx.x >> 5] = cb; }
     __syncthreads();
     if(threadIdx.x == 0) {
-      for(int i = 1; i < (int)(blockDim.x >> 5); ++i) { a = max(a, sA[i]); b = max(b, sB[i]); }
-      nlA[t] = a; nlB[t] = b;
+      for(int i = 1; i < (int)(blockDim.x >> 5); ++i) { a = max(a, sA[i]); b = max(b, sB[i]); ca += sCA[i]; cb += sCB[i]; }
+      nlA[t] = a; nlB[t] = b; cntA[t] = ca; cntB[t] = cb;
     }
     __syncthreads();
   }
@@ -108,6 +113,27 @@ __global__ void __launch_bounds__(1024) tile_state_kernel(const uint8_t* __restr
   }
 }
 
+// FASTQ: line type at the start of every window = (type at the batch start + newlines before it) mod 4
+__global__ void __launch_bounds__(1024) tile_state_fastq_kernel(uint64_t n_tiles, const uint32_t* __restrict__ cntA, const uint32_t* __restrict__ cntB,
+                                                                const Carry* __restrict__ carry_in, uint8_t* __restrict__ tile_state) {
+  __shared__ uint32_t part[1024];
+  const uint64_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+  const uint64_t lo = min(n_tiles, per * threadIdx.x), hi = min(n_tiles, lo + per);
+  uint32_t m = 0;
+  for(uint64_t u = lo; u < hi; ++u) m += cntA[u] + cntB[u];
+  part[threadIdx.x] = m;
+  __syncthreads();
+  if(threadIdx.x == 0) { uint32_t run = 0; for(int i = 0; i < (int)blockDim.x; ++i) { uint32_t x = part[i]; part[i] = run; run += x; } }
+  __syncthreads();
+  uint32_t mu = part[threadIdx.x];     // newlines in tiles < u (mod 2^32 is fine: only mod 4 matters)
+  const uint32_t ctype = carry_in->state & 3u;
+  if(threadIdx.x == 0 && n_tiles) tile_state[0] = (uint8_t)ctype;
+  for(uint64_t u = lo; u < hi; ++u) {
+    if(u + 1 < n_tiles) tile_state[u + 1] = (uint8_t)((ctype + mu + cntA[u]) & 3u);
+    mu += cntA[u] + cntB[u];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // parser state machine helpers (semantics: mer_overlap_sequence_parser.hpp:161-185,260-287)
 //   state L (line start): '\n','\r' stay; '>' -> H (new record: emits a window reset, the 'N'
@@ -117,13 +143,20 @@ __global__ void __launch_bounds__(1024) tile_state_kernel(const uint8_t* __restr
 //   state H (in header)  : '\n' -> L; everything else ignored
 // A transition function over {H,S,L} is packed 2 bits per input state.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fn_const(uint32_t s) { return s | (s << 2) | (s << 4); }
+__device__ __forceinline__ uint32_t fn_const(uint32_t s) { return s | (s << 2) | (s << 4) | (s << 6); }
 __device__ __forceinline__ uint32_t fn_apply(uint32_t f, uint32_t s) { return (f >> (2 * s)) & 3u; }
 // first f, then g
 __device__ __forceinline__ uint32_t fn_compose(uint32_t f, uint32_t g) {
-  return fn_apply(g, fn_apply(f, 0)) | (fn_apply(g, fn_apply(f, 1)) << 2) | (fn_apply(g, fn_apply(f, 2)) << 4);
+  return fn_apply(g, fn_apply(f, 0)) | (fn_apply(g, fn_apply(f, 1)) << 2) | (fn_apply(g, fn_apply(f, 2)) << 4) |
+         (fn_apply(g, fn_apply(f, 3)) << 6);
 }
-constexpr uint32_t FN_ID = 0u | (1u << 2) | (2u << 4);
+constexpr uint32_t FN_ID = 0u | (1u << 2) | (2u << 4) | (3u << 6);
+// FASTQ: the state is the line type 0..3 (header '@', sequence, '+', qualities) of 4-line records;
+// a piece of text containing n newlines advances it by n
+__device__ __forceinline__ uint32_t fn_rot(uint32_t n) {
+  n &= 3u;
+  return (n & 3u) | (((1 + n) & 3u) << 2) | (((2 + n) & 3u) << 4) | (((3 + n) & 3u) << 6);
+}
 
 // is the '\r' at position p (inside a sequence line) dropped?  True when the run of '\r'
 // it belongs to is followed by '\n' or by the end of the file.
@@ -157,7 +190,7 @@ struct CountArgs {
   uint32_t       hash_fast;
   uint32_t       n_prow;
   uint32_t       lut_bytes;     // bytes of hash tables to stage in shared memory
-  uint32_t       pad1;
+  uint32_t       format;        // 0 = FASTA, 1 = FASTQ (4-line records)
   uint64_t       prow[8];
 };
 
@@ -207,6 +240,32 @@ __device__ void backfill_symbols(const uint8_t* in, uint64_t n, const Carry* cin
       return;
     }
     cur_end = q;                     // continue with the previous line (the '\n' itself emits nothing)
+  }
+}
+
+// FASTQ slow path: a sequence line is never continued from another line, so the symbols before
+// `end` are those of the same line (back to its '\n'), then a reset; before the batch start the
+// previous batch's carry continues the line.
+__device__ void backfill_fastq(const uint8_t* in, uint64_t n, const Carry* cin, long long end, int need, uint8_t* out) {
+  for(int i = 0; i < need; ++i) out[i] = SYM_BREAK;
+  int got = 0;
+  for(long long p = end - 1; got < need; --p) {
+    if(p < 0) {
+      if((cin->state & 3u) != 1u || (cin->state & 4u)) return;       // the batch did not start inside a sequence line
+      for(int j = PRE - 1; j >= 0 && got < need; --j) {
+        const uint32_t sy = cin->sym[j];
+        if(sy == SYM_BREAK) return;
+        out[need - 1 - got] = (uint8_t)sy; ++got;
+      }
+      return;
+    }
+    const uint32_t b = in[p];
+    if(b == '\n') return;
+    uint32_t sy;
+    if(b == '\r') { if(cr_dropped(in, (uint64_t)p, n)) continue; sy = SYM_BREAK; }
+    else sy = base_symbol(b);
+    if(sy == SYM_BREAK) return;
+    out[need - 1 - got] = (uint8_t)sy; ++got;
   }
 }
 
@@ -364,8 +423,23 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
     int vhi = (wend_ll - g0) < 0 ? 0 : ((wend_ll - g0) > 32 ? 32 : (int)(wend_ll - g0));
     if(vhi < vlo) vhi = vlo;
 
+    // FASTQ needs to know whether a thread's first byte starts a line: remember the byte before it
+    // now, while the window buffer is still intact (it is refilled right after the next barrier)
+    uint32_t prevb = 'x';
+    if(a.format == 1 && vhi > vlo) {
+      const long long gp = g0 + vlo - 1;
+      if(gp < 0) prevb = (a.carry_in->state & 4u) ? '\n' : 'x';
+      else if(tid * 32 + vlo - 1 >= 0) prevb = sm.win[tid * 32 + vlo - 1];
+      else prevb = a.in[gp];
+    }
     uint32_t f;
-    {
+    if(a.format == 1) {
+      uint32_t nnl = 0;
+#pragma unroll
+      for(int i = 0; i < 32; ++i)
+        if(i >= vlo && i < vhi) nnl += (((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu) == '\n');
+      f = fn_rot(nnl);
+    } else {
       uint32_t st = ST_L; bool seen_nl = false;
 #pragma unroll
       for(int i = 0; i < 32; ++i) {
@@ -375,7 +449,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
           else if(st == ST_L && b != '\r') st = (b == '>') ? ST_H : ST_S;
         }
       }
-      f = seen_nl ? fn_const(st) : ((uint32_t)ST_H | ((uint32_t)ST_S << 2) | (st << 4));
+      f = seen_nl ? fn_const(st) : ((uint32_t)ST_H | ((uint32_t)ST_S << 2) | (st << 4) | (3u << 6));
       if(vhi == vlo) f = FN_ID;
     }
     uint32_t inc = f;
@@ -388,7 +462,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
     __syncthreads();
     // every thread holds its bytes: the window buffer is free, fetch the next window now
     { const uint64_t tn = t + gridDim.x; if(tn < a.n_tiles && tid == 0) issue(tn); }
-    uint32_t entry = (t == 0) ? a.carry_in->state : (uint32_t)a.tile_state[t];
+    uint32_t entry = (t == 0) ? (a.format == 1 ? (a.carry_in->state & 3u) : a.carry_in->state) : (uint32_t)a.tile_state[t];
     uint32_t wpre = FN_ID;
     for(int i = 0; i < warp; ++i) wpre = fn_compose(wpre, sm.warp_fn[i]);
     uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
@@ -399,7 +473,36 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
     // ---- phase C: emit symbols (4 bits each, 32 max) ----
     uint64_t pk0 = 0, pk1 = 0;
     uint32_t cnt = 0; bool brk = false;
-    {
+    if(a.format == 1) {
+      // FASTQ, 4-line records (mer_overlap_sequence_parser.hpp:187-217): only sequence lines emit
+      // symbols; the start of a header line emits the window reset ('N' between reads, :205);
+      // '@' / '+' at the line starts are verified (else "Invalid fastq sequence", :304-306)
+      uint32_t ty = st_in; bool at_start = prevb == '\n';
+#pragma unroll
+      for(int i = 0; i < 32; ++i) {
+        if(i >= vlo && i < vhi) {
+          uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+          uint32_t sy = 8;
+          if(b == '\n') { ty = (ty + 1) & 3u; at_start = true; }
+          else {
+            if(at_start && b != '\r') {
+              at_start = false;
+              if(ty == 0) { sy = SYM_BREAK; if(b != '@') atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull); }
+              else if(ty == 2 && b != '+') atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull);
+            }
+            if(ty == 1) {
+              if(b == '\r') { if(!cr_dropped(a.in, (uint64_t)(g0 + i), a.n_look)) sy = SYM_BREAK; }
+              else sy = base_symbol(b);
+            }
+          }
+          if(sy != 8) {
+            if(cnt < 16) pk0 |= (uint64_t)sy << (4 * cnt); else pk1 |= (uint64_t)sy << (4 * (cnt - 16));
+            brk |= (sy == SYM_BREAK);
+            ++cnt;
+          }
+        }
+      }
+    } else {
       uint32_t st = st_in;
 #pragma unroll
       for(int i = 0; i < 32; ++i) {
@@ -456,9 +559,11 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
       } else {
         sm.sym[lane] = SYM_BREAK; sm.sym[lane + 32] = SYM_BREAK;
         __syncwarp();
-        if(lane == 0 && a.tile_state[t] != ST_H && idx0 < k - 1 && !sm.halo_break) {
+        const bool in_seq = a.format == 1 ? (a.tile_state[t] == 1) : (a.tile_state[t] != ST_H);
+        if(lane == 0 && in_seq && idx0 < k - 1 && !sm.halo_break) {
           // pathological input (very short lines / long runs of blank lines): exact slow path
-          backfill_symbols(a.in, a.n_look, a.carry_in, h, -2, PRE, sm.sym);
+          if(a.format == 1) backfill_fastq(a.in, a.n_look, a.carry_in, h, PRE, sm.sym);
+          else backfill_symbols(a.in, a.n_look, a.carry_in, h, -2, PRE, sm.sym);
         }
       }
     }
@@ -467,12 +572,15 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const 
     // hand the parser state to the next batch
     if(t == a.n_tiles - 1 && warp == 1) {
       uint8_t* cs = a.carry_out->sym;
-      if(nsym >= (uint32_t)PRE || t == 0 || sm.halo_break || a.tile_state[t] == ST_H) {
+      const bool not_seq = a.format == 1 ? (a.tile_state[t] != 1) : (a.tile_state[t] == ST_H);
+      if(nsym >= (uint32_t)PRE || t == 0 || sm.halo_break || not_seq) {
         cs[lane] = sm.sym[nsym + lane]; cs[lane + 32] = sm.sym[nsym + lane + 32];
       } else if(lane == 0) {
-        backfill_symbols(a.in, a.n_look, a.carry_in, (long long)n, -2, PRE, cs);
+        if(a.format == 1) backfill_fastq(a.in, a.n_look, a.carry_in, (long long)n, PRE, cs);
+        else backfill_symbols(a.in, a.n_look, a.carry_in, (long long)n, -2, PRE, cs);
       }
-      if(lane == 0) a.carry_out->state = sm.total_state;
+      // FASTQ carries the line type plus "the batch ended right after a newline" (bit 2)
+      if(lane == 0) a.carry_out->state = a.format == 1 ? (sm.total_state | (a.in[n - 1] == '\n' ? 4u : 0u)) : sm.total_state;
     }
 
     // ---- phase E: roll canonical k-mers over the compacted symbols, hash, insert / stage ----

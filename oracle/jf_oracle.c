@@ -133,8 +133,48 @@ static int count_file(const char* path) {
   fclose(f);
   filled = 0; fwd = rev = 0;
   if(n == 0) { free(d); return 1; }
-  if(d[0] != '>') { fprintf(stderr, "Unsupported format\n"); exit(134); }
+  if(d[0] != '>' && d[0] != '@') { fprintf(stderr, "Unsupported format\n"); exit(134); }
   long p = 0;
+  if(d[0] == '@') {
+    /* FASTQ: mer_overlap_sequence_parser.hpp:187-217 (read_fastq) and :290-307 (skip_quals):
+     * header line dropped; sequence lines up to the line starting with '+'; the '+' line dropped;
+     * then exactly as many quality characters as there were sequence characters are skipped (BY
+     * LENGTH, across lines), after which '@' or EOF must follow; an 'N' separates reads. */
+    while(p < n && d[p] != '\n') ++p;                       /* first header */
+    if(p < n) ++p;
+    for(;;) {
+      long seq_len = 0;
+      for(;;) {                                              /* sequence lines */
+        while(p < n && (d[p] == '\n' || d[p] == '\r')) ++p;
+        if(p >= n || d[p] == '+') break;
+        long e = p; while(e < n && d[e] != '\n') ++e;
+        long t = e; while(t > p && d[t - 1] == '\r') --t;
+        for(long i = p; i < t; ++i) feed_char(d[i]);
+        seq_len += t - p;
+        p = e;
+      }
+      if(p >= n) break;
+      while(p < n && d[p] != '\n') ++p;                      /* the '+' line */
+      if(p < n) ++p;
+      long quals = 0;
+      while(p < n && quals < seq_len) {                      /* qualities, by length */
+        while(p < n && (d[p] == '\n' || d[p] == '\r')) ++p;
+        long e = p; while(e < n && d[e] != '\n' && quals + (e - p) < seq_len) ++e;
+        long t = e; while(t > p && d[t - 1] == '\r' && e < n && d[e] == '\n') --t;
+        quals += t - p;
+        p = e;
+      }
+      while(p < n && (d[p] == '\n' || d[p] == '\r')) ++p;
+      if(p >= n) break;
+      if(quals != seq_len || d[p] != '@') { fprintf(stderr, "Invalid fastq sequence\n"); exit(1); }
+      feed_char('N');
+      while(p < n && d[p] != '\n') ++p;                      /* next header */
+      if(p < n) ++p;
+    }
+    free(d);
+    filled = 0;
+    return 1;
+  }
   int at_line_start = 1;
   while(p < n) {
     if(at_line_start) {

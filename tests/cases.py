@@ -33,6 +33,14 @@ CASES = {
     "cr_mid":       (["-m", "4", "-s", "1k", "-C"], ["cr_mid.fa"]),
     "oneline":      (["-m", "21", "-s", "300k", "-C"], ["oneline.fa"]),
     "k63_multi":    (["-m", "63", "-s", "1M", "-C"], ["multi.fa", "dos.fa"]),
+    # FASTQ, default path (no -Q): mer_overlap_sequence_parser.hpp:187-217,290-307
+    # (a FASTQ file WITHOUT a final newline is not a golden case: the reference silently drops the
+    #  last buffer of such a file -- see tests/test_gpu_parity.py::test_fastq_without_final_newline)
+    "fq":           (["-m", "21", "-s", "1M", "-C"], ["reads.fq"]),
+    "fq_dos":       (["-m", "17", "-s", "600k", "-C"], ["reads_dos.fq"]),
+    "fq_long":      (["-m", "25", "-s", "2M", "-C"], ["reads_long.fq"]),
+    "fq_k63":       (["-m", "63", "-s", "1M", "-C"], ["reads.fq", "one_read.fq"]),
+    "fq_fa_mixed":  (["-m", "21", "-s", "2M", "-C"], ["reads.fq", "multi.fa", "reads_dos.fq", "plain.fa", "one_read.fq"]),
     # counters: large counts, output clipping, count filters
     "polya":        (["-m", "21", "-s", "1k", "-C"], ["polya.fa"]),
     "repeat":       (["-m", "21", "-s", "10k", "-C"], ["repeat.fa"]),

@@ -62,4 +62,30 @@ def make_all(d):
     w("polya.fa", fasta(b"A" * 100000))
     w("repeat.fa", fasta(_seq(500, 11) * 400))
     w("plain1m.fa", fasta(_seq(1000000, 2)))
+    # FASTQ (4-line records): ragged read lengths, N's and lower case, quality strings that begin
+    # with '@' or '+', DOS line ends, a missing final newline, reads longer than a device tile
+    rng = random.Random(11)
+
+    def fastq(n_reads, seed, eol=b"\n", lens=(36, 76, 101, 150, 151, 250), long_read=0, final_eol=True):
+        r = random.Random(seed)
+        out = []
+        for i in range(n_reads):
+            ln = long_read if (long_read and i % 7 == 3) else r.choice(lens)
+            sq = bytearray(_seq(ln, seed * 100003 + i))
+            for _ in range(r.randrange(0, 3)):
+                sq[r.randrange(ln)] = r.choice(b"NnRacgt")
+            q = bytearray(r.randrange(33, 75) for _ in range(ln))
+            if i % 5 == 0:
+                q[0] = ord("@")
+            if i % 5 == 1:
+                q[0] = ord("+")
+            out.append(b"@read_%d/1 len=%d" % (i, ln) + eol + bytes(sq) + eol + (b"+" if i % 2 else b"+read_%d/1" % i) + eol + bytes(q) + eol)
+        data = b"".join(out)
+        return data if final_eol else data[:-len(eol)]
+
+    w("reads.fq", fastq(3000, 21))
+    w("reads_dos.fq", fastq(1500, 22, eol=b"\r\n"))
+    w("reads_noeol.fq", fastq(1500, 23, final_eol=False))
+    w("reads_long.fq", fastq(40, 24, long_read=40000))
+    w("one_read.fq", b"@r\nACGTACGTACGTACGTTTGCAAGCATCGAT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n")
     return f

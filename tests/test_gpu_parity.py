@@ -259,3 +259,32 @@ def test_route_and_shards_on_one_gpu(name, world, part, built, workdir, inputs):
     g = GOLDEN[name]
     assert jfutil.semantic(h) == g["header"]
     assert jfutil.md5(b) == g["body_md5"]
+
+
+def test_fastq_without_final_newline(built, workdir, inputs):
+    """Deliberate divergence from a reference bug: when a FASTQ file lacks the final newline the
+    reference throws inside skip_quals (mer_overlap_sequence_parser.hpp:290-307), the exception is
+    swallowed by the producer (cooperative_pool2.hpp:252) and the last buffer of reads is silently
+    lost (an 2-read file gives an EMPTY database).  The engine counts every read; the checker here is
+    the C restatement, which implements the documented semantics without that loss."""
+    from jellyfish_b200 import HashCounter
+    db = os.path.join(workdir, "noeol_oracle.jf")
+    jfutil.run([jfutil.ORACLE_C, "count", "-m", "31", "-s", "600k", "-o", db, inputs["reads_noeol.fq"]])
+    h, b = jfutil.split_db(db)
+    with HashCounter(600000, 7, k=31, canonical=False) as hc:
+        hc.add_files([inputs["reads_noeol.fq"]])
+        hc.done()
+        assert hc.dump_records() == b
+        hdr = hc.header()
+        assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == jfutil.semantic(h)
+
+
+def test_fastq_format_errors(built, workdir):
+    """Not 4-line FASTQ -> loud failure ("Invalid fastq sequence"), never a silent miscount."""
+    from jellyfish_b200 import HashCounter, JellyfishError
+    bad = b"@r1\nACGTACGTAC\nACGTACGTAA\n+\nIIIIIIIIIIIIIIIIIIII\n@r2\nACGT\n+\nIIII\n"     # two sequence lines
+    with HashCounter(1000, 7, k=4, canonical=True) as hc:
+        with pytest.raises(JellyfishError) as ei:
+            hc.add_text(bad)
+            hc.done()
+        assert "fastq" in str(ei.value).lower()
