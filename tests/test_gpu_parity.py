@@ -173,7 +173,8 @@ def test_large_scale_properties(built):
         assert all(h2[2 * i] == h1[i] for i in range(1, 31)) and all(h2[2 * i + 1] == 0 for i in range(0, 31))
 
 
-@pytest.mark.parametrize("name", ["k21C", "multi_files", "k63_multi", "k31C", "ovf32", "ovf128", "polya", "repeat", "grow2", "grow_k40", "c3", "one_per_line"])
+@pytest.mark.parametrize("name", ["k21C", "multi_files", "k63_multi", "k31C", "ovf32", "ovf128", "polya", "repeat", "grow2", "grow_k40", "c3", "one_per_line",
+                                  "fq_long", "fq_fa_mixed"])
 def test_partitioned_insertion_matches_golden(name, built, inputs):
     """The region-by-region path (records staged per table region, then inserted region by region)
     forced on small tables, including table doubling in the middle of a drain."""
@@ -288,3 +289,27 @@ def test_fastq_format_errors(built, workdir):
             hc.add_text(bad)
             hc.done()
         assert "fastq" in str(ei.value).lower()
+
+
+def test_skewed_input_in_region_mode(built, workdir):
+    """20 Mbp with long low-complexity stretches (poly-A, short tandem repeats) through the default
+    region-by-region path (table >= 256 MB): hot regions overflow their chunks within one iteration,
+    so the spill list and the direct-insertion fallback are exercised under load.  Checked against the
+    C restatement (sort-based, so independent of any table)."""
+    import gen
+    from jellyfish_b200 import HashCounter
+    parts = [gen._seq(5000000, 71), b"A" * 4000000, b"ACG" * 1500000, gen._seq(3000000, 72), b"AT" * 1000000, gen._seq(1500000, 73)]
+    fa = os.path.join(workdir, "skew.fa")
+    with open(fa, "wb") as f:
+        f.write(gen.fasta(b"".join(parts)))
+    db = os.path.join(workdir, "skew_oracle.jf")
+    jfutil.run([jfutil.ORACLE_C, "count", "-m", "21", "-s", "64M", "-C", "-o", db, fa])
+    h, b = jfutil.split_db(db)
+    with HashCounter(64000000, 7, k=21, canonical=True) as hc:
+        assert hc.info()["part_regions"] > 0
+        hc.add_files([fa])
+        st = hc.done()
+        assert st["kmers"] == st["inserted"]
+        assert hc.dump_records() == b
+        hdr = hc.header()
+        assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == jfutil.semantic(h)
