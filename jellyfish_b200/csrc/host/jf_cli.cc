@@ -164,10 +164,24 @@ struct count_args {
   std::vector<const char*> files;
 };
 
-struct sink_ctx { FILE* f; bool ok; };
+struct sink_ctx { FILE* f; bool ok; bool text; unsigned k, key_bytes, rec; };
 int file_sink(void* ctx, const void* recs, size_t n) {
   sink_ctx* c = (sink_ctx*)ctx;
-  if(fwrite(recs, 1, n, c->f) != n) { c->ok = false; return 1; }
+  if(!c->text) {
+    if(fwrite(recs, 1, n, c->f) != n) { c->ok = false; return 1; }
+    return 0;
+  }
+  // --text (text_dumper.hpp: "MER count" lines, counts not clipped): records arrive with 8-byte counters
+  const unsigned char* p = (const unsigned char*)recs;
+  std::string line;
+  for(size_t off = 0; off + c->rec <= n; off += c->rec) {
+    uint64_t w[2] = {0, 0}, v = 0;
+    memcpy(w, p + off, c->key_bytes);
+    memcpy(&v, p + off + c->key_bytes, 8);
+    line = mer_to_string(w, c->k);
+    line += ' '; line += std::to_string((unsigned long long)v); line += '\n';
+    if(fwrite(line.data(), 1, line.size(), c->f) != line.size()) { c->ok = false; return 1; }
+  }
   return 0;
 }
 
@@ -237,7 +251,6 @@ int count_main(int argc, char* argv[]) {
   if(a.bc_given || a.bf_size_given) usage_error("Bloom prefilters (--bc/--bf-size) are not implemented yet in jellyfish-b200");
   if(a.if_given) usage_error("--if is not implemented yet in jellyfish-b200");
   if(a.qual_given) usage_error("quality filtering (-Q/--min-quality) is not implemented yet in jellyfish-b200");
-  if(a.text) usage_error("--text is not implemented yet in jellyfish-b200");
   if(a.disk) usage_error("--disk is not implemented in jellyfish-b200 (the table is doubled on the device instead)");
   if(a.mer_len < 1 || a.mer_len > 64) usage_error("jellyfish-b200 supports mer lengths 1..64");
 
@@ -316,8 +329,8 @@ int count_main(int argc, char* argv[]) {
     else header.matrix(jfb::gf2_matrix(ti.matrix_r, ti.matrix_c, ti.matrix_columns));
     header.max_reprobe(ti.max_reprobe);
     header.set_reprobes(ti.reprobes);
-    header.format("binary/sorted");
-    header.counter_len(a.out_counter_len);
+    if(a.text) header.format("text/sorted");
+    else { header.format("binary/sorted"); header.counter_len(a.out_counter_len); }
     std::ofstream out(a.output, std::ios::binary);
     if(!out.good()) die(std::string("Can't open output file '") + a.output + "'");
     header.write(out);
@@ -326,9 +339,10 @@ int count_main(int argc, char* argv[]) {
     if(!f) die(std::string("Can't open output file '") + a.output + "'");
     std::vector<char> iobuf((size_t)8 << 20);
     setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
-    sink_ctx sc = { f, true };
+    const unsigned key_bytes = (2 * a.mer_len + 7) / 8;
+    sink_ctx sc = { f, true, a.text, a.mer_len, key_bytes, key_bytes + 8 };
     const uint64_t lo = a.lower_given ? a.lower : 0, hi = a.upper_given ? a.upper : std::numeric_limits<uint64_t>::max();
-    int rc = jfgpu_dump(h, lo, hi, a.out_counter_len, file_sink, &sc, nullptr);
+    int rc = jfgpu_dump(h, lo, hi, a.text ? 8 : a.out_counter_len, file_sink, &sc, nullptr);
     fclose(f);
     if(rc != JFGPU_OK) die(std::string("Error while dumping: ") + jfgpu_last_error(h));
   }

@@ -238,6 +238,7 @@ int main(int argc, char** argv) {
   }
   if(argc < 2 || strcmp(argv[1], "count")) { fprintf(stderr, "usage: jf_oracle count ... | matrix R C [SKIP]\n"); return 1; }
   uint64_t size = 0, low = 0, high = ~0ULL; unsigned val_len = 7, reprobes = 126, ocl = 4; const char* out = "mer_counts.jf";
+  int text = 0;   /* --text: text_dumper.hpp ("MER count" lines, format "text/sorted", no counter_len) */
   int first_file = argc;
   for(int i = 2; i < argc; ++i) {
     if(!strcmp(argv[i], "-m")) K = atoi(argv[++i]);
@@ -250,6 +251,7 @@ int main(int argc, char** argv) {
     else if(!strcmp(argv[i], "-U")) high = strtoull(argv[++i], 0, 0);
     else if(!strcmp(argv[i], "-o")) out = argv[++i];
     else if(!strcmp(argv[i], "-t")) ++i;
+    else if(!strcmp(argv[i], "--text")) text = 1;
     else { first_file = i; break; }
   }
   if(K < 1 || K > 64 || size == 0) { fprintf(stderr, "need -m (1..64) and -s\n"); return 1; }
@@ -312,8 +314,10 @@ int main(int argc, char** argv) {
   FILE* f = fopen(out, "wb");
   if(!f) { fprintf(stderr, "Can't open output file '%s'\n", out); return 1; }
   char* js = malloc(1 << 20); size_t o = 0;
-  o += sprintf(js + o, "{\"alignment\":8,\"canonical\":%s,\"cmdline\":[\"jf_oracle\"],\"counter_len\":%u,\"exe_path\":\"jf_oracle\",\"format\":\"binary/sorted\",\"hostname\":\"hostname\",\"key_len\":%u,\"matrix1\":{\"c\":%u,",
-               canonical ? "true" : "false", ocl, kbits, M.c);
+  o += sprintf(js + o, "{\"alignment\":8,\"canonical\":%s,\"cmdline\":[\"jf_oracle\"],", canonical ? "true" : "false");
+  if(!text) o += sprintf(js + o, "\"counter_len\":%u,", ocl);
+  o += sprintf(js + o, "\"exe_path\":\"jf_oracle\",\"format\":\"%s\",\"hostname\":\"hostname\",\"key_len\":%u,\"matrix1\":{\"c\":%u,",
+               text ? "text/sorted" : "binary/sorted", kbits, M.c);
   if(!M.identity) {
     o += sprintf(js + o, "\"columns\":[");
     for(unsigned i = 0; i < M.c; ++i) o += sprintf(js + o, "%s%llu", i ? "," : "", (unsigned long long)M.col[i]);
@@ -332,6 +336,13 @@ int main(int argc, char** argv) {
   uint64_t maxv = ocl >= 8 ? ~0ULL : ((1ULL << (8 * ocl)) - 1);
   for(size_t i = 0; i < n_rec; ++i) {
     if(recs[i].count < low || recs[i].count > high) continue;
+    if(text) {
+      char mer[80];
+      for(unsigned j = 0; j < K; ++j) mer[j] = "ACGT"[(unsigned)(recs[i].key >> (2 * (K - 1 - j))) & 3];
+      mer[K] = 0;
+      fprintf(f, "%s %llu\n", mer, (unsigned long long)recs[i].count);
+      continue;
+    }
     fwrite(&recs[i].key, 1, kb, f);
     uint64_t v = recs[i].count < maxv ? recs[i].count : maxv;
     fwrite(&v, 1, ocl, f);

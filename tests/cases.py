@@ -50,6 +50,8 @@ CASES = {
     "ovf32":        (["-m", "14", "-s", "100k", "-C"], ["polya.fa", "repeat.fa"]),
     "ovf64":        (["-m", "32", "-s", "30k", "-C"], ["polya.fa", "repeat.fa"]),
     "ovf128":       (["-m", "63", "-s", "700k", "-C"], ["polya.fa", "repeat.fa"]),
+    "text":         (["-m", "21", "-s", "600k", "-C", "--text"], ["plain.fa"]),
+    "text_k40_LU":  (["-m", "40", "-s", "10k", "--text", "-L", "2"], ["repeat.fa", "polya.fa"]),
     "c3":           (["-m", "12", "-s", "300k", "-C", "-c", "3"], ["plain.fa"]),
     # size doubling with new matrix draws (hash_counter.hpp:200-238)
     "grow2":        (["-m", "21", "-s", "100k", "-C"], ["plain.fa"]),
