@@ -3,13 +3,16 @@ import os
 import random
 
 
+_QUAD = [bytes(b"ACGT"[(v >> (2 * j)) & 3] for j in range(4)) for v in range(256)]
+
+
 def _seq(n, seed):
+    """n iid bases; base i = bits (2i, 2i+1) of one big random integer (linear time: the integer is
+    turned into little-endian bytes, every byte yields 4 bases)."""
     rng = random.Random(seed)
     bits = rng.getrandbits(2 * n)
-    out = bytearray(n)
-    for i in range(n):
-        out[i] = b"ACGT"[(bits >> (2 * i)) & 3]
-    return bytes(out)
+    raw = bits.to_bytes((2 * n + 7) // 8, "little")
+    return b"".join(_QUAD[v] for v in raw)[:n]
 
 
 def fasta(seq, line=70, name=b"read1", eol=b"\n"):
