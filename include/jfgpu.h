@@ -142,6 +142,12 @@ int  jfgpu_extract_route(jfgpu_handle h, const void* dev_bytes, size_t n, uint32
  * stream-ordered (returns without synchronising). */
 int  jfgpu_insert_keys(jfgpu_handle h, const void* dev_keys, uint64_t n, void* stream);
 
+/* -- mer_counter_base's operation (sub_commands/count_main.cc:133,152-184): JFGPU_OP_COUNT adds
+ *    (hash_counter::add), JFGPU_OP_PRIME inserts keys with count 0 (hash_counter::set, the first pass
+ *    of `count --if`), JFGPU_OP_UPDATE adds only to keys already present (update_add, the second pass).
+ *    Applies to the text fed after the call; drains pending work first. */
+int  jfgpu_set_op(jfgpu_handle h, uint32_t op);
+
 /* -- zero the table and the statistics, keep geometry and hash matrix: what the dumper's
  *    zero_blocks leaves behind (sorted_dumper.hpp:67-68,98-99) so the counter can be reused. */
 int  jfgpu_clear(jfgpu_handle h);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libjfgpu.so")
 # every symbol include/jfgpu.h declares
 SYMBOLS = [
     "jfgpu_create", "jfgpu_destroy", "jfgpu_last_error", "jfgpu_feed", "jfgpu_feed_device",
-    "jfgpu_extract_route", "jfgpu_insert_keys", "jfgpu_clear", "jfgpu_finish", "jfgpu_get_stats",
+    "jfgpu_extract_route", "jfgpu_insert_keys", "jfgpu_clear", "jfgpu_set_op", "jfgpu_finish", "jfgpu_get_stats",
     "jfgpu_table_info_get", "jfgpu_dump", "jfgpu_lookup", "jfgpu_histogram",
     "jfgpu_reference_matrix", "jfgpu_synth_fasta_bytes", "jfgpu_synth_fasta_device",
     "jfgpu_host_alloc", "jfgpu_host_free", "jfgpu_memcpy_h2d", "jfgpu_kernel_launches", "jfgpu_version",
@@ -81,6 +81,8 @@ def load():
     lib.jfgpu_extract_route.restype = C.c_int
     lib.jfgpu_insert_keys.argtypes = [H, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.jfgpu_insert_keys.restype = C.c_int
+    lib.jfgpu_set_op.argtypes = [H, C.c_uint32]
+    lib.jfgpu_set_op.restype = C.c_int
     lib.jfgpu_clear.argtypes = [H]
     lib.jfgpu_clear.restype = C.c_int
     lib.jfgpu_finish.argtypes = [H, C.POINTER(Stats)]

@@ -162,6 +162,7 @@ struct count_args {
   const char* timing = "";
   int device = 0;
   std::vector<const char*> files;
+  std::vector<const char*> if_files;
 };
 
 struct sink_ctx { FILE* f; bool ok; bool text; unsigned k, key_bytes, rec; };
@@ -226,7 +227,7 @@ int count_main(int argc, char* argv[]) {
     case O_BC: a.bc_given = true; break;
     case O_BFSIZE: a.bf_size = parse_u64(optarg, true, "--bf-size"); a.bf_size_given = true; break;
     case O_BFFP: a.bf_fp = atof(optarg); break;
-    case O_IF: a.if_given = true; break;
+    case O_IF: a.if_given = true; a.if_files.push_back(optarg); break;
     case 'Q': case O_QSTART: case O_MINQ: a.qual_given = true; break;
     case 'p': a.reprobes = (uint32_t)parse_u64(optarg, false, "-p"); break;
     case O_TEXT: a.text = true; break;
@@ -249,7 +250,6 @@ int count_main(int argc, char* argv[]) {
   if(a.sam_given) usage_error("SAM/BAM/CRAM not supported (missing htslib).");
   if(a.generator_given) usage_error("generators (-g) are not supported by jellyfish-b200");
   if(a.bc_given || a.bf_size_given) usage_error("Bloom prefilters (--bc/--bf-size) are not implemented yet in jellyfish-b200");
-  if(a.if_given) usage_error("--if is not implemented yet in jellyfish-b200");
   if(a.qual_given) usage_error("quality filtering (-Q/--min-quality) is not implemented yet in jellyfish-b200");
   if(a.disk) usage_error("--disk is not implemented in jellyfish-b200 (the table is doubled on the device instead)");
   if(a.mer_len < 1 || a.mer_len > 64) usage_error("jellyfish-b200 supports mer lengths 1..64");
@@ -266,6 +266,7 @@ int count_main(int argc, char* argv[]) {
 
   // ---- stream the files through the engine: a reader thread fills pinned buffers --------------
   const size_t BUF = (size_t)64 << 20;
+  auto stream_files = [&](const std::vector<const char*>& file_list) {
   struct chunk { char* data; size_t n; uint32_t flags; bool last; std::string error; };
   const int NBUF = 3;
   std::vector<char*> bufs(NBUF);
@@ -276,9 +277,9 @@ int count_main(int argc, char* argv[]) {
   std::thread reader([&] {
     auto get_buf = [&]() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !freeb.empty(); }); char* b = freeb.front(); freeb.pop(); return b; };
     auto put = [&](chunk c) { std::unique_lock<std::mutex> l(mu); ready.push(c); cv.notify_all(); };
-    for(size_t fi = 0; fi < a.files.size(); ++fi) {
-      int fd = ::open(a.files[fi], O_RDONLY);
-      if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + a.files[fi] + "'"}); return; }
+    for(size_t fi = 0; fi < file_list.size(); ++fi) {
+      int fd = ::open(file_list[fi], O_RDONLY);
+      if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + file_list[fi] + "'"}); return; }
       bool first = true, eof = false;
       char* cur = get_buf();
       size_t have = 0;
@@ -313,6 +314,15 @@ int count_main(int argc, char* argv[]) {
   }
   reader.join();
   if(!feed_error.empty()) die(feed_error);
+  for(int i = 0; i < NBUF; ++i) jfgpu_host_free(bufs[i]);
+  };
+  // count_main.cc:288-295: with --if the keys of those files are primed first, then only they are counted
+  if(a.if_given) {
+    if(jfgpu_set_op(h, JFGPU_OP_PRIME) != JFGPU_OK) die(jfgpu_last_error(h));
+    stream_files(a.if_files);
+    if(jfgpu_set_op(h, JFGPU_OP_UPDATE) != JFGPU_OK) die(jfgpu_last_error(h));
+  }
+  stream_files(a.files);
   jfgpu_stats st;
   if(jfgpu_finish(h, &st) != JFGPU_OK) die(jfgpu_last_error(h));
   auto after_count_time = clk::now();
@@ -354,7 +364,6 @@ int count_main(int argc, char* argv[]) {
        << "Counting " << secs(after_count_time - after_init_time) << "\n"
        << "Writing  " << secs(after_dump_time - after_count_time) << "\n";
   }
-  for(int i = 0; i < NBUF; ++i) jfgpu_host_free(bufs[i]);
   jfgpu_destroy(h);
   return 0;
 }

@@ -45,7 +45,7 @@ struct TableDev {
   uint32_t  rbits;           // width of the reprobe field
   uint32_t  fbits;           // width of the key field  = max(2k - lsize, 0) + rbits
   uint32_t  max_reprobe;
-  uint32_t  pad;
+  uint32_t  op;              // 0 COUNT (add), 1 PRIME (insert with count 0), 2 UPDATE (add only to keys already present)
   unsigned long long* ovf_keys;    // side table for counter carries: slot index + 1
   unsigned long long* ovf_vals;    //   number of carries (units of 2^cbits)
   uint64_t  ovf_mask;
@@ -192,9 +192,52 @@ __device__ __forceinline__ uint64_t ovf_get(const TableDev& T, uint64_t slot_idx
 // ---------------------------------------------------------------------------------------
 struct LocalStats { uint32_t kmers, inserted, distinct, reprobes, failed; };
 
+template<int SB> __device__ __forceinline__ bool slot_decode(const TableDev& T, uint64_t idx, u128& high, uint32_t& reprobe, uint64_t& count);
+
+// add `count` to the counter field of an occupied slot (carry -> side table)
+template<int SB>
+__device__ __forceinline__ void slot_add(const TableDev& T, uint64_t idx, uint64_t count) {
+  if(count == 0) return;
+  const uint32_t fb = T.fbits;
+  if(SB == 32) {
+    const uint32_t cb = 32 - fb;
+    const uint32_t c_lo = (uint32_t)(count & ((1ull << cb) - 1));
+    uint64_t carry = count >> cb;
+    if(c_lo) { uint32_t o2 = atomicAdd(&((uint32_t*)T.slots)[idx], c_lo << fb); carry += ((uint64_t)(o2 >> fb) + c_lo) >> cb; }
+    if(carry) ovf_add(T, idx, carry);
+  } else {
+    const uint32_t fhi = SB == 128 ? (fb > 64 ? fb - 64 : 0) : fb;
+    const uint32_t cb = 64 - fhi;
+    const uint64_t c_lo = cb >= 64 ? count : (count & ((1ull << cb) - 1));
+    uint64_t carry = cb >= 64 ? 0 : (count >> cb);
+    unsigned long long* wp = SB == 128 ? ((unsigned long long*)T.slots + 2 * idx + 1) : ((unsigned long long*)T.slots + idx);
+    if(c_lo) {
+      unsigned long long o2 = atomicAdd(wp, (unsigned long long)(c_lo << fhi));
+      uint64_t oc = o2 >> fhi, sum = oc + c_lo;
+      if((cb < 64 && (sum >> cb)) || sum < oc) carry += 1;
+    }
+    if(carry) ovf_add(T, idx, carry);
+  }
+}
+
+// UPDATE (array::update_add, large_hash_array.hpp:335-347): add only when the key is already there
+template<int SB>
+__device__ __forceinline__ bool table_update_hp(const TableDev& T, const uint64_t base, const u128 high, uint64_t count) {
+  uint64_t idx = base;
+  for(uint32_t i = 0; i <= T.max_reprobe; ++i) {
+    u128 h2; uint32_t rp; uint64_t cnt;
+    if(!slot_decode<SB>(T, idx, h2, rp, cnt)) return true;            // empty slot: the key is not in the table
+    if(rp == i && h2.lo == high.lo && h2.hi == high.hi) { slot_add<SB>(T, idx, count); return true; }
+    idx = base + tri(i + 1);
+  }
+  return true;
+}
+
 template<int SB>
 __device__ __forceinline__ bool table_add_hp(const TableDev& T, const uint64_t base, const u128 high,
                                              uint64_t count, LocalStats& ls, const uint32_t first_probe = 0) {
+  if(T.op == 2) return table_update_hp<SB>(T, base, high, count);
+  if(T.op == 1) count = 0;                   // PRIME (array::set, large_hash_array.hpp:313-319): claim the key, add nothing
   const uint32_t rb = T.rbits, fb = T.fbits;
   uint64_t idx = base + (first_probe ? tri(first_probe) : 0);
 
@@ -287,6 +330,11 @@ __device__ __forceinline__ void table_add_batch(const TableDev& T, const uint64_
                                                 const bool (&valid)[R], bool (&ok)[R], LocalStats& ls) {
   constexpr uint32_t LOOK = 4;
   const uint32_t rb = T.rbits, fb = T.fbits;
+  if(T.op != 0) {
+#pragma unroll
+    for(int r = 0; r < R; ++r) ok[r] = valid[r] ? table_add_hp<SB>(T, base[r], high[r], 1, ls) : true;
+    return;
+  }
   if(SB == 32 || SB == 64) {
     typedef typename std::conditional<SB == 32, uint32_t, unsigned long long>::type W;
     W* tab = (W*)T.slots;
@@ -360,7 +408,7 @@ __device__ __forceinline__ void record_failure(const TableDev& T, const uint64_t
   if(at < T.fail_cap) {
 #pragma unroll
     for(int w = 0; w < KW; ++w) T.fail_keys[at * KW + w] = key[w];
-    T.fail_counts[at] = count;
+    T.fail_counts[at] = T.op == 1 ? 0 : count;          // a primed key is re-inserted with count 0 after a regrow
   } else {
     atomicAdd(&T.stats[STAT_FAIL_DROPPED], 1ull);
   }

@@ -98,6 +98,7 @@ struct jfgpu_engine {
   // per-batch scratch
   DevBuf nlA, nlB, cntA, cntB, tstate; uint64_t scratch_tiles = 0;
   int format = 0;                 // 0 = FASTA, 1 = FASTQ: format of the file being fed
+  uint32_t op = 0;                // JFGPU_OP_*
   // bookkeeping
   bool in_file = false;
   uint64_t bytes_fed = 0, regrows = 0;
@@ -134,6 +135,7 @@ TableDev table_dev(const jfgpu_engine* e, const Table& t) {
   d.rbits = t.rbits;
   d.fbits = t.fbits;
   d.max_reprobe = t.max_reprobe;
+  d.op = e->op;
   d.ovf_keys = t.ovf_keys.as<unsigned long long>();
   d.ovf_vals = t.ovf_vals.as<unsigned long long>();
   d.ovf_mask = e->ovf_size - 1;
@@ -367,7 +369,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st);
     TableDev T = table_dev(e, e->tab);
     if(!rebuilt) {
-      if(e->tab.slot_bits == 32 && pd.rec_bytes == 4 && !getenv("JFGPU_K2_GENERIC")) {
+      if(e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && !getenv("JFGPU_K2_GENERIC")) {
         // lean 32-bit specialisation: 2 CTAs x 1024 threads per SM
         if(e->kw == 1) insert_chunks32_kernel<1><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
         else           insert_chunks32_kernel<2><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
@@ -424,9 +426,9 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   cudaEventRecord(e->ev_d1, st);
   cudaStreamSynchronize(st);
   { float ms = 0; if(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1) == cudaSuccess) e->drain_ms += ms; else cudaGetLastError(); }
-  ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
   ps.pending = false;
   if(rebuilt) { cudaStreamSynchronize(st); old_inv.free(); part_configure(e); if(!e->part.P) part_release(e); }
+  ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
   if(rc) return rc;
   CUDA_OK(e, cudaGetLastError());
   return JFGPU_OK;
@@ -616,7 +618,16 @@ uint64_t pick_segment(const Table& t) {
 
 // Move every (key, count) of the current table, plus `n_failed` entries of failure list
 // `old_fail`, into a fresh table of 2^nl global slots hashed with M.
+int rebuild_table_impl(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int old_fail, uint64_t n_failed);
 int rebuild_table(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int old_fail, uint64_t n_failed) {
+  // moving (key, count) pairs is plain addition whatever operation the counter is in
+  const uint32_t op = e->op;
+  e->op = 0;
+  const int rc = rebuild_table_impl(e, nl, M, old_fail, n_failed);
+  e->op = op;
+  return rc;
+}
+int rebuild_table_impl(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int old_fail, uint64_t n_failed) {
   Table nt;
   int rc = table_setup(e, nt, nl, M);
   if(rc) { nt.release(); return rc == JFGPU_ERR_NOMEM ? fail(e, JFGPU_ERR_FULL, "Hash full (" + e->err + ")") : rc; }
@@ -843,6 +854,8 @@ void jfgpu_destroy(jfgpu_handle e) {
   if(e->h_stats) cudaFreeHost(e->h_stats);
   if(e->ev_t0) cudaEventDestroy(e->ev_t0);
   if(e->ev_t1) cudaEventDestroy(e->ev_t1);
+  if(e->ev_d0) cudaEventDestroy(e->ev_d0);
+  if(e->ev_d1) cudaEventDestroy(e->ev_d1);
   for(cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
   if(e->cs) cudaStreamDestroy(e->cs);
   if(e->hs) cudaStreamDestroy(e->hs);
@@ -1022,6 +1035,15 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
   cudaEventRecord(e->ev_t1, st);
   CUDA_OK(e, cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms;
+  return JFGPU_OK;
+}
+
+int jfgpu_set_op(jfgpu_handle e, uint32_t op) {
+  if(!e || op > JFGPU_OP_UPDATE) return JFGPU_ERR_ARG;
+  // records staged under the previous operation must reach the table under that operation
+  int rc = jfgpu_finish(e, nullptr);
+  if(rc) return rc;
+  e->op = op;
   return JFGPU_OK;
 }
 

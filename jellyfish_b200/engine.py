@@ -153,6 +153,13 @@ class HashCounter(object):
     def insert_keys(self, keys_ptr, n, stream=None):
         self._check(self._lib.jfgpu_insert_keys(self._h, C.c_void_p(keys_ptr), n, C.c_void_p(stream or 0)))
 
+    OP_COUNT, OP_PRIME, OP_UPDATE = 0, 1, 2
+
+    def set_op(self, op):
+        """COUNT (add), PRIME (insert with count 0) or UPDATE (add only to present keys): the two passes
+        of `jellyfish count --if` (sub_commands/count_main.cc:288-295)."""
+        self._check(self._lib.jfgpu_set_op(self._h, op))
+
     def clear(self):
         """Zero the table and statistics (same geometry and hash matrix)."""
         self._check(self._lib.jfgpu_clear(self._h))

@@ -238,6 +238,7 @@ int main(int argc, char** argv) {
   }
   if(argc < 2 || strcmp(argv[1], "count")) { fprintf(stderr, "usage: jf_oracle count ... | matrix R C [SKIP]\n"); return 1; }
   uint64_t size = 0, low = 0, high = ~0ULL; unsigned val_len = 7, reprobes = 126, ocl = 4; const char* out = "mer_counts.jf";
+  const char* if_files[64]; int n_if = 0;   /* --if: count only the k-mers of these files (count_main.cc:288-295) */
   int text = 0;   /* --text: text_dumper.hpp ("MER count" lines, format "text/sorted", no counter_len) */
   int first_file = argc;
   for(int i = 2; i < argc; ++i) {
@@ -252,6 +253,7 @@ int main(int argc, char** argv) {
     else if(!strcmp(argv[i], "-o")) out = argv[++i];
     else if(!strcmp(argv[i], "-t")) ++i;
     else if(!strcmp(argv[i], "--text")) text = 1;
+    else if(!strcmp(argv[i], "--if")) { if(n_if < 64) if_files[n_if++] = argv[++i]; else ++i; }
     else { first_file = i; break; }
   }
   if(K < 1 || K > 64 || size == 0) { fprintf(stderr, "need -m (1..64) and -s\n"); return 1; }
@@ -263,7 +265,28 @@ int main(int argc, char** argv) {
   matrix_t M;
   if(size < key_space) mat_draw(lsize, kbits, &M); else { M.identity = 1; M.r = M.c = kbits; }
 
+  /* --if: first pass PRIME (array::set, every key enters with count 0), second pass UPDATE
+   * (update_add: only keys already present are incremented) */
+  u128* if_keys = 0; size_t n_if_keys = 0;
+  if(n_if) {
+    for(int i = 0; i < n_if; ++i) if(!count_file(if_files[i])) return 1;
+    qsort(mers, n_mers, sizeof(u128), cmp_u128);
+    for(size_t i = 0; i < n_mers; ++i) if(i == 0 || mers[i] != mers[i - 1]) mers[n_if_keys++] = mers[i];
+    if_keys = malloc((n_if_keys ? n_if_keys : 1) * sizeof(u128));
+    memcpy(if_keys, mers, n_if_keys * sizeof(u128));
+    n_mers = 0;
+  }
   for(int i = first_file; i < argc; ++i) if(!count_file(argv[i])) return 1;
+  if(n_if) {
+    /* keep the occurrences of primed keys, then add one zero-count marker per primed key */
+    size_t kept = 0;
+    for(size_t i = 0; i < n_mers; ++i) {
+      size_t lo = 0, hi = n_if_keys;
+      while(lo < hi) { size_t mid = (lo + hi) / 2; if(if_keys[mid] < mers[i]) lo = mid + 1; else hi = mid; }
+      if(lo < n_if_keys && if_keys[lo] == mers[i]) mers[kept++] = mers[i];
+    }
+    n_mers = kept;
+  }
 
   /* first-occurrence order of the distinct keys (insertion order of a -t 1 run) */
   u128* order = malloc((n_mers ? n_mers : 1) * sizeof(u128));
@@ -275,9 +298,25 @@ int main(int argc, char** argv) {
     size_t j = i; while(j < n_mers && mers[j] == mers[i]) ++j;
     recs[n_rec].key = mers[i]; recs[n_rec].count = j - i; ++n_rec; i = j;
   }
+  if(n_if) {
+    /* primed keys never seen again stay in the table with count 0 (and are dumped: dumper min = 0) */
+    rec_t* all = malloc((n_if_keys ? n_if_keys : 1) * sizeof(rec_t));
+    size_t j = 0;
+    for(size_t i = 0; i < n_if_keys; ++i) {
+      all[i].key = if_keys[i]; all[i].count = 0;
+      while(j < n_rec && recs[j].key < if_keys[i]) ++j;
+      if(j < n_rec && recs[j].key == if_keys[i]) all[i].count = recs[j].count;
+    }
+    free(recs); recs = all; n_rec = n_if_keys;
+    /* insertion order of the PRIME pass = first occurrence in the --if files: approximated by key
+     * order (only matters for the fullness decision near the reprobe limit) */
+    free(order); order = malloc((n_rec ? n_rec : 1) * sizeof(u128));
+    for(size_t i = 0; i < n_rec; ++i) order[i] = recs[i].key;
+    n_mers = 0;
+  }
   /* distinct keys in first-occurrence order: mark seen through a sorted lookup */
-  size_t n_order = 0;
-  {
+  size_t n_order = n_if ? n_rec : 0;
+  if(!n_if) {
     unsigned char* seen = calloc(n_rec ? n_rec : 1, 1);
     for(size_t i = 0; i < n_mers; ++i) {
       size_t lo = 0, hi = n_rec;

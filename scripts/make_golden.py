@@ -22,7 +22,7 @@ with tempfile.TemporaryDirectory() as d:
     files = gen.make_all(d)
     for name, (args, ins) in sorted(CASES.items()):
         db = os.path.join(d, name + ".jf")
-        jfutil.run([jfutil.REF_JF, "count", "-t", "1"] + args + ["-o", db] + [files[i] for i in ins])
+        jfutil.run([jfutil.REF_JF, "count", "-t", "1"] + jfutil.subst(args, files) + ["-o", db] + [files[i] for i in ins])
         h, b = jfutil.split_db(db)
         out[name] = {"args": args, "inputs": ins, "header": jfutil.semantic(h), "body_md5": jfutil.md5(b), "body_len": len(b)}
         print(name, out[name]["body_md5"], len(b))

@@ -52,6 +52,10 @@ CASES = {
     "ovf128":       (["-m", "63", "-s", "700k", "-C"], ["polya.fa", "repeat.fa"]),
     "text":         (["-m", "21", "-s", "600k", "-C", "--text"], ["plain.fa"]),
     "text_k40_LU":  (["-m", "40", "-s", "10k", "--text", "-L", "2"], ["repeat.fa", "polya.fa"]),
+    # --if: count only the k-mers of the given files (PRIME then UPDATE, tests/subset_hashing.sh)
+    "if_sub":       (["-m", "17", "-s", "1M", "-C", "--if", "@multi2.fa"], ["multi.fa", "multi2.fa", "dangling.fa"]),
+    "if_zeros":     (["-m", "21", "-s", "600k", "--if", "@plain.fa", "--if", "@dangling.fa"], ["multi.fa", "dangling.fa"]),
+    "if_k40_rep":   (["-m", "40", "-s", "10k", "-C", "--if", "@repeat.fa"], ["repeat.fa", "polya.fa", "repeat.fa"]),
     "c3":           (["-m", "12", "-s", "300k", "-C", "-c", "3"], ["plain.fa"]),
     # size doubling with new matrix draws (hash_counter.hpp:200-238)
     "grow2":        (["-m", "21", "-s", "100k", "-C"], ["plain.fa"]),

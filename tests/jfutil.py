@@ -57,3 +57,8 @@ def records(header, body):
 
 def generate(prefix, seed, *lengths, extra=()):
     run([REF_GEN, "-o", prefix, "-s", str(seed)] + list(extra) + [str(x) for x in lengths])
+
+
+def subst(args, files):
+    """'@name' in a case's switches stands for the path of that generated input (e.g. --if @multi2.fa)."""
+    return [files[a[1:]] if a.startswith("@") else a for a in args]

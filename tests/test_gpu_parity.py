@@ -18,7 +18,7 @@ GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golde
 
 def _count_cli(workdir, inputs, name, args, ins, extra=()):
     db = os.path.join(workdir, "gpu_%s.jf" % name)
-    jfutil.run([jfutil.OUR_JF, "count"] + list(args) + list(extra) + ["-o", db] + [inputs[i] for i in ins])
+    jfutil.run([jfutil.OUR_JF, "count"] + jfutil.subst(list(args), inputs) + list(extra) + ["-o", db] + [inputs[i] for i in ins])
     return jfutil.split_db(db)
 
 
@@ -313,3 +313,20 @@ def test_skewed_input_in_region_mode(built, workdir):
         assert hc.dump_records() == b
         hdr = hc.header()
         assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == jfutil.semantic(h)
+
+
+@pytest.mark.parametrize("part", [0, 1])
+def test_if_passes_via_api(part, built, inputs):
+    """`count --if`: PRIME the keys of one file (count 0), then UPDATE with the others -- through the
+    Python mirror, in both insertion modes (direct / region by region)."""
+    from jellyfish_b200 import HashCounter
+    g = GOLDEN["if_sub"]
+    with HashCounter(1000000, 7, k=17, canonical=True, part_min_mb=part, pool_bytes=(128 << 20) if part else 0, max_batch_bytes=1 << 20) as hc:
+        hc.set_op(HashCounter.OP_PRIME)
+        hc.add_files([inputs["multi2.fa"]])
+        hc.set_op(HashCounter.OP_UPDATE)
+        hc.add_files([inputs["multi.fa"], inputs["multi2.fa"], inputs["dangling.fa"]])
+        hc.done()
+        assert jfutil.md5(hc.dump_records()) == g["body_md5"]
+        hdr = hc.header()
+        assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == g["header"]
