@@ -12,7 +12,8 @@
  * whose observable behaviour it restates (paths relative to /root/reference).
  *
  *   jf_oracle count -m K -s SIZE [-C] [-c VAL_LEN] [-p REPROBES] [--out-counter-len N]
- *                   [-L LOW] [-U HIGH] [-o OUT] file...
+ *                   [-L LOW] [-U HIGH] [--text] [--if FILE]... [-Q CHAR | --min-quality N
+ *                   [--quality-start S]] [-o OUT] file...
  *   jf_oracle matrix R C [SKIP]        print the hash matrix columns the reference would draw
  */
 #define _GNU_SOURCE
@@ -193,6 +194,73 @@ static int count_file(const char* path) {
   return 1;
 }
 
+/* ---- -Q / --min-quality: whole reads with their quality strings -----------------------------
+ * count_main.cc:326-329 switches to mer_qual_counter = whole_sequence_parser (one record at a
+ * time: whole_sequence_parser.hpp:137-152 read_fasta, :154-193 read_fastq) + mer_qual_iterator
+ * (mer_qual_iterator.hpp:64-92: a base counts only if it is ACGT/acgt AND its quality character,
+ * compared as a (signed) char, is >= min_qual; a FASTA record has no qualities = all pass; every
+ * record starts with filled_ = 0). Unlike the default parser, std::getline keeps a line-end '\r'
+ * inside the sequence (where it breaks the k-mer) and inside the quality string (where it is
+ * counted), FASTQ sequence and quality may span several lines, and a malformed record is an
+ * error rather than being skipped. */
+static int min_qual = 0, use_qual = 0;
+static long ws_getline(const unsigned char* d, long n, long p, long* b, long* e) {   /* std::getline: [b,e) without '\n' */
+  *b = p; while(p < n && d[p] != '\n') ++p;
+  *e = p; return p < n ? p + 1 : n;
+}
+static int count_file_qual(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if(!f) { fprintf(stderr, "Can't open file '%s'\n", path); return 0; }
+  fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+  unsigned char* d = malloc(n + 1);
+  if(n && fread(d, 1, n, f) != (size_t)n) { perror("fread"); exit(1); }
+  fclose(f);
+  filled = 0; fwd = rev = 0;
+  if(n == 0) { free(d); return 1; }
+  if(d[0] != '>' && d[0] != '@') { fprintf(stderr, "Unsupported format\n"); exit(134); }
+  long p = 0, b, e;
+  if(d[0] == '>') {
+    while(p < n) {
+      ++p;                                                   /* '>' */
+      p = ws_getline(d, n, p, &b, &e);                       /* header */
+      filled = 0;
+      while(p < n && d[p] != '>') {                          /* lines up to the next line starting with '>' */
+        p = ws_getline(d, n, p, &b, &e);
+        for(long i = b; i < e; ++i) feed_char(d[i]);
+      }
+    }
+    free(d); filled = 0; return 1;
+  }
+  unsigned char* seq = malloc(n + 1); unsigned char* qual = malloc(n + 1);
+  while(p < n) {
+    long ns = 0, nq = 0;
+    ++p;                                                     /* '@' (whatever the character is) */
+    p = ws_getline(d, n, p, &b, &e);                         /* header */
+    while(p < n && d[p] != '+') {                            /* sequence lines up to the line starting with '+' */
+      p = ws_getline(d, n, p, &b, &e);
+      memcpy(seq + ns, d + b, e - b); ns += e - b;
+    }
+    if(p >= n) { fprintf(stderr, "Truncated fastq file\n"); exit(1); }
+    p = ws_getline(d, n, p, &b, &e);                         /* the '+' line */
+    /* first quality line unconditionally when the read is not empty (a line starting with '+' is
+     * cleared and then appended by the loop: same bytes); an empty read consumes one line unless it starts with '+' */
+    if(ns == 0 && p < n && d[p] != '+') { p = ws_getline(d, n, p, &b, &e); memcpy(qual, d + b, e - b); nq = e - b; }
+    while(nq < ns && p < n) {
+      p = ws_getline(d, n, p, &b, &e);
+      memcpy(qual + nq, d + b, e - b); nq += e - b;
+    }
+    if(nq != ns) { fprintf(stderr, "Invalid fastq file: wrong number of quals\n"); exit(1); }
+    if(p < n && d[p] != '@') { fprintf(stderr, "Invalid fastq file: header missing\n"); exit(1); }
+    filled = 0;
+    for(long i = 0; i < ns; ++i) {
+      if((signed char)qual[i] >= (signed char)min_qual) feed_char(seq[i]); else filled = 0;
+    }
+  }
+  free(seq); free(qual); free(d);
+  filled = 0;
+  return 1;
+}
+
 static int cmp_u128(const void* a, const void* b) { u128 x = *(const u128*)a, y = *(const u128*)b; return x < y ? -1 : x > y; }
 typedef struct { uint64_t pos; u128 key; uint64_t count; } rec_t;
 static int cmp_rec(const void* a, const void* b) {
@@ -241,6 +309,7 @@ int main(int argc, char** argv) {
   const char* if_files[64]; int n_if = 0;   /* --if: count only the k-mers of these files (count_main.cc:288-295) */
   int text = 0;   /* --text: text_dumper.hpp ("MER count" lines, format "text/sorted", no counter_len) */
   int first_file = argc;
+  int min_quality = 0, quality_start = 64;   /* count_main_cmdline.yaggo:56-61 */
   for(int i = 2; i < argc; ++i) {
     if(!strcmp(argv[i], "-m")) K = atoi(argv[++i]);
     else if(!strcmp(argv[i], "-s")) size = parse_size(argv[++i]);
@@ -253,8 +322,19 @@ int main(int argc, char** argv) {
     else if(!strcmp(argv[i], "-o")) out = argv[++i];
     else if(!strcmp(argv[i], "-t")) ++i;
     else if(!strcmp(argv[i], "--text")) text = 1;
+    else if(!strcmp(argv[i], "-Q") || !strcmp(argv[i], "--min-qual-char")) {   /* count_main.cc:234-244 */
+      const char* a = argv[++i];
+      if(strlen(a) != 1 || a[0] < '!' || a[0] > '~') { fprintf(stderr, "[-Q, --min-qual-char] must be one printable character\n"); return 1; }
+      min_qual = a[0]; use_qual = 1;
+    }
+    else if(!strcmp(argv[i], "--min-quality")) { min_quality = atoi(argv[++i]); use_qual = 2; }
+    else if(!strcmp(argv[i], "--quality-start")) quality_start = atoi(argv[++i]);
     else if(!strcmp(argv[i], "--if")) { if(n_if < 64) if_files[n_if++] = argv[++i]; else ++i; }
     else { first_file = i; break; }
+  }
+  if(use_qual == 2) {   /* count_main.cc:245-256 */
+    min_qual = quality_start + min_quality;
+    if(quality_start < '!' || quality_start > '~' || min_qual < '!' || min_qual > '~') { fprintf(stderr, "Quality out of range\n"); return 1; }
   }
   if(K < 1 || K > 64 || size == 0) { fprintf(stderr, "need -m (1..64) and -s\n"); return 1; }
   const unsigned kbits = 2 * K;
@@ -276,7 +356,7 @@ int main(int argc, char** argv) {
     memcpy(if_keys, mers, n_if_keys * sizeof(u128));
     n_mers = 0;
   }
-  for(int i = first_file; i < argc; ++i) if(!count_file(argv[i])) return 1;
+  for(int i = first_file; i < argc; ++i) if(!(use_qual ? count_file_qual(argv[i]) : count_file(argv[i]))) return 1;
   if(n_if) {
     /* keep the occurrences of primed keys, then add one zero-count marker per primed key */
     size_t kept = 0;

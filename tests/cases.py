@@ -62,3 +62,25 @@ CASES = {
     "grow_k40":     (["-m", "40", "-s", "50k"], ["plain.fa"]),
     "grow_to_full": (["-m", "8", "-s", "10k", "-C"], ["plain.fa"]),
 }
+
+# -Q / --min-quality (count_main.cc:326-329: whole_sequence_parser + mer_qual_iterator). The
+# restatement is pinned against these; the device path for them is a round-2 row, so they are
+# kept apart from CASES (which the GPU parity tests iterate). FASTA files come before FASTQ files in
+# a case: read_fasta (whole_sequence_parser.hpp:137-152) never clears the record's quality string,
+# so a FASTA record read into a buffer slot that held a FASTQ read is filtered with that read's
+# stale qualities -- which slot depends on thread timing; not reproduced.
+QUAL_CASES = {
+    "q_fq":        (["-m", "21", "-s", "1M", "-C", "-Q", "5"], ["reads_q.fq"]),
+    "q_fq_hi":     (["-m", "17", "-s", "1M", "-Q", "G"], ["reads_q.fq"]),
+    "q_minq":      (["-m", "17", "-s", "1M", "-C", "--min-quality", "20", "--quality-start", "33"], ["reads_q.fq"]),
+    "q_minq_dflt": (["-m", "15", "-s", "1M", "-C", "--min-quality", "6"], ["reads_q.fq"]),
+    "q_all_pass":  (["-m", "21", "-s", "1M", "-C", "-Q", "!"], ["reads.fq"]),
+    "q_uniform":   (["-m", "12", "-s", "1M", "-C", "-Q", "#"], ["reads.fq"]),
+    "q_dos":       (["-m", "17", "-s", "600k", "-C", "-Q", "5"], ["reads_q_dos.fq"]),
+    "q_noeol":     (["-m", "21", "-s", "1M", "-C", "-Q", "\""], ["reads_noeol.fq"]),
+    "q_long":      (["-m", "25", "-s", "2M", "-C", "-Q", "\""], ["reads_long.fq"]),
+    "q_ml":        (["-m", "21", "-s", "1M", "-C", "-Q", "$"], ["reads_ml.fq"]),
+    "q_fa":        (["-m", "21", "-s", "1M", "-C", "-Q", "5"], ["multi.fa", "dos.fa", "cr_mid.fa", "noeol.fa", "blank_runs.fa"]),
+    "q_mixed":     (["-m", "25", "-s", "4M", "-C", "-Q", "4"], ["multi.fa", "empty.fa", "reads_q.fq", "reads_ml.fq", "one_read.fq", "reads_q_dos.fq"]),
+    "q_k40_if":    (["-m", "40", "-s", "1M", "-Q", "3", "--if", "@reads_q.fq"], ["reads_q.fq", "reads_q_dos.fq"]),
+}

@@ -91,4 +91,36 @@ def make_all(d):
     w("reads_noeol.fq", fastq(1500, 23, final_eol=False))
     w("reads_long.fq", fastq(40, 24, long_read=40000))
     w("one_read.fq", b"@r\nACGTACGTACGTACGTTTGCAAGCATCGAT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n")
+    # multi-line FASTQ (sequence and qualities wrapped at 60), an empty read, no final newline
+    r = random.Random(31)
+    ml = []
+    for i in range(400):
+        ln = r.choice((0, 59, 60, 61, 150, 400)) if i % 50 == 7 else r.choice((59, 60, 61, 150, 400))
+        sq = _seq(ln, 777000 + i) if ln else b""
+        q = bytes(r.randrange(35, 74) for _ in range(ln))
+        wrap = lambda x: b"".join(x[j:j + 60] + b"\n" for j in range(0, len(x), 60)) if x else b"\n"
+        ml.append(b"@ml_%d\n" % i + wrap(sq) + b"+\n" + wrap(q))
+    w("reads_ml.fq", b"".join(ml)[:-1])
+
+    # realistic qualities for -Q: mostly high, ~4% low bases, low tails, a few bytes >= 0x80
+    # (negative as a char: always below the threshold)
+    def fastq_q(n_reads, seed, eol=b"\n"):
+        r = random.Random(seed)
+        out = []
+        for i in range(n_reads):
+            ln = r.choice((50, 76, 101, 151))
+            sq = bytearray(_seq(ln, seed * 7919 + i))
+            if i % 9 == 0:
+                sq[r.randrange(ln)] = ord("N")
+            q = bytearray(r.choice(b"FGHIIIIJ") if r.random() > 0.04 else r.randrange(33, 60) for _ in range(ln))
+            tail = r.randrange(0, 12)
+            for j in range(ln - tail, ln):
+                q[j] = r.randrange(33, 45)
+            if i % 37 == 5:
+                q[r.randrange(ln)] = r.randrange(128, 256)
+            out.append(b"@q%d" % i + eol + bytes(sq) + eol + b"+" + eol + bytes(q) + eol)
+        return b"".join(out)
+
+    w("reads_q.fq", fastq_q(3000, 41))
+    w("reads_q_dos.fq", fastq_q(1000, 42, eol=b"\r\n"))
     return f
