@@ -38,10 +38,10 @@ public:
   }
   // == random()
   long next() { return (long)step(); }
-  // == random_bits(length), reference lib/misc.cc:66-72 (RAND_MAX = 2^31-1 => 31 bits per draw)
+  // == random_bits(length), reference lib/misc.cc:66-72 (step ConstFloorLog2<RAND_MAX> = 30 bits: the 31-bit draws overlap by one bit)
   uint64_t bits(int length) {
     uint64_t res = 0;
-    for(int i = 0; i < length; i += 31)
+    for(int i = 0; i < length; i += 30)
       res ^= (uint64_t)next() << i;
     return res & ((uint64_t)-1 >> (64 - length));
   }

@@ -13,7 +13,7 @@
  *
  *   jf_oracle count -m K -s SIZE [-C] [-c VAL_LEN] [-p REPROBES] [--out-counter-len N]
  *                   [-L LOW] [-U HIGH] [--text] [--if FILE]... [-Q CHAR | --min-quality N
- *                   [--quality-start S]] [-o OUT] file...
+ *                   [--quality-start S]] [--bf-size N [--bf-fp P]] [-o OUT] file...
  *   jf_oracle matrix R C [SKIP]        print the hash matrix columns the reference would draw
  */
 #define _GNU_SOURCE
@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <math.h>
 
 typedef unsigned __int128 u128;
 
@@ -48,7 +49,7 @@ static void rnd_seed(uint32_t seed) {
 /* random_bits(64): lib/misc.cc:66-72 */
 static uint64_t random_bits64(void) {
   uint64_t res = 0;
-  for(int i = 0; i < 64; i += 31) res ^= (uint64_t)rnd_step() << i;
+  for(int i = 0; i < 64; i += 30) res ^= (uint64_t)rnd_step() << i;   /* step = floor(log2(RAND_MAX)) = 30: draws overlap by one bit */
   return res;
 }
 
@@ -102,7 +103,10 @@ static void mat_draw(unsigned r, unsigned c, matrix_t* out) {
 static unsigned K;
 static int canonical;
 static u128* mers; static size_t n_mers, cap_mers;
+static int bf_filter(u128 m);
+static int bf_on;
 static void emit(u128 m) {
+  if(bf_on && !bf_filter(m)) return;   /* filter_bf: count_main.cc:122-133,157-161 */
   if(n_mers == cap_mers) { cap_mers = cap_mers ? cap_mers * 2 : (1 << 20); mers = realloc(mers, cap_mers * sizeof(u128)); if(!mers) { perror("realloc"); exit(1); } }
   mers[n_mers++] = m;
 }
@@ -192,6 +196,40 @@ static int count_file(const char* path) {
   free(d);
   filled = 0;
   return 1;
+}
+
+/* ---- --bf-size / --bf-fp: one-pass Bloom prefilter --------------------------------------------
+ * count_main.cc:317-321 builds mer_dna_bloom_filter(bf_fp, bf_size) AFTER the table (and after the
+ * --if pass), so its two 64 x 2k hash matrices (mer_dna_bloom_counter.hpp:22-36: randomize(), no
+ * invertibility test) are the draws that follow the first table matrix.  bloom_common.hpp:62-67:
+ * m = n * lrint(-ln fp / ln^2 2) bits, k = lrint(-ln fp / ln 2) functions.  bloom_filter.hpp:40-63
+ * insert__: positions (h1 % m + i * (h2 % m)) % m, test-and-set, "present" = all k bits were set.
+ * An occurrence reaches the table only when the filter already held the k-mer (or a false
+ * positive).  The outcome depends on the ORDER of insertions: this restatement processes the
+ * occurrences in input order, which is what the reference does with -t 1 (one thread, one
+ * parser buffer at a time); with more threads the reference's own output varies in the false
+ * positives. */
+static unsigned char* bf_bits; static uint64_t bf_m; static unsigned long bf_k; static matrix_t bf_m1, bf_m2;
+static void bf_setup(double fp, uint64_t n) {
+  const double LOG2 = 0.6931471805599453, LOG2_SQ = 0.4804530139182014;
+  bf_m = n * (uint64_t)lrint(-log(fp) / LOG2_SQ);
+  bf_k = lrint(-log(fp) / LOG2);
+  bf_bits = calloc(bf_m / 8 + (bf_m % 8 != 0) + 1, 1);
+  if(!bf_bits) { perror("calloc"); exit(1); }
+  bf_m1.r = bf_m2.r = 64; bf_m1.c = bf_m2.c = 2 * K; bf_m1.identity = bf_m2.identity = 0;
+  for(unsigned i = 0; i < 2 * K; ++i) bf_m1.col[i] = random_bits64();
+  for(unsigned i = 0; i < 2 * K; ++i) bf_m2.col[i] = random_bits64();
+  bf_on = 1;
+}
+static int bf_filter(u128 m) {
+  uint64_t base = mat_times(&bf_m1, m) % bf_m, inc = mat_times(&bf_m2, m) % bf_m;
+  int present = 1;
+  for(unsigned long i = 0; i < bf_k; ++i) {
+    uint64_t pos = (base + i * inc) % bf_m;
+    unsigned char mask = (unsigned char)(1u << (pos % 8));
+    if(!(bf_bits[pos / 8] & mask)) { present = 0; bf_bits[pos / 8] |= mask; }
+  }
+  return present;
 }
 
 /* ---- -Q / --min-quality: whole reads with their quality strings -----------------------------
@@ -309,6 +347,7 @@ int main(int argc, char** argv) {
   const char* if_files[64]; int n_if = 0;   /* --if: count only the k-mers of these files (count_main.cc:288-295) */
   int text = 0;   /* --text: text_dumper.hpp ("MER count" lines, format "text/sorted", no counter_len) */
   int first_file = argc;
+  uint64_t bf_size = 0; double bf_fp = 0.01;   /* count_main_cmdline.yaggo:44-49 */
   int min_quality = 0, quality_start = 64;   /* count_main_cmdline.yaggo:56-61 */
   for(int i = 2; i < argc; ++i) {
     if(!strcmp(argv[i], "-m")) K = atoi(argv[++i]);
@@ -327,6 +366,8 @@ int main(int argc, char** argv) {
       if(strlen(a) != 1 || a[0] < '!' || a[0] > '~') { fprintf(stderr, "[-Q, --min-qual-char] must be one printable character\n"); return 1; }
       min_qual = a[0]; use_qual = 1;
     }
+    else if(!strcmp(argv[i], "--bf-size")) bf_size = parse_size(argv[++i]);
+    else if(!strcmp(argv[i], "--bf-fp")) bf_fp = atof(argv[++i]);
     else if(!strcmp(argv[i], "--min-quality")) { min_quality = atoi(argv[++i]); use_qual = 2; }
     else if(!strcmp(argv[i], "--quality-start")) quality_start = atoi(argv[++i]);
     else if(!strcmp(argv[i], "--if")) { if(n_if < 64) if_files[n_if++] = argv[++i]; else ++i; }
@@ -356,6 +397,7 @@ int main(int argc, char** argv) {
     memcpy(if_keys, mers, n_if_keys * sizeof(u128));
     n_mers = 0;
   }
+  if(bf_size) bf_setup(bf_fp, bf_size);
   for(int i = first_file; i < argc; ++i) if(!(use_qual ? count_file_qual(argv[i]) : count_file(argv[i]))) return 1;
   if(n_if) {
     /* keep the occurrences of primed keys, then add one zero-count marker per primed key */

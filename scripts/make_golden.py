@@ -14,16 +14,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gen      # noqa: E402
 import jfutil   # noqa: E402
-from cases import CASES, QUAL_CASES  # noqa: E402
+from cases import BIG_CASES, CASES, QUAL_CASES  # noqa: E402
 
 os.environ["SOURCE_DATE_EPOCH"] = "0"
 with tempfile.TemporaryDirectory() as d:
   files = gen.make_all(d)
-  for cases, target in ((CASES, "golden.json"), (QUAL_CASES, "golden_qual.json")):
+  sets = ((BIG_CASES, "golden_big.json"),) if "--big" in sys.argv else ((CASES, "golden.json"), (QUAL_CASES, "golden_qual.json"))
+  for cases, target in sets:
     out = {}
     for name, (args, ins) in sorted(cases.items()):
         db = os.path.join(d, name + ".jf")
-        jfutil.run([jfutil.REF_JF, "count", "-t", "1"] + jfutil.subst(args, files) + ["-o", db] + [files[i] for i in ins])
+        jfutil.run([jfutil.REF_JF, "count", "-t", "8" if "--big" in sys.argv else "1"] + jfutil.subst(args, files) + ["-o", db] + [files[i] for i in ins])
         h, b = jfutil.split_db(db)
         out[name] = {"args": args, "inputs": ins, "header": jfutil.semantic(h), "body_md5": jfutil.md5(b), "body_len": len(b)}
         print(name, out[name]["body_md5"], len(b))

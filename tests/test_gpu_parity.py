@@ -10,7 +10,7 @@ import random
 import pytest
 
 import jfutil
-from cases import CASES
+from cases import BIG_CASES, CASES
 
 pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
@@ -330,3 +330,18 @@ def test_if_passes_via_api(part, built, inputs):
         assert jfutil.md5(hc.dump_records()) == g["body_md5"]
         hdr = hc.header()
         assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == g["header"]
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: not yet run on a device "
+                                        "(host-side matrix draw for > 30 rows is pinned on CPU in test_host.py)")
+@pytest.mark.parametrize("name", sorted(BIG_CASES))
+def test_cli_count_matches_reference_golden_large_table(name, built, workdir, inputs):
+    """A table of 2^31 slots (8 GB of 32-bit slots): the matrix has 31 rows, where the reference's
+    random_bits() overlaps its draws (lib/misc.cc:66-72); header and body against the reference's golden."""
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_big.json")))
+    args, ins = BIG_CASES[name]
+    h, b = _count_cli(workdir, inputs, name, args, ins)
+    g = golden[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"]
+    assert jfutil.md5(b) == g["body_md5"]

@@ -47,6 +47,17 @@ def test_reference_matrix_stream(built):
         assert j.reference_matrix(r, c, skip) == [int(x) for x in out]
 
 
+def test_reference_matrix_against_reference_library_golden(built):
+    # tests/golden/matrix_golden.json: drawn by the unmodified reference library, shapes with more
+    # than 30 rows included (tables of 2^31 slots and more -- BASELINE configs[1] uses 2^32..2^34)
+    import json
+    import jellyfish_b200 as j
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "matrix_golden.json")))
+    assert any(g["r"] > 30 for g in golden)
+    for g in golden:
+        assert j.reference_matrix(g["r"], g["c"], g["skip"]) == g["columns"], (g["r"], g["c"], g["skip"])
+
+
 def test_no_cpu_fallback(built):
     """Without a CUDA device the engine refuses to run (it must never count on the CPU)."""
     import torch
