@@ -92,3 +92,17 @@ QUAL_CASES = {
 BIG_CASES = {
     "big_l31": (["-m", "21", "-s", "2G", "-C"], ["plain.fa"]),
 }
+
+# --bf-size / --bf-fp: one-pass Bloom prefilter (count_main.cc:317-321, bloom_filter.hpp:40-63).
+# Which first occurrences are false positives depends on the insertion ORDER, so these goldens are
+# the reference with -t 1 (input order) and pin the restatement only; a device path can be held to
+# count(x) in {occ(x) - 1, occ(x)}. Restatement-only for now.
+BF_CASES = {
+    "bf_twice":    (["-m", "21", "-s", "1M", "-C", "--bf-size", "1M"], ["plain.fa", "plain.fa"]),
+    "bf_small":    (["-m", "21", "-s", "1M", "-C", "--bf-size", "300k"], ["repeat.fa", "multi.fa", "multi.fa"]),
+    "bf_fp10_grow": (["-m", "17", "-s", "100k", "--bf-size", "200k", "--bf-fp", "0.1"], ["plain.fa", "multi.fa", "plain.fa"]),
+    "bf_k40":      (["-m", "40", "-s", "100k", "--bf-size", "500k", "--bf-fp", "0.001"], ["plain.fa", "multi.fa", "plain.fa"]),
+    "bf_fq":       (["-m", "21", "-s", "1M", "-C", "--bf-size", "100k"], ["reads.fq", "reads.fq"]),
+    "bf_q":        (["-m", "17", "-s", "1M", "-C", "--bf-size", "400k", "-Q", "5"], ["reads_q.fq", "reads_q.fq", "reads_q_dos.fq"]),
+    "bf_k63":      (["-m", "63", "-s", "700k", "-C", "--bf-size", "700k", "--bf-fp", "0.05"], ["plain.fa", "dos.fa", "plain.fa"]),
+}
