@@ -14,6 +14,8 @@
  *   jf_oracle count -m K -s SIZE [-C] [-c VAL_LEN] [-p REPROBES] [--out-counter-len N]
  *                   [-L LOW] [-U HIGH] [--text] [--if FILE]... [-Q CHAR | --min-quality N
  *                   [--quality-start S]] [--bf-size N [--bf-fp P]] [-o OUT] file...
+ *   jf_oracle bc -m K -s N [-f FPR] [-C] -o OUT file...     the Bloom counter file of `jellyfish bc`
+ *   (count also takes --bc FILE: keep the k-mers that file has seen at least twice)
  *   jf_oracle matrix R C [SKIP]        print the hash matrix columns the reference would draw
  */
 #define _GNU_SOURCE
@@ -105,8 +107,12 @@ static int canonical;
 static u128* mers; static size_t n_mers, cap_mers;
 static int bf_filter(u128 m);
 static int bf_on;
+static void bc_insert(u128 m); static int bc_check(u128 m);
+static int bc_build, bc_on;
 static void emit(u128 m) {
+  if(bc_build) { bc_insert(m); return; }   /* `jellyfish bc`: bc_main.cc:66-70 */
   if(bf_on && !bf_filter(m)) return;   /* filter_bf: count_main.cc:122-133,157-161 */
+  if(bc_on && bc_check(m) <= 1) return;    /* filter_bc: count_main.cc:110-120 */
   if(n_mers == cap_mers) { cap_mers = cap_mers ? cap_mers * 2 : (1 << 20); mers = realloc(mers, cap_mers * sizeof(u128)); if(!mers) { perror("realloc"); exit(1); } }
   mers[n_mers++] = m;
 }
@@ -232,6 +238,111 @@ static int bf_filter(u128 m) {
   return present;
 }
 
+/* ---- `jellyfish bc` and `count --bc FILE`: two-pass Bloom counter ------------------------------
+ * bloom_counter2.hpp:34-36,49-108: m positions, each a base-3 digit (0,1,2 = saturated) packed
+ * five to a byte; insert increments the k positions (h1 % m + i * (h2 % m)) % m that are below 2.
+ * Every position ends at min(2, number of hits): the file does not depend on insertion order or
+ * thread count.  check = minimum digit over the k positions; `count --bc` keeps a k-mer
+ * occurrence only if check > 1 (count_main.cc:110-120), i.e. all occurrences of k-mers seen at
+ * least twice (plus false positives).  bc_main.cc:103-113: the two 64 x 2k matrices are the first
+ * two draws of the random stream (randomize(), no invertibility test), m = n * lrint(-ln f / ln^2 2),
+ * k = lrint(-ln f / ln 2); header format "bloomcounter" with matrix1, matrix2, size = m, nb_hashes = k. */
+static const unsigned bc_pow3[5] = {1, 3, 9, 27, 81};
+static void bc_insert(u128 m) {
+  uint64_t base = mat_times(&bf_m1, m) % bf_m, inc = mat_times(&bf_m2, m) % bf_m;
+  for(unsigned long i = 0; i < bf_k; ++i) {
+    uint64_t pos = (base + i * inc) % bf_m;
+    unsigned d = pos % 5;
+    if(bf_bits[pos / 5] / bc_pow3[d] % 3 < 2) bf_bits[pos / 5] += bc_pow3[d];
+  }
+}
+static int bc_check(u128 m) {
+  uint64_t base = mat_times(&bf_m1, m) % bf_m, inc = mat_times(&bf_m2, m) % bf_m;
+  unsigned res = 2;
+  for(unsigned long i = 0; i < bf_k; ++i) {
+    uint64_t pos = (base + i * inc) % bf_m;
+    unsigned w = bf_bits[pos / 5] / bc_pow3[pos % 5] % 3;
+    if(w < res) res = w;
+  }
+  return (int)res;
+}
+static const char* js_find(const char* js, const char* key) {
+  const char* p = strstr(js, key);
+  if(!p) { fprintf(stderr, "Failed to parse bloom filter file (no %s)\n", key); exit(1); }
+  return p + strlen(key);
+}
+static void js_columns(const char* js, const char* name, matrix_t* m) {
+  const char* p = js_find(js_find(js, name), "\"columns\":[");
+  unsigned n = 0;
+  while(*p && *p != ']') { char* e; m->col[n++] = strtoull(p, &e, 10); p = *e == ',' ? e + 1 : e; if(n > 256) break; }
+  m->c = n; m->r = 64; m->identity = 0;
+}
+/* load_bloom_filter: count_main.cc:191-206 */
+static void bc_load(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if(!f) { fprintf(stderr, "Failed to parse bloom filter file '%s'\n", path); exit(1); }
+  char digits[10] = {0};
+  if(fread(digits, 1, 9, f) != 9) { fprintf(stderr, "Failed to parse bloom filter file '%s'\n", path); exit(1); }
+  size_t hlen = strtoull(digits, 0, 10);
+  char* js = calloc(hlen + 1, 1);
+  if(fread(js, 1, hlen, f) != hlen) { fprintf(stderr, "Failed to parse bloom filter file '%s'\n", path); exit(1); }
+  if(!strstr(js, "\"format\":\"bloomcounter\"")) { fprintf(stderr, "Invalid format. Expected 'bloomcounter'\n"); exit(1); }
+  if(strtoul(js_find(js, "\"key_len\":"), 0, 10) != 2 * K) { fprintf(stderr, "Invalid mer length in bloom filter\n"); exit(1); }
+  js_columns(js, "\"matrix1\":", &bf_m1); js_columns(js, "\"matrix2\":", &bf_m2);
+  bf_m = strtoull(js_find(js, "\"size\":"), 0, 10);
+  bf_k = strtoul(js_find(js, "\"nb_hashes\":"), 0, 10);
+  size_t nb = bf_m / 5 + (bf_m % 5 != 0);
+  bf_bits = calloc(nb + 1, 1);
+  if(fread(bf_bits, 1, nb, f) != nb) { fprintf(stderr, "Bloom filter file is truncated\n"); exit(1); }
+  fclose(f); free(js);
+  bc_on = 1;
+}
+static uint64_t parse_size(const char* s);
+static int count_file(const char* path);
+static int bc_main(int argc, char** argv) {
+  uint64_t n = 0; double fpr = 0.001; const char* out = 0; int first = argc;   /* bc_main_cmdline.yaggo */
+  for(int i = 2; i < argc; ++i) {
+    if(!strcmp(argv[i], "-m")) K = atoi(argv[++i]);
+    else if(!strcmp(argv[i], "-s")) n = parse_size(argv[++i]);
+    else if(!strcmp(argv[i], "-f")) fpr = atof(argv[++i]);
+    else if(!strcmp(argv[i], "-C")) canonical = 1;
+    else if(!strcmp(argv[i], "-t")) ++i;
+    else if(!strcmp(argv[i], "-o")) out = argv[++i];
+    else { first = i; break; }
+  }
+  if(K < 1 || K > 64 || n == 0 || !out) { fprintf(stderr, "usage: jf_oracle bc -m K -s N [-f FPR] [-C] -o OUT file...\n"); return 1; }
+  const double LOG2 = 0.6931471805599453, LOG2_SQ = 0.4804530139182014;
+  bf_m1.r = bf_m2.r = 64; bf_m1.c = bf_m2.c = 2 * K; bf_m1.identity = bf_m2.identity = 0;
+  for(unsigned i = 0; i < 2 * K; ++i) bf_m1.col[i] = random_bits64();
+  for(unsigned i = 0; i < 2 * K; ++i) bf_m2.col[i] = random_bits64();
+  bf_m = n * (uint64_t)lrint(-log(fpr) / LOG2_SQ);
+  bf_k = lrint(-log(fpr) / LOG2);
+  size_t nb = bf_m / 5 + (bf_m % 5 != 0);
+  bf_bits = calloc(nb + 1, 1);
+  bc_build = 1;
+  for(int i = first; i < argc; ++i) if(!count_file(argv[i])) return 1;
+  FILE* f = fopen(out, "wb");
+  if(!f) { fprintf(stderr, "Can't open output file '%s'\n", out); return 1; }
+  char* js = malloc(1 << 20); size_t o = 0;
+  o += sprintf(js + o, "{\"alignment\":8,\"canonical\":%s,\"cmdline\":[\"jf_oracle\"],\"exe_path\":\"jf_oracle\",\"format\":\"bloomcounter\",\"hostname\":\"hostname\",\"key_len\":%u,",
+               canonical ? "true" : "false", 2 * K);
+  for(int w = 1; w <= 2; ++w) {
+    const matrix_t* M = w == 1 ? &bf_m1 : &bf_m2;
+    o += sprintf(js + o, "\"matrix%d\":{\"c\":%u,\"columns\":[", w, M->c);
+    for(unsigned i = 0; i < M->c; ++i) o += sprintf(js + o, "%s%llu", i ? "," : "", (unsigned long long)M->col[i]);
+    o += sprintf(js + o, "],\"identity\":false,\"r\":64},");
+  }
+  o += sprintf(js + o, "\"nb_hashes\":%lu,\"pwd\":\".\",\"size\":%llu,\"time\":\"Thu Jan  1 00:00:00 1970\"}", bf_k, (unsigned long long)bf_m);
+  size_t hlen = o, pad = (9 + o) % 8;
+  if(pad) hlen += 8 - pad;
+  fprintf(f, "%09zu", hlen);
+  fwrite(js, 1, o, f);
+  for(size_t i = o; i < hlen; ++i) fputc(0, f);
+  fwrite(bf_bits, 1, nb, f);
+  fclose(f);
+  return 0;
+}
+
 /* ---- -Q / --min-quality: whole reads with their quality strings -----------------------------
  * count_main.cc:326-329 switches to mer_qual_counter = whole_sequence_parser (one record at a
  * time: whole_sequence_parser.hpp:137-152 read_fasta, :154-193 read_fastq) + mer_qual_iterator
@@ -342,11 +453,13 @@ int main(int argc, char** argv) {
     for(unsigned i = 0; i < c; ++i) printf("%llu\n", (unsigned long long)m.col[i]);
     return 0;
   }
+  if(argc >= 2 && !strcmp(argv[1], "bc")) return bc_main(argc, argv);
   if(argc < 2 || strcmp(argv[1], "count")) { fprintf(stderr, "usage: jf_oracle count ... | matrix R C [SKIP]\n"); return 1; }
   uint64_t size = 0, low = 0, high = ~0ULL; unsigned val_len = 7, reprobes = 126, ocl = 4; const char* out = "mer_counts.jf";
   const char* if_files[64]; int n_if = 0;   /* --if: count only the k-mers of these files (count_main.cc:288-295) */
   int text = 0;   /* --text: text_dumper.hpp ("MER count" lines, format "text/sorted", no counter_len) */
   int first_file = argc;
+  const char* bc_path = 0;
   uint64_t bf_size = 0; double bf_fp = 0.01;   /* count_main_cmdline.yaggo:44-49 */
   int min_quality = 0, quality_start = 64;   /* count_main_cmdline.yaggo:56-61 */
   for(int i = 2; i < argc; ++i) {
@@ -368,6 +481,7 @@ int main(int argc, char** argv) {
     }
     else if(!strcmp(argv[i], "--bf-size")) bf_size = parse_size(argv[++i]);
     else if(!strcmp(argv[i], "--bf-fp")) bf_fp = atof(argv[++i]);
+    else if(!strcmp(argv[i], "--bc")) bc_path = argv[++i];
     else if(!strcmp(argv[i], "--min-quality")) { min_quality = atoi(argv[++i]); use_qual = 2; }
     else if(!strcmp(argv[i], "--quality-start")) quality_start = atoi(argv[++i]);
     else if(!strcmp(argv[i], "--if")) { if(n_if < 64) if_files[n_if++] = argv[++i]; else ++i; }
@@ -397,6 +511,7 @@ int main(int argc, char** argv) {
     memcpy(if_keys, mers, n_if_keys * sizeof(u128));
     n_mers = 0;
   }
+  if(bc_path) bc_load(bc_path);
   if(bf_size) bf_setup(bf_fp, bf_size);
   for(int i = first_file; i < argc; ++i) if(!(use_qual ? count_file_qual(argv[i]) : count_file(argv[i]))) return 1;
   if(n_if) {

@@ -106,3 +106,18 @@ BF_CASES = {
     "bf_q":        (["-m", "17", "-s", "1M", "-C", "--bf-size", "400k", "-Q", "5"], ["reads_q.fq", "reads_q.fq", "reads_q_dos.fq"]),
     "bf_k63":      (["-m", "63", "-s", "700k", "-C", "--bf-size", "700k", "--bf-fp", "0.05"], ["plain.fa", "dos.fa", "plain.fa"]),
 }
+
+# `jellyfish bc` (bc_main.cc) then `count --bc FILE` (count_main.cc:110-120,191-206): two-pass Bloom
+# counter. Both outputs are independent of insertion order and thread count (every position of the
+# counter ends at min(2, hits)), so a device path can be held to these byte for byte.
+# name -> (bc switches, bc inputs, count switches (--bc FILE is appended), count inputs)
+BC_CASES = {
+    "bc_k21C":  (["-m", "21", "-s", "400k", "-C"], ["plain.fa", "multi.fa", "plain.fa"],
+                 ["-m", "21", "-s", "1M", "-C"], ["plain.fa", "multi.fa", "plain.fa"]),
+    "bc_k40":   (["-m", "40", "-s", "100k", "-f", "0.05"], ["plain.fa", "dos.fa", "reads.fq"],
+                 ["-m", "40", "-s", "100k"], ["plain.fa", "dos.fa", "dos.fa", "reads.fq"]),
+    "bc_k63C":  (["-m", "63", "-s", "700k", "-C", "-f", "0.01"], ["plain.fa", "repeat.fa"],
+                 ["-m", "63", "-s", "700k", "-C"], ["repeat.fa", "plain.fa", "plain.fa"]),
+    "bc_tiny":  (["-m", "12", "-s", "20k", "-C"], ["multi.fa"],
+                 ["-m", "12", "-s", "300k", "-C", "-L", "2"], ["multi.fa", "multi2.fa"]),
+}
