@@ -410,32 +410,250 @@ static int count_file_qual(const char* path) {
   return 1;
 }
 
-static int cmp_u128(const void* a, const void* b) { u128 x = *(const u128*)a, y = *(const u128*)b; return x < y ? -1 : x > y; }
-typedef struct { uint64_t pos; u128 key; uint64_t count; } rec_t;
-static int cmp_rec(const void* a, const void* b) {
-  const rec_t* x = a; const rec_t* y = b;
-  if(x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
-  return x->key < y->key ? -1 : x->key > y->key;
-}
+typedef struct { uint64_t pos; u128 key; uint64_t count; uint64_t id; } rec_t;
 static unsigned ceil_log2(uint64_t x) { unsigned l = 0; while(l < 64 && (1ULL << l) < x) ++l; return l; }
-static unsigned bitsize(uint64_t x) { unsigned b = 0; while(x) { ++b; x >>= 1; } return b ? b : 1; }
 static uint64_t reprobe_off(unsigned i) { return i == 0 ? 1 : (uint64_t)i * (i + 1) / 2; }   /* lib/storage.cc:13-41 */
 
-/* Would every distinct key find a slot within `limit` reprobes?  claim_key probing,
- * large_hash_array.hpp:509-597 (one slot per key; continuation entries of counts > 2^val_len
- * are not modelled, so the fullness decision is exact only for data without such counts). */
-static int fits(const rec_t* recs, size_t n, uint64_t size, unsigned limit, const matrix_t* m, const u128* order, size_t n_order) {
-  unsigned char* used = calloc(size, 1);
-  (void)recs; (void)n;
-  int ok = 1;
-  for(size_t i = 0; i < n_order && ok; ++i) {
-    uint64_t pos = mat_times(m, order[i]) & (size - 1);
-    unsigned r = 0; uint64_t id = pos;
-    while(used[id]) { if(++r > limit) { ok = 0; break; } id = (pos + reprobe_off(r)) & (size - 1); }
-    if(ok) used[id] = 1;
+/* ---- the table, slot by slot ------------------------------------------------------------------
+ * A logical model of large_hash::array (large_hash_array.hpp) and of hash_counter's growth
+ * (hash_counter.hpp:91-115,178-238), driven in input order, i.e. what the reference does with one
+ * thread.  A slot is EMPTY, the first entry of a KEY (key + the reprobe count it was claimed with +
+ * val_len bits of value) or a LARGE continuation entry (the reprobe count back to where its chain
+ * step started + lval_len = min(raw_key_len + val_len, 64) bits of value: offsets_key_value.hpp:91).
+ *  - claim_key (:509-597): probe pos, pos+1, pos+3, ... up to the reprobe limit for an EMPTY slot
+ *    or this key's own first entry; failure = "full".
+ *  - add_rec_at (:674-694): add into the value field; a carry goes to a LARGE entry searched from
+ *    (id + reprobes[0]) with the same probe sequence (claim_large_key :603-643: EMPTY, or LARGE
+ *    with the same reprobe count); its carry continues from there.  A failure leaves what was
+ *    stored in place and hands the rest (carry << bits stored) back to the caller.
+ *  - full (handle_full_ary/double_size): a new array of twice the size -- or, once size == 4^k,
+ *    of the same size with val_len + 1 -- with a new matrix draw (identity when size >= 4^k,
+ *    :992-1002) and the OLD array's clipped reprobe limit (ary_->max_reprobe()), clipped again
+ *    (reprobe_limit_t :29-39; 0 when key_len <= lsize :160).  Every first entry of the old array
+ *    is re-added in slot order with its resolved value (resolve_val_rec :889-937; a failure of
+ *    this add is ignored, as in the reference); then the failed operation is retried with the
+ *    remaining value.
+ * Slots are kept in a sparse map so that a 2^31-slot table costs memory only for what it holds. */
+enum { SLOT_EMPTY = 0, SLOT_KEY = 1, SLOT_LARGE = 2 };
+enum { SIM_ADD, SIM_SET, SIM_UPDATE };
+typedef struct { uint64_t id; u128 key; uint64_t val; unsigned char state; unsigned short r; } slot_t;
+typedef struct {
+  slot_t* a; size_t cap, n;
+  unsigned lsize, kbits, limit, val_len, lval_len; uint64_t mask; matrix_t M;
+} sim_t;
+static size_t sim_home(const sim_t* T, uint64_t id) { return (size_t)((id * 0x9E3779B97F4A7C15ULL) >> 20) & (T->cap - 1); }
+static slot_t* sim_get(const sim_t* T, uint64_t id) {
+  for(size_t h = sim_home(T, id); ; h = (h + 1) & (T->cap - 1)) {
+    if(T->a[h].state == SLOT_EMPTY) return 0;
+    if(T->a[h].id == id) return &T->a[h];
   }
-  free(used);
-  return ok;
+}
+static slot_t* sim_put(sim_t* T, uint64_t id) {
+  if((T->n + 1) * 2 > T->cap) {
+    slot_t* old = T->a; size_t ocap = T->cap;
+    T->cap *= 2; T->a = calloc(T->cap, sizeof(slot_t));
+    if(!T->a) { perror("calloc"); exit(1); }
+    for(size_t i = 0; i < ocap; ++i) if(old[i].state != SLOT_EMPTY) {
+      size_t h = sim_home(T, old[i].id);
+      while(T->a[h].state != SLOT_EMPTY) h = (h + 1) & (T->cap - 1);
+      T->a[h] = old[i];
+    }
+    free(old);
+  }
+  size_t h = sim_home(T, id);
+  while(T->a[h].state != SLOT_EMPTY) h = (h + 1) & (T->cap - 1);
+  T->a[h].id = id; ++T->n;
+  return &T->a[h];
+}
+static unsigned ceil_log2(uint64_t x);
+static uint64_t reprobe_off(unsigned i);
+static void sim_geometry(sim_t* T, unsigned lsize, unsigned limit_in) {
+  T->lsize = lsize; T->mask = (1ULL << lsize) - 1;
+  unsigned limit = T->kbits > lsize ? limit_in : 0;                                  /* :160 */
+  while(limit >= 1 && reprobe_off(limit) >= (1ULL << lsize)) --limit;                /* :29-39 */
+  T->limit = limit;
+  unsigned raw = T->kbits > lsize ? T->kbits - lsize : 0;
+  T->lval_len = raw + T->val_len < 64 ? raw + T->val_len : 64;
+}
+static void sim_init(sim_t* T, unsigned lsize, unsigned kbits, unsigned val_len, unsigned reprobes, const matrix_t* M) {
+  memset(T, 0, sizeof(*T));
+  T->cap = 1 << 16; T->a = calloc(T->cap, sizeof(slot_t));
+  T->kbits = kbits; T->val_len = val_len; T->M = *M;
+  sim_geometry(T, lsize, reprobes);
+}
+/* add `v` to the field of `bits` bits of slot s; returns the carry */
+static uint64_t sim_add_field(slot_t* s, uint64_t v, unsigned bits) {
+  u128 nval = (u128)s->val + v;
+  if(bits >= 64) { s->val = (uint64_t)nval; return (uint64_t)(nval >> 64); }
+  s->val = (uint64_t)nval & ((1ULL << bits) - 1);
+  return (uint64_t)(nval >> bits);
+}
+/* returns 1 when done, 0 when full (*rem = what is left to add), -1 when UPDATE found no key */
+static int sim_try(sim_t* T, u128 key, uint64_t v, int op, uint64_t* rem) {
+  const uint64_t pos = mat_times(&T->M, key) & T->mask;
+  uint64_t cid = pos; unsigned r = 0; slot_t* s;
+  for(;;) {                                                  /* claim_key / get_key_id */
+    s = sim_get(T, cid);
+    if(!s) {
+      if(op == SIM_UPDATE) return -1;
+      s = sim_put(T, cid); s->state = SLOT_KEY; s->key = key; s->r = (unsigned short)r; s->val = 0;
+      break;
+    }
+    if(s->state == SLOT_KEY && s->key == key) break;
+    if(++r > T->limit) { if(op == SIM_UPDATE) return -1; *rem = v; return 0; }
+    cid = (pos + reprobe_off(r)) & T->mask;
+  }
+  if(op == SIM_SET) return 1;
+  uint64_t carry = sim_add_field(s, v, T->val_len);
+  unsigned stored = T->val_len;
+  while(carry) {                                             /* claim_large_key from (id + reprobes[0]) */
+    const uint64_t start = (cid + reprobe_off(0)) & T->mask;
+    uint64_t c = start; r = 0;
+    for(;;) {
+      s = sim_get(T, c);                                     /* (sim_put may move entries: re-fetched each time) */
+      if(!s) { s = sim_put(T, c); s->state = SLOT_LARGE; s->r = (unsigned short)r; s->val = 0; break; }
+      if(s->state == SLOT_LARGE && s->r == r) break;
+      if(++r > T->limit) { *rem = stored >= 64 ? 0 : carry << stored; return 0; }
+      c = (start + reprobe_off(r)) & T->mask;
+    }
+    carry = sim_add_field(s, carry, T->lval_len);
+    stored += T->lval_len;
+    cid = c;
+  }
+  return 1;
+}
+/* value of the key whose first entry is at id: get_val_at_id + resolve_val_rec (:868-937) */
+static uint64_t sim_resolve(const sim_t* T, uint64_t id) {
+  const slot_t* s = sim_get(T, id);
+  uint64_t val = s->val; unsigned shift = T->val_len;
+  uint64_t start = (id + reprobe_off(0)) & T->mask;
+  for(;;) {
+    unsigned r = 0; uint64_t c = start; int found = 0;
+    while(r <= T->limit) {
+      s = sim_get(T, c);
+      if(s && s->state == SLOT_LARGE) { if(s->r == r) { found = 1; break; } }
+      else if(!s) break;
+      c = (start + reprobe_off(++r)) & T->mask;
+    }
+    if(!found) return val;
+    if(shift < 64) val += s->val << shift;
+    shift += T->lval_len;
+    start = (c + reprobe_off(0)) & T->mask;
+  }
+}
+static int cmp_slot_id(const void* a, const void* b) { const slot_t* x = a; const slot_t* y = b; return x->id < y->id ? -1 : x->id > y->id; }
+static void mat_draw(unsigned r, unsigned c, matrix_t* out);
+static void sim_grow(sim_t* T) {                             /* hash_counter.hpp:200-238 */
+  sim_t N = *T;
+  N.cap = T->cap; N.a = calloc(N.cap, sizeof(slot_t)); N.n = 0;
+  if(!N.a) { perror("calloc"); exit(1); }
+  const int can_double = T->kbits >= 64 || T->lsize < T->kbits;
+  unsigned nl = T->lsize;
+  if(can_double) ++nl; else ++N.val_len;
+  if(T->kbits < 64 && nl >= T->kbits) { N.M.identity = 1; N.M.r = N.M.c = T->kbits; }   /* :992-1002: size >= 4^k */
+  else mat_draw(nl, T->kbits, &N.M);
+  sim_geometry(&N, nl, T->limit);
+  /* re-add every first entry in slot order with its resolved value (eager_slice(0, 1)) */
+  size_t nk = 0;
+  slot_t* keys = malloc((T->n ? T->n : 1) * sizeof(slot_t));
+  for(size_t i = 0; i < T->cap; ++i) if(T->a[i].state == SLOT_KEY) keys[nk++] = T->a[i];
+  qsort(keys, nk, sizeof(slot_t), cmp_slot_id);
+  for(size_t i = 0; i < nk; ++i) {
+    uint64_t rem, v = sim_resolve(T, keys[i].id);
+    if(v == 0) sim_try(&N, keys[i].key, 0, SIM_ADD, &rem);   /* add(key, 0): the key is claimed, nothing to add */
+    else sim_try(&N, keys[i].key, v, SIM_ADD, &rem);         /* a failure here is ignored by the reference too */
+  }
+  free(keys); free(T->a);
+  *T = N;
+}
+static void sim_op(sim_t* T, u128 key, uint64_t v, int op) {
+  uint64_t rem = 0;
+  for(unsigned guard = 0; ; ++guard) {
+    int rc = sim_try(T, key, v, op, &rem);
+    if(rc != 0) return;
+    if(guard > 200) { fprintf(stderr, "Hash full\n"); exit(1); }
+    sim_grow(T);
+    if(op == SIM_SET) continue;
+    v = rem; op = SIM_ADD;                                   /* hash_counter::add retries with carry_shift */
+    if(v == 0) return;
+  }
+}
+
+/* ---- order of the records in the dump ---------------------------------------------------------
+ * sorted_dumper.hpp:57-101: the table is cut into chunks of B slots, B = the smallest multiple of
+ * the packing block length (offsets_key_value.hpp:236-262) holding 5 * max(1, reprobes[limit])
+ * records; a chunk yields the keys whose ORIGINAL position lies in it, read in slot order from its
+ * start up to reprobes[limit] slots past its end (large_hash_iterator.hpp:150-198, wrapping), and
+ * passes them through a min-heap on (position, key) of capacity reprobes[limit]
+ * (mer_heap.hpp:26-30,57-100): fill, then pop one / push one.  With the default limit (capacity
+ * 8001) that is a sort by (position, key); with a clipped limit of 1 or 2 (tables of a few
+ * slots grown from -s < 8) the heap is too small to reorder equal positions and the output keeps
+ * slot order there.  Chunk boundaries do not depend on the number of dumper threads. */
+static unsigned bitsize(uint64_t x) { unsigned b = 0; while(x) { ++b; x >>= 1; } return b ? b : 1; }
+static unsigned packing_block_len(unsigned key_field, unsigned val_len) {
+  unsigned cword = 0, cboff = 0, n = 0;
+  do {
+    unsigned add = key_field + 1;                            /* + large bit */
+    if(cboff + add <= 64) { cboff = (cboff + add) % 64; cword += cboff == 0; }
+    else { add -= 63 - cboff; cword += 1 + add / 63; cboff = add % 63; cboff += cboff > 0; }
+    cboff += val_len; cword += cboff / 64; cboff %= 64;
+    ++n;
+  } while(cboff != 0 && cboff < 62);
+  (void)cword;
+  return n;
+}
+static int cmp_rec_id(const void* a, const void* b) { const rec_t* x = a; const rec_t* y = b; return x->id < y->id ? -1 : x->id > y->id; }
+static int cmp_u64(const void* a, const void* b) { uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : x > y; }
+static int rec_less(const rec_t* x, const rec_t* y) { return x->pos != y->pos ? x->pos < y->pos : x->key < y->key; }
+static void heap_push(const rec_t** h, size_t* n, const rec_t* r) {
+  size_t i = (*n)++; h[i] = r;
+  while(i && rec_less(h[i], h[(i - 1) / 2])) { const rec_t* t = h[i]; h[i] = h[(i - 1) / 2]; h[(i - 1) / 2] = t; i = (i - 1) / 2; }
+}
+static const rec_t* heap_pop(const rec_t** h, size_t* n) {
+  const rec_t* top = h[0]; h[0] = h[--*n];
+  for(size_t i = 0; ; ) {
+    size_t l = 2 * i + 1, r = l + 1, m = i;
+    if(l < *n && rec_less(h[l], h[m])) m = l;
+    if(r < *n && rec_less(h[r], h[m])) m = r;
+    if(m == i) break;
+    const rec_t* t = h[i]; h[i] = h[m]; h[m] = t; i = m;
+  }
+  return top;
+}
+static rec_t* dump_order(rec_t* recs, size_t n, uint64_t size, unsigned limit, unsigned key_field, unsigned val_len) {
+  const uint64_t max_off = reprobe_off(limit), cap = max_off;
+  const unsigned blen = packing_block_len(key_field, val_len);
+  const uint64_t want = 5 * (max_off > 1 ? max_off : 1);
+  const uint64_t B = (want / blen + (want % blen != 0)) * blen;
+  qsort(recs, n, sizeof(rec_t), cmp_rec_id);
+  uint64_t* chunks = malloc((n ? n : 1) * sizeof(uint64_t));
+  for(size_t i = 0; i < n; ++i) chunks[i] = recs[i].pos / B;
+  qsort(chunks, n, sizeof(uint64_t), cmp_u64);
+  rec_t* out = malloc((n ? n : 1) * sizeof(rec_t)); size_t no = 0;
+  const rec_t** heap = malloc((cap + 1) * sizeof(rec_t*));
+  const rec_t** stream = malloc((n ? n : 1) * sizeof(rec_t*));
+  for(size_t ci = 0; ci < n; ++ci) {
+    if(ci && chunks[ci] == chunks[ci - 1]) continue;
+    const uint64_t start = chunks[ci] * B, end = start + B < size ? start + B : size;
+    uint64_t mid = end - start + max_off; if(mid > size) mid = size;
+    /* slots start .. start + mid - 1 (mod size) in that order, keys whose position is in [start, end) */
+    size_t ns = 0, lo = 0, hi = n;
+    while(lo < hi) { size_t m = (lo + hi) / 2; if(recs[m].id < start) lo = m + 1; else hi = m; }
+    const uint64_t lim1 = start + mid < size ? start + mid : size;
+    for(size_t i = lo; i < n && recs[i].id < lim1; ++i) if(recs[i].pos >= start && recs[i].pos < end) stream[ns++] = &recs[i];
+    if(start + mid > size) {
+      const uint64_t lim2 = start + mid - size;
+      for(size_t i = 0; i < n && recs[i].id < lim2 && recs[i].id < start; ++i) if(recs[i].pos >= start && recs[i].pos < end) stream[ns++] = &recs[i];
+    }
+    size_t hn = 0, next = 0;
+    while(next < ns && hn < cap) heap_push(heap, &hn, stream[next++]);
+    while(hn) {
+      out[no++] = *heap_pop(heap, &hn);
+      if(next < ns) heap_push(heap, &hn, stream[next++]);
+    }
+  }
+  free(heap); free(stream); free(chunks); free(recs);
+  return out;
 }
 
 static uint64_t parse_size(const char* s) {
@@ -498,93 +716,37 @@ int main(int argc, char** argv) {
   uint64_t key_space = kbits >= 64 ? ~0ULL / 2 : (1ULL << kbits);
   unsigned lsize = ceil_log2(size < key_space ? size : key_space);
   matrix_t M;
+  if(lsize == 0) { fprintf(stderr, "Invalid matrix size\n"); return 134; }   /* RectangularBinaryMatrix(0, c) throws: the reference aborts */
   if(size < key_space) mat_draw(lsize, kbits, &M); else { M.identity = 1; M.r = M.c = kbits; }
 
-  /* --if: first pass PRIME (array::set, every key enters with count 0), second pass UPDATE
-   * (update_add: only keys already present are incremented) */
-  u128* if_keys = 0; size_t n_if_keys = 0;
+  /* The table is simulated slot by slot in input order (= a reference run with -t 1): see sim_*
+   * above.  --if: first pass PRIME over the --if files (array::set: the key enters with count 0),
+   * second pass UPDATE (update_add: only keys already present are incremented),
+   * count_main.cc:288-295,152-184. */
+  sim_t T;
+  sim_init(&T, lsize, kbits, val_len, reprobes, &M);
   if(n_if) {
     for(int i = 0; i < n_if; ++i) if(!count_file(if_files[i])) return 1;
-    qsort(mers, n_mers, sizeof(u128), cmp_u128);
-    for(size_t i = 0; i < n_mers; ++i) if(i == 0 || mers[i] != mers[i - 1]) mers[n_if_keys++] = mers[i];
-    if_keys = malloc((n_if_keys ? n_if_keys : 1) * sizeof(u128));
-    memcpy(if_keys, mers, n_if_keys * sizeof(u128));
+    for(size_t i = 0; i < n_mers; ++i) sim_op(&T, mers[i], 0, SIM_SET);
     n_mers = 0;
   }
   if(bc_path) bc_load(bc_path);
   if(bf_size) bf_setup(bf_fp, bf_size);
   for(int i = first_file; i < argc; ++i) if(!(use_qual ? count_file_qual(argv[i]) : count_file(argv[i]))) return 1;
-  if(n_if) {
-    /* keep the occurrences of primed keys, then add one zero-count marker per primed key */
-    size_t kept = 0;
-    for(size_t i = 0; i < n_mers; ++i) {
-      size_t lo = 0, hi = n_if_keys;
-      while(lo < hi) { size_t mid = (lo + hi) / 2; if(if_keys[mid] < mers[i]) lo = mid + 1; else hi = mid; }
-      if(lo < n_if_keys && if_keys[lo] == mers[i]) mers[kept++] = mers[i];
-    }
-    n_mers = kept;
-  }
+  for(size_t i = 0; i < n_mers; ++i) sim_op(&T, mers[i], 1, n_if ? SIM_UPDATE : SIM_ADD);
 
-  /* first-occurrence order of the distinct keys (insertion order of a -t 1 run) */
-  u128* order = malloc((n_mers ? n_mers : 1) * sizeof(u128));
-  memcpy(order, mers, n_mers * sizeof(u128));
-  qsort(mers, n_mers, sizeof(u128), cmp_u128);
+  /* what the dumper sees: every first entry of a key with the sum of its chain */
   size_t n_rec = 0;
-  rec_t* recs = malloc((n_mers ? n_mers : 1) * sizeof(rec_t));
-  for(size_t i = 0; i < n_mers; ) {
-    size_t j = i; while(j < n_mers && mers[j] == mers[i]) ++j;
-    recs[n_rec].key = mers[i]; recs[n_rec].count = j - i; ++n_rec; i = j;
+  rec_t* recs = malloc((T.n ? T.n : 1) * sizeof(rec_t));
+  for(size_t i = 0; i < T.cap; ++i) {
+    if(T.a[i].state != SLOT_KEY) continue;
+    recs[n_rec].key = T.a[i].key; recs[n_rec].count = sim_resolve(&T, T.a[i].id);
+    recs[n_rec].pos = mat_times(&T.M, T.a[i].key) & T.mask; recs[n_rec].id = T.a[i].id; ++n_rec;
   }
-  if(n_if) {
-    /* primed keys never seen again stay in the table with count 0 (and are dumped: dumper min = 0) */
-    rec_t* all = malloc((n_if_keys ? n_if_keys : 1) * sizeof(rec_t));
-    size_t j = 0;
-    for(size_t i = 0; i < n_if_keys; ++i) {
-      all[i].key = if_keys[i]; all[i].count = 0;
-      while(j < n_rec && recs[j].key < if_keys[i]) ++j;
-      if(j < n_rec && recs[j].key == if_keys[i]) all[i].count = recs[j].count;
-    }
-    free(recs); recs = all; n_rec = n_if_keys;
-    /* insertion order of the PRIME pass = first occurrence in the --if files: approximated by key
-     * order (only matters for the fullness decision near the reprobe limit) */
-    free(order); order = malloc((n_rec ? n_rec : 1) * sizeof(u128));
-    for(size_t i = 0; i < n_rec; ++i) order[i] = recs[i].key;
-    n_mers = 0;
-  }
-  /* distinct keys in first-occurrence order: mark seen through a sorted lookup */
-  size_t n_order = n_if ? n_rec : 0;
-  if(!n_if) {
-    unsigned char* seen = calloc(n_rec ? n_rec : 1, 1);
-    for(size_t i = 0; i < n_mers; ++i) {
-      size_t lo = 0, hi = n_rec;
-      while(lo < hi) { size_t mid = (lo + hi) / 2; if(recs[mid].key < order[i]) lo = mid + 1; else hi = mid; }
-      if(!seen[lo]) { seen[lo] = 1; order[n_order++] = order[i]; }
-    }
-    free(seen);
-  }
-
-  /* size doubling: hash_counter.hpp:200-238 -- a new array (new matrix draw) twice as large
-   * until everything fits; at 4^k the table is direct-indexed with the identity matrix and the
-   * value field grows instead (:205-212). */
-  unsigned limit;
-  for(;;) {
-    uint64_t tsize = 1ULL << lsize;
-    limit = kbits > lsize ? reprobes : 0;                                 /* large_hash_array.hpp:160 */
-    while(limit >= 1 && reprobe_off(limit) >= tsize) --limit;             /* reprobe_limit_t :29-39 */
-    if(fits(recs, n_rec, tsize, limit, &M, order, n_order)) break;
-    ++lsize;
-    if(kbits < 64 && (1ULL << lsize) >= (1ULL << kbits)) { lsize = kbits; M.identity = 1; M.r = M.c = kbits; }
-    else mat_draw(lsize, kbits, &M);
-  }
-  uint64_t tsize = 1ULL << lsize, maxc = 0;
-  for(size_t i = 0; i < n_rec; ++i) { recs[i].pos = mat_times(&M, recs[i].key) & (tsize - 1); if(recs[i].count > maxc) maxc = recs[i].count; }
-  if(kbits <= lsize && maxc >= (1ULL << val_len)) {       /* direct indexing: val_len grows, matrix becomes identity */
-    val_len = bitsize(maxc);
-    M.identity = 1; M.r = M.c = kbits;
-    for(size_t i = 0; i < n_rec; ++i) recs[i].pos = mat_times(&M, recs[i].key) & (tsize - 1);
-  }
-  /* sorted_dumper: ascending (position, key): sorted_dumper.hpp:72-101, mer_heap.hpp:26-30 */
-  qsort(recs, n_rec, sizeof(rec_t), cmp_rec);
+  M = T.M; lsize = T.lsize; val_len = T.val_len;
+  const unsigned limit = T.limit;
+  const uint64_t tsize = 1ULL << lsize;
+  recs = dump_order(recs, n_rec, tsize, limit, (kbits > lsize ? kbits - lsize : 0) + bitsize(limit + 1), val_len);
 
   /* header: generic_file_header.hpp:88-111, file_header.hpp:26-108 (keys sorted, terse JSON) */
   FILE* f = fopen(out, "wb");
