@@ -121,3 +121,22 @@ BC_CASES = {
     "bc_tiny":  (["-m", "12", "-s", "20k", "-C"], ["multi.fa"],
                  ["-m", "12", "-s", "300k", "-C", "-L", "2"], ["multi.fa", "multi2.fa"]),
 }
+
+# Corners found by scripts/fuzz_oracle.py (differential fuzz of the restatement against the reference):
+# tables that start with a few slots keep their CLIPPED reprobe limit through every doubling
+# (hash_counter.hpp:205-209 passes ary_->max_reprobe()); counts beyond 2^val_len occupy continuation
+# slots that count towards fullness; with a limit of 1 the dumper's heap cannot reorder equal positions;
+# a direct-indexed table (size = 4^k) grows val_len only when a continuation entry finds no slot.
+# The restatement reproduces all of these (reference run with -t 1); the device engine does not yet
+# (DESIGN.md section 7a), so these stay out of CASES.
+EDGE_CASES = {
+    "edge_s100_k48":   (["-m", "48", "-s", "100", "-C"], ["multi.fa"]),
+    "edge_s10_k54":    (["-m", "54", "-s", "10"], ["multi2.fa"]),
+    "edge_s2_ties":    (["-m", "25", "-s", "2", "-C"], ["dangling.fa", "cr_mid.fa", "one_read.fq"]),
+    "edge_s2_k31_p62": (["-m", "31", "-s", "2", "-C", "-p", "62"], ["multi2.fa"]),
+    "edge_direct_sparse": (["-m", "4", "-s", "100k", "-C"], ["polya.fa", "dangling.fa"]),
+    "edge_c1_p2":      (["-m", "17", "-s", "10", "-C", "-c", "1", "-p", "2"], ["repeat.fa", "multi2.fa"]),
+    "edge_k5_s10_c1":  (["-m", "5", "-s", "10", "-c", "1"], ["multi.fa", "polya.fa"]),
+    "edge_k5_s2_p10":  (["-m", "5", "-s", "2", "-C", "-p", "10"], ["repeat.fa", "polya.fa"]),
+    "edge_rep_c2":     (["-m", "21", "-s", "2k", "-C", "-c", "2"], ["repeat.fa", "polya.fa", "multi2.fa"]),
+}

@@ -10,7 +10,7 @@ import random
 import pytest
 
 import jfutil
-from cases import BIG_CASES, CASES
+from cases import BIG_CASES, CASES, EDGE_CASES
 
 pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
@@ -340,6 +340,23 @@ def test_cli_count_matches_reference_golden_large_table(name, built, workdir, in
     random_bits() overlaps its draws (lib/misc.cc:66-72); header and body against the reference's golden."""
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_big.json")))
     args, ins = BIG_CASES[name]
+    db = os.path.join(workdir, "gpu_%s.jf" % name)
+    jfutil.run([jfutil.OUR_JF, "count"] + list(args) + ["-o", db] + [inputs[i] for i in ins], timeout=600)
+    h, b = jfutil.split_db(db)
+    g = golden[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"]
+    assert jfutil.md5(b) == g["body_md5"]
+
+
+@pytest.mark.skip(reason="known divergences in tables grown from a few slots (DESIGN.md section 7a): the engine recomputes the "
+                         "reprobe limit after a doubling, keeps counter carries out of the slots and sorts the dump strictly. "
+                         "Found by the differential fuzzer after the last GPU run of round 1; tables this small were never run on "
+                         "a device, so the cases are not even attempted until the engine side is written and checked (round 2)")
+@pytest.mark.parametrize("name", sorted(EDGE_CASES))
+def test_cli_count_corner_cases_against_reference_golden(name, built, workdir, inputs):
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_edge.json")))
+    args, ins = EDGE_CASES[name]
     h, b = _count_cli(workdir, inputs, name, args, ins)
     g = golden[name]
     assert jfutil.semantic(h) == g["header"]
