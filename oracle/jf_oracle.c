@@ -572,9 +572,14 @@ static void sim_op(sim_t* T, u128 key, uint64_t v, int op) {
     int rc = sim_try(T, key, v, op, &rem);
     if(rc != 0) return;
     if(guard > 200) { fprintf(stderr, "Hash full\n"); exit(1); }
+    /* hash_counter::update_add (hash_counter.hpp:155-165) takes "carry_shift == v" for "key not
+     * present" and gives up: a retried remainder that fails again with the same remainder (one
+     * carry unit that still finds no continuation slot after the growth) is dropped -- the
+     * reference loses those occurrences, and so does this model */
+    if(op == SIM_UPDATE && rem == v) return;
     sim_grow(T);
     if(op == SIM_SET) continue;
-    v = rem; op = SIM_ADD;                                   /* hash_counter::add retries with carry_shift */
+    v = rem;                                                 /* hash_counter::add / update_add retry with carry_shift */
     if(v == 0) return;
   }
 }

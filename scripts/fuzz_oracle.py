@@ -42,10 +42,14 @@ def rand_fasta(path):
 
 def rand_fastq(path):
     out = []
+    wrap = rng.choice([0, 0, 0, 50])        # multi-line records now and then
     for i in range(rng.randrange(1, 40)):
         n = rng.choice([1, 30, 76, 150, 400])
         s = rand_seq(n, rng.choice(["ACGT", "ACGTN", "ACGTacgt"]))
-        q = "".join(chr(rng.randrange(33, 75)) for _ in range(n))
+        q = "".join(chr(rng.randrange(33, 75)) if rng.random() < 0.1 else rng.choice("FGHIJ") for _ in range(n))
+        if wrap:
+            s = "\n".join(s[j:j + wrap] for j in range(0, n, wrap))
+            q = "\n".join(q[j:j + wrap] for j in range(0, n, wrap))
         out.append("@r%d\n%s\n+%s\n%s\n" % (i, s, rng.choice(["", "r%d" % i]), q))
     open(path, "w").write("".join(out))
 
@@ -54,9 +58,10 @@ bad = 0
 with tempfile.TemporaryDirectory() as d:
     for it in range(n_iter):
         files = []
-        for j in range(rng.randrange(1, 4)):
+        kinds = sorted(rng.random() < 0.3 for _ in range(rng.randrange(1, 4)))   # FASTA files first (see -Q note in tests/cases.py)
+        for j, fq in enumerate(kinds):
             p = os.path.join(d, "in%d_%d" % (it, j))
-            (rand_fastq if rng.random() < 0.25 else rand_fasta)(p)
+            (rand_fastq if fq else rand_fasta)(p)
             files.append(p)
         k = rng.choice([1, 2, 3, 4, 5, 8, 11, 12, 15, 16, 17, 21, 25, 31, 32, 33, 40, 48, 63, 64, rng.randrange(1, 65)])
         size = rng.choice(["1", "2", "10", "100", "1k", "5k", "64k", "100k", "1M", str(rng.randrange(1, 300000))])
@@ -75,6 +80,23 @@ with tempfile.TemporaryDirectory() as d:
             args += ["-U", str(rng.choice([1, 3, 100]))]
         if rng.random() < 0.1:
             args.append("--text")
+        if rng.random() < 0.15:
+            args += ["--if", rng.choice(files)]
+        if rng.random() < 0.15:
+            args += rng.choice([["-Q", rng.choice("#5AF")], ["--min-quality", str(rng.randrange(0, 9)), "--quality-start", "33"]])
+        u = rng.random()
+        if u < 0.1:
+            args += ["--bf-size", rng.choice(["100", "5k", "100k"]), "--bf-fp", rng.choice(["0.01", "0.2", "0.001"])]
+        elif u < 0.2:
+            bc = os.path.join(d, "f.bc")
+            bargs = ["-m", str(k), "-s", rng.choice(["100", "5k", "100k"]), "-f", rng.choice(["0.001", "0.05", "0.3"])] + (["-C"] if "-C" in args else [])
+            r1 = subprocess.run([jfutil.REF_JF, "bc", "-t", "2"] + bargs + ["-o", bc] + files[:2], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            r2 = subprocess.run([jfutil.ORACLE_C, "bc"] + bargs + ["-o", bc + ".o"] + files[:2], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            if r1.returncode == 0 and r2.returncode == 0:
+                if jfutil.split_db(bc)[1] != jfutil.split_db(bc + ".o")[1]:
+                    bad += 1
+                    print("MISMATCH #%d: bc files differ: bc %s %s" % (it, " ".join(bargs), " ".join(files[:2])))
+                args += ["--bc", bc]
         r_db, o_db = os.path.join(d, "r.jf"), os.path.join(d, "o.jf")
         for f in (r_db, o_db):
             if os.path.exists(f):
