@@ -14,6 +14,7 @@
 #include "../../include/jfgpu.h"
 #include "host/jf_matrix.hpp"
 #include "jf_kernels.cuh"
+#include "jf_window.cuh"
 
 using namespace jfk;
 
@@ -74,6 +75,9 @@ struct PartState {
   uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0, margin = 0;
   DevBuf pool, dir, order, pool_next, cta_chunk, cta_fill, spill_keys, spill_counts, spill_n, hist, start, cursor, unit_cursor;
   uint64_t spill_cap = 0;
+  // experimental window form of K2 (jf_window.cuh), JFGPU_K2_WINDOW only
+  DevBuf w_start, w_cursor, w_rec, w_def_pos, w_def_high, w_def_n;
+  uint64_t w_rec_cap = 0, w_def_cap = 0;
   uint64_t bound_chunks = 0;     // host-side upper bound of chunks in use
   bool pending = false;          // records sit in the pool
 };
@@ -327,11 +331,106 @@ void part_release(jfgpu_engine* e) {
   PartState& ps = e->part;
   ps.pool.free(); ps.dir.free(); ps.order.free(); ps.pool_next.free(); ps.cta_chunk.free(); ps.cta_fill.free();
   ps.spill_keys.free(); ps.spill_counts.free(); ps.spill_n.free(); ps.hist.free(); ps.start.free(); ps.cursor.free(); ps.unit_cursor.free();
+  ps.w_start.free(); ps.w_cursor.free(); ps.w_rec.free(); ps.w_def_pos.free(); ps.w_def_high.free(); ps.w_def_n.free();
+  ps.w_rec_cap = ps.w_def_cap = 0;
   ps.n_chunks = 0; ps.pending = false;
 }
 
 int regrow(jfgpu_engine* e);
 int read_stats(jfgpu_engine* e);
+
+// EXPERIMENTAL (JFGPU_K2_WINDOW, never run on a device yet): the window form of K2, jf_window.cuh.
+// Processes whole regions in groups, starting at unit `*done` (which must be the first unit of a
+// region), until every unit is inserted or -- with regrow enabled -- a group has reported keys that
+// found no slot.  Regions too large for the group buffer are left to the L2 kernel.
+static bool window_enabled(jfgpu_engine* e, const PartDev& pd) {
+  static const bool on = getenv("JFGPU_K2_WINDOW") != nullptr;
+  return on && e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && pd.region_bits > WIN_LG &&
+         pd.region_bits - WIN_LG <= 11 && CHUNK_BYTES == WIN_NTH * 16;
+}
+int read_stats(jfgpu_engine* e);
+static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, unsigned n_units, bool careful, unsigned group_units,
+                        unsigned* done, bool* failed) {
+  PartState& ps = e->part;
+  *failed = false;
+  const uint32_t wpr_lg = pd.region_bits - WIN_LG;
+  if(!ps.w_rec.p) {
+    ps.w_rec_cap = (uint64_t)64 << 20;                       // records per group (256 MB)
+    ps.w_def_cap = (uint64_t)16 << 20;
+    bool ok = ps.w_rec.alloc(ps.w_rec_cap * 4) == cudaSuccess && ps.w_start.alloc((((size_t)WIN_MAX_G << 11) + 1) * 4) == cudaSuccess &&
+              ps.w_cursor.alloc(((size_t)WIN_MAX_G << 11) * 4) == cudaSuccess && ps.w_def_pos.alloc(ps.w_def_cap * 8) == cudaSuccess &&
+              ps.w_def_high.alloc(ps.w_def_cap * 4) == cudaSuccess && ps.w_def_n.alloc(8) == cudaSuccess;
+    if(!ok) { cudaGetLastError(); return fail(e, JFGPU_ERR_NOMEM, "device allocation of the window buffers failed"); }
+    CUDA_OK(e, cudaMemsetAsync(ps.w_def_n.p, 0, 8, st));
+  }
+  // first unit of every region (chunk_scan_kernel wrote it), on the host
+  std::vector<uint32_t> start(pd.P + 1);
+  CUDA_OK(e, cudaMemcpyAsync(start.data(), ps.start.p, (size_t)pd.P * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(e, cudaStreamSynchronize(st));
+  start[pd.P] = n_units;
+  for(uint32_t r = 0; r < pd.P; ++r) start[r] = std::min(start[r], n_units);
+  uint32_t r0 = 0;
+  while(r0 < pd.P && start[r0] < *done) ++r0;
+  const size_t scatter_smem = ((size_t)4 * ((size_t)1 << wpr_lg) + (size_t)WIN_TILE_UNITS * pd.chunk_recs) * 4;
+  cudaFuncSetAttribute(win_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
+  const size_t insert_smem = (size_t)WIN_SLOTS * 4;
+  const uint64_t max_units = std::min<uint64_t>(ps.w_rec_cap / pd.chunk_recs, careful ? group_units : 0xFFFFFFFFu);
+  while(r0 < pd.P && *done < n_units) {
+    WinDev wd;
+    memset(&wd, 0, sizeof(wd));
+    uint32_t G = 0, tiles = 0;
+    while(r0 + G < pd.P && G < WIN_MAX_G) {
+      const uint32_t nu = start[r0 + G + 1] - start[r0 + G];
+      if((uint64_t)(start[r0 + G + 1] - start[r0]) > max_units) break;
+      wd.tile_first[G] = tiles; wd.unit_first[G] = start[r0 + G];
+      tiles += (nu + WIN_TILE_UNITS - 1) / WIN_TILE_UNITS;
+      ++G;
+    }
+    TableDev T = table_dev(e, e->tab);
+    if(G == 0) {
+      // a single region holds more records than the group buffer (heavily repeated k-mers): L2 kernel for it
+      const unsigned upto = start[r0 + 1];
+      cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st);
+      if(e->kw == 1) insert_chunks32_kernel<1><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), *done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
+      else           insert_chunks32_kernel<2><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), *done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
+      JF_LAUNCHED();
+      *done = upto; r0 += 1;
+    } else {
+      wd.tile_first[G] = tiles; wd.unit_first[G] = start[r0 + G];
+      wd.g0 = r0; wd.G = G; wd.wpr_lg = wpr_lg; wd.n_tiles = tiles;
+      wd.wstart = ps.w_start.as<uint32_t>(); wd.wcursor = ps.w_cursor.as<uint32_t>();
+      wd.wrec = ps.w_rec.as<uint32_t>(); wd.wrec_cap = ps.w_rec_cap;
+      wd.def_pos = ps.w_def_pos.as<uint64_t>(); wd.def_high = ps.w_def_high.as<uint32_t>();
+      wd.def_n = ps.w_def_n.as<unsigned long long>(); wd.def_cap = ps.w_def_cap;
+      const uint32_t hb = e->tab.fbits - e->tab.rbits;
+      if(tiles) {
+        CUDA_OK(e, cudaMemsetAsync(ps.w_cursor.p, 0, ((size_t)G << wpr_lg) * 4, st));
+        win_hist_kernel<<<tiles, WIN_NTH, 0, st>>>(pd, wd, ps.order.as<uint32_t>(), hb); JF_LAUNCHED();
+        win_scan_kernel<<<1, 1024, 0, st>>>(wd, T.stats); JF_LAUNCHED();
+        win_scatter_kernel<<<tiles, WIN_NTH, scatter_smem, st>>>(pd, wd, ps.order.as<uint32_t>(), hb); JF_LAUNCHED();
+        if(e->kw == 1) {
+          cudaFuncSetAttribute(win_insert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)insert_smem);
+          win_insert_kernel<1><<<e->n_sm * 3, WIN_NTH, insert_smem, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
+          win_deferred_kernel<1><<<e->n_sm * 2, 256, 0, st>>>(T, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
+        } else {
+          cudaFuncSetAttribute(win_insert_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)insert_smem);
+          win_insert_kernel<2><<<e->n_sm * 3, WIN_NTH, insert_smem, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
+          win_deferred_kernel<2><<<e->n_sm * 2, 256, 0, st>>>(T, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
+        }
+        CUDA_OK(e, cudaMemsetAsync(ps.w_def_n.p, 0, 8, st));
+      }
+      *done = start[r0 + G]; r0 += G;
+    }
+    if(careful) {
+      if(st != e->cs) cudaStreamSynchronize(st);
+      int rc = read_stats(e);
+      if(rc) return rc;
+      if(e->h_stats[STAT_FAILED]) { *failed = true; return JFGPU_OK; }
+    }
+  }
+  CUDA_OK(e, cudaGetLastError());
+  return JFGPU_OK;
+}
 
 // Insert everything that sits in the record pool (K1b), region by region, then the spill list.
 // With regrow enabled the chunks go in groups small enough for the failure list, and the
@@ -364,6 +463,25 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   DevBuf old_inv;     // inverse tables of the geometry the records belong to, once the table has been rebuilt
   unsigned done = 0;
   bool rebuilt = false;
+  if(window_enabled(e, pd)) {
+    if(!careful) {
+      CUDA_OK(e, cudaMemcpyAsync(&n_units, ps.pool_next.p, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(e, cudaStreamSynchronize(st));
+      n_units = std::min(n_units, ps.n_chunks);
+    }
+    bool w_failed = false;
+    rc = window_drain(e, st, pd, n_units, careful, group, &done, &w_failed);
+    if(!rc && w_failed) {        // same as below: keep the old inverse tables, rebuild, the rest goes through the rehash kernel
+      if(old_inv.alloc(e->tab.inv_lut.bytes) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "device allocation failed"); }
+      else {
+        cudaMemcpyAsync(old_inv.p, e->tab.inv_lut.p, e->tab.inv_lut.bytes, cudaMemcpyDeviceToDevice, e->cs);
+        cudaStreamSynchronize(e->cs);
+        rebuilt = true;
+        rc = regrow(e);
+      }
+    }
+  }
+  if(!rc && !(window_enabled(e, pd) && done >= n_units && !rebuilt))
   do {
     const unsigned upto = careful ? (unsigned)std::min<uint64_t>((uint64_t)done + group, n_units) : 0xFFFFFFFFu;
     cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st);
