@@ -91,6 +91,9 @@ QUAL_CASES = {
 # materialise the table. Kept apart from CASES: the device table is 8 GB.
 BIG_CASES = {
     "big_l31": (["-m", "21", "-s", "2G", "-C"], ["plain.fa"]),
+    # the bench's own table geometry (BASELINE configs[1] after its two doublings): 2^34 slots, a 34-row
+    # matrix; the reference needs 50 GB and 7 min for it, the device table is 68.7 GB of 32-bit slots
+    "big_l34": (["-m", "21", "-s", "16G", "-C"], ["plain.fa"]),
 }
 
 # --bf-size / --bf-fp: one-pass Bloom prefilter (count_main.cc:317-321, bloom_filter.hpp:40-63).
