@@ -94,6 +94,10 @@ BIG_CASES = {
     # the bench's own table geometry (BASELINE configs[1] after its two doublings): 2^34 slots, a 34-row
     # matrix; the reference needs 50 GB and 7 min for it, the device table is 68.7 GB of 32-bit slots
     "big_l34": (["-m", "21", "-s", "16G", "-C"], ["plain.fa"]),
+    # BASELINE configs[4] geometry: k=63 (two key words, 128-bit device slots), 2^31 slots
+    "big_k63_l31": (["-m", "63", "-s", "2G", "-C"], ["plain.fa"]),
+    # k=31 with a 2^33-slot table (64-bit device slots; the largest k=31 table the reference fits in this container's RAM)
+    "big_k31_l33": (["-m", "31", "-s", "8G", "-C"], ["plain.fa"]),
 }
 
 # --bf-size / --bf-fp: one-pass Bloom prefilter (count_main.cc:317-321, bloom_filter.hpp:40-63).
