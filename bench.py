@@ -160,7 +160,7 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     have_ref = os.path.exists(jfutil.REF_JF)
     if not have_ref:
-        sample = min(sample, 20_000_000)
+        sample = min(sample, 5_000_000)
     size = 1 << max(10, (int(sample / 0.6) - 1).bit_length())   # final load ~0.3-0.6, no doubling
     with tempfile.TemporaryDirectory() as d:
         fa = os.path.join(d, "sample.fa")
@@ -384,7 +384,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import jfutil
-        sample = args.cpu_sample_bases if os.path.exists(jfutil.REF_JF) else 20_000_000
+        sample = args.cpu_sample_bases if os.path.exists(jfutil.REF_JF) else 5_000_000
         csize = 1 << max(10, (int(sample / 0.6) - 1).bit_length())
         with tempfile.TemporaryDirectory() as d:
             fa = os.path.join(d, "sample.fa")

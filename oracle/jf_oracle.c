@@ -25,6 +25,7 @@
 #include <string.h>
 #include <time.h>
 #include <math.h>
+#include <sys/mman.h>
 
 typedef unsigned __int128 u128;
 
@@ -434,9 +435,21 @@ static uint64_t reprobe_off(unsigned i) { return i == 0 ? 1 : (uint64_t)i * (i +
  *    this add is ignored, as in the reference); then the failed operation is retried with the
  *    remaining value.
  * Slots are kept in a sparse map so that a 2^31-slot table costs memory only for what it holds. */
+/* zeroed memory for the slot map: anonymous mmap with transparent huge pages requested (random
+ * first touches of 4 KB pages are what this program would otherwise spend its time on) */
+static void* big_zalloc(size_t bytes) {
+  bytes = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+  void* p = mmap(0, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if(p == MAP_FAILED) { perror("mmap"); exit(1); }
+#ifdef MADV_HUGEPAGE
+  madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+static void big_free(void* p, size_t bytes) { if(p) munmap(p, (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1)); }
 enum { SLOT_EMPTY = 0, SLOT_KEY = 1, SLOT_LARGE = 2 };
 enum { SIM_ADD, SIM_SET, SIM_UPDATE };
-typedef struct { uint64_t id; u128 key; uint64_t val; unsigned char state; unsigned short r; } slot_t;
+typedef struct { u128 key; uint64_t val; uint64_t id : 48, r : 12, state : 4; } slot_t;   /* 32 bytes: memory touched is what this program costs */
 typedef struct {
   slot_t* a; size_t cap, n;
   unsigned lsize, kbits, limit, val_len, lval_len; uint64_t mask; matrix_t M;
@@ -449,16 +462,15 @@ static slot_t* sim_get(const sim_t* T, uint64_t id) {
   }
 }
 static slot_t* sim_put(sim_t* T, uint64_t id) {
-  if((T->n + 1) * 2 > T->cap) {
+  if((T->n + 1) * 10 > T->cap * 7) {
     slot_t* old = T->a; size_t ocap = T->cap;
-    T->cap *= 2; T->a = calloc(T->cap, sizeof(slot_t));
-    if(!T->a) { perror("calloc"); exit(1); }
+    T->cap *= 2; T->a = big_zalloc(T->cap * sizeof(slot_t));
     for(size_t i = 0; i < ocap; ++i) if(old[i].state != SLOT_EMPTY) {
       size_t h = sim_home(T, old[i].id);
       while(T->a[h].state != SLOT_EMPTY) h = (h + 1) & (T->cap - 1);
       T->a[h] = old[i];
     }
-    free(old);
+    big_free(old, ocap * sizeof(slot_t));
   }
   size_t h = sim_home(T, id);
   while(T->a[h].state != SLOT_EMPTY) h = (h + 1) & (T->cap - 1);
@@ -477,7 +489,7 @@ static void sim_geometry(sim_t* T, unsigned lsize, unsigned limit_in) {
 }
 static void sim_init(sim_t* T, unsigned lsize, unsigned kbits, unsigned val_len, unsigned reprobes, const matrix_t* M) {
   memset(T, 0, sizeof(*T));
-  T->cap = 1 << 16; T->a = calloc(T->cap, sizeof(slot_t));
+  T->cap = 1 << 16; T->a = big_zalloc(T->cap * sizeof(slot_t));
   T->kbits = kbits; T->val_len = val_len; T->M = *M;
   sim_geometry(T, lsize, reprobes);
 }
@@ -496,7 +508,7 @@ static int sim_try(sim_t* T, u128 key, uint64_t v, int op, uint64_t* rem) {
     s = sim_get(T, cid);
     if(!s) {
       if(op == SIM_UPDATE) return -1;
-      s = sim_put(T, cid); s->state = SLOT_KEY; s->key = key; s->r = (unsigned short)r; s->val = 0;
+      s = sim_put(T, cid); s->state = SLOT_KEY; s->key = key; s->r = r; s->val = 0;
       break;
     }
     if(s->state == SLOT_KEY && s->key == key) break;
@@ -511,7 +523,7 @@ static int sim_try(sim_t* T, u128 key, uint64_t v, int op, uint64_t* rem) {
     uint64_t c = start; r = 0;
     for(;;) {
       s = sim_get(T, c);                                     /* (sim_put may move entries: re-fetched each time) */
-      if(!s) { s = sim_put(T, c); s->state = SLOT_LARGE; s->r = (unsigned short)r; s->val = 0; break; }
+      if(!s) { s = sim_put(T, c); s->state = SLOT_LARGE; s->r = r; s->val = 0; break; }
       if(s->state == SLOT_LARGE && s->r == r) break;
       if(++r > T->limit) { *rem = stored >= 64 ? 0 : carry << stored; return 0; }
       c = (start + reprobe_off(r)) & T->mask;
@@ -545,8 +557,7 @@ static int cmp_slot_id(const void* a, const void* b) { const slot_t* x = a; cons
 static void mat_draw(unsigned r, unsigned c, matrix_t* out);
 static void sim_grow(sim_t* T) {                             /* hash_counter.hpp:200-238 */
   sim_t N = *T;
-  N.cap = T->cap; N.a = calloc(N.cap, sizeof(slot_t)); N.n = 0;
-  if(!N.a) { perror("calloc"); exit(1); }
+  N.cap = T->cap; N.a = big_zalloc(N.cap * sizeof(slot_t)); N.n = 0;
   const int can_double = T->kbits >= 64 || T->lsize < T->kbits;
   unsigned nl = T->lsize;
   if(can_double) ++nl; else ++N.val_len;
@@ -563,7 +574,7 @@ static void sim_grow(sim_t* T) {                             /* hash_counter.hpp
     if(v == 0) sim_try(&N, keys[i].key, 0, SIM_ADD, &rem);   /* add(key, 0): the key is claimed, nothing to add */
     else sim_try(&N, keys[i].key, v, SIM_ADD, &rem);         /* a failure here is ignored by the reference too */
   }
-  free(keys); free(T->a);
+  free(keys); big_free(T->a, T->cap * sizeof(slot_t));
   *T = N;
 }
 static void sim_op(sim_t* T, u128 key, uint64_t v, int op) {
@@ -721,7 +732,8 @@ int main(int argc, char** argv) {
   uint64_t key_space = kbits >= 64 ? ~0ULL / 2 : (1ULL << kbits);
   unsigned lsize = ceil_log2(size < key_space ? size : key_space);
   matrix_t M;
-  if(lsize == 0) { fprintf(stderr, "Invalid matrix size\n"); return 134; }   /* RectangularBinaryMatrix(0, c) throws: the reference aborts */
+  if(lsize == 0) { fprintf(stderr, "Invalid matrix size\n"); return 134; }
+  if(lsize > 47) { fprintf(stderr, "jf_oracle: tables of more than 2^47 slots are not modelled\n"); return 1; }   /* RectangularBinaryMatrix(0, c) throws: the reference aborts */
   if(size < key_space) mat_draw(lsize, kbits, &M); else { M.identity = 1; M.r = M.c = kbits; }
 
   /* The table is simulated slot by slot in input order (= a reference run with -t 1): see sim_*
