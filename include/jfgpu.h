@@ -74,7 +74,11 @@ typedef struct {
   uint32_t no_partition;   /* 1: always insert straight into the table (random HBM access) */
   uint32_t part_min_mb;    /* tables of at least this many MB are filled region by region
                               (0 = default 256); tests use 1 to exercise that path on small tables */
-  uint64_t reserved[4];
+  uint32_t k2_mode;        /* how the staged records reach the table (K2): 0 = default (shared-memory window
+                              insert where the geometry allows it, else the L2 kernels), 1 = L2 kernels only,
+                              2 = the generic L2 kernel only (no 32-bit specialisation); for tests/benchmarks */
+  uint32_t region_mb;      /* target size of a table region of the region-by-region insertion (0 = default 32) */
+  uint64_t reserved[3];
 } jfgpu_params;
 
 /* What file_header::update_from_ary records (file_header.hpp:26-33). */

@@ -30,7 +30,8 @@ class Params(C.Structure):
         ("allow_regrow", C.c_uint32), ("device", C.c_int32), ("shard_index", C.c_uint32),
         ("n_shards", C.c_uint32), ("matrix_skip", C.c_uint32), ("bf_size", C.c_uint64),
         ("bf_fp", C.c_double), ("max_batch_bytes", C.c_uint64), ("pool_bytes", C.c_uint64),
-        ("no_partition", C.c_uint32), ("part_min_mb", C.c_uint32), ("reserved", C.c_uint64 * 4),
+        ("no_partition", C.c_uint32), ("part_min_mb", C.c_uint32), ("k2_mode", C.c_uint32), ("region_mb", C.c_uint32),
+        ("reserved", C.c_uint64 * 3),
     ]
 
 

@@ -14,6 +14,7 @@
 #include "../../include/jfgpu.h"
 #include "host/jf_matrix.hpp"
 #include "jf_kernels.cuh"
+#include "jf_extract.cuh"
 #include "jf_window.cuh"
 
 using namespace jfk;
@@ -151,14 +152,16 @@ TableDev table_dev(const jfgpu_engine* e, const Table& t) {
 }
 
 // Geometry of a table of 2^lsize GLOBAL slots -- large_hash_array.hpp:150-173,29-39.
-int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix& M) {
+// `reprobe_limit` is -p for the first table and the CLIPPED limit of the previous table after a doubling: the reference
+// hands ary_->max_reprobe() to the new array (hash_counter.hpp:205-209), so a limit clipped by a tiny table never grows back.
+int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix& M, unsigned reprobe_limit) {
   const unsigned kbits = 2 * e->k;
   t.lsize = lsize;
   t.size = (uint64_t)1 << lsize;
   t.local_lsize = lsize - e->shard_bits;
   t.local_size = (uint64_t)1 << t.local_lsize;
   t.hb = kbits > lsize ? kbits - lsize : 0;
-  unsigned limit = kbits > lsize ? e->p.max_reprobe : 0;
+  unsigned limit = kbits > lsize ? reprobe_limit : 0;
   // reprobes[0] = 1, reprobes[i] = i(i+1)/2 (lib/storage.cc:13-41); clip so that reprobes[limit] < size
   auto rp = [](unsigned i) -> uint64_t { return i == 0 ? 1 : tri(i); };
   while(limit >= 1 && rp(limit) >= t.size) --limit;
@@ -244,7 +247,7 @@ int dispatch(jfgpu_engine* e, unsigned kw, unsigned sb, F&& f) {
 
 template<int NTH>
 size_t count_smem_bytes(size_t lut_bytes, size_t stage_bytes) {
-  return ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + (stage_bytes ? PMAX * 4 + stage_bytes : 0);
+  return ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + (stage_bytes ? PMAX * 4 + stage_bytes : 0);
 }
 
 int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
@@ -282,7 +285,7 @@ void part_configure(jfgpu_engine* e) {
   ps.P = 0;
   if(e->p.no_partition || t.bytes() < ((size_t)(e->p.part_min_mb ? e->p.part_min_mb : 256) << 20)) return;       // small tables live in L2 anyway
   uint32_t P = 256;
-  const size_t region_target = (size_t)(getenv("JFGPU_REGION_MB") ? atoi(getenv("JFGPU_REGION_MB")) : 32) << 20;
+  const size_t region_target = (size_t)(e->p.region_mb ? e->p.region_mb : 32) << 20;
   while(P < (uint32_t)PMAX && (t.bytes() / P) > region_target) P <<= 1;
   for(;; P >>= 1) {
     if(P < 64 || t.local_lsize < 8 || (1u << (t.local_lsize - 8)) < P) return;
@@ -290,8 +293,8 @@ void part_configure(jfgpu_engine* e) {
     const uint32_t bits = region_bits + t.hb;
     const uint32_t rec = bits <= 32 ? 4 : bits <= 64 ? 8 : bits <= 128 ? 16 : 0;
     if(!rec) return;
-    // records arriving per region between two roll-over passes: 1024 threads x QSYM symbols / P
-    const double mean = 2.0 * 1024.0 * QSYM / P;              // (roll-over runs every second iteration)
+    // records arriving per region between two roll-over passes (one per window): 1024 threads x 32 symbols / P
+    const double mean = 1024.0 * 32 / P;
     const uint32_t margin = (uint32_t)(mean + 6.0 * sqrt(mean) + 8.0);
     if(margin * 2 > CHUNK_BYTES / rec) return;               // chunks would be closed half empty: insert directly
     ps.P = P; ps.region_bits = region_bits; ps.rec_bytes = rec; ps.cap = 0; ps.flush_min = 0; ps.margin = margin;
@@ -344,8 +347,7 @@ int read_stats(jfgpu_engine* e);
 // region), until every unit is inserted or -- with regrow enabled -- a group has reported keys that
 // found no slot.  Regions too large for the group buffer are left to the L2 kernel.
 static bool window_enabled(jfgpu_engine* e, const PartDev& pd) {
-  static const bool on = getenv("JFGPU_K2_WINDOW") != nullptr;
-  return on && e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && pd.region_bits > WIN_LG &&
+  return e->p.k2_mode == 0 && e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && pd.region_bits > WIN_LG &&
          pd.region_bits - WIN_LG <= 11 && CHUNK_BYTES == WIN_NTH * 16;
 }
 int read_stats(jfgpu_engine* e);
@@ -487,7 +489,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st);
     TableDev T = table_dev(e, e->tab);
     if(!rebuilt) {
-      if(e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && !getenv("JFGPU_K2_GENERIC")) {
+      if(e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && e->p.k2_mode != 2) {
         // lean 32-bit specialisation: 2 CTAs x 1024 threads per SM
         if(e->kw == 1) insert_chunks32_kernel<1><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
         else           insert_chunks32_kernel<2><<<e->n_sm * 2, 768, 0, st>>>(T, pd, ps.order.as<uint32_t>(), ps.unit_cursor.as<unsigned int>(), done, upto, e->tab.inv_lut.as<uint64_t>(), e->nbytes);
@@ -618,9 +620,9 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   };
   rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
     constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
-    if(part)      return launch(count_kernel<kw, sb, 2, 1024>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes), true);
-    if(mode == 1) return launch(count_kernel<kw, sb, 1, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
-    return launch(count_kernel<kw, sb, 0, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
+    if(part)      return launch(extract_kernel<kw, sb, 2, 1024>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes), true);
+    if(mode == 1) return launch(extract_kernel<kw, sb, 1, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
+    return launch(extract_kernel<kw, sb, 0, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
   });
   if(rc) return rc;
   JF_LAUNCHED();
@@ -747,7 +749,7 @@ int rebuild_table(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int ol
 }
 int rebuild_table_impl(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, int old_fail, uint64_t n_failed) {
   Table nt;
-  int rc = table_setup(e, nt, nl, M);
+  int rc = table_setup(e, nt, nl, M, e->tab.max_reprobe);
   if(rc) { nt.release(); return rc == JFGPU_ERR_NOMEM ? fail(e, JFGPU_ERR_FULL, "Hash full (" + e->err + ")") : rc; }
   // distinct / reprobes statistics restart for the new table; STAT_INSERTED counts k-mer
   // occurrences and must not change
@@ -946,7 +948,7 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   if(!ok) { cudaGetLastError(); e->err = "device allocation failed"; return bail(JFGPU_ERR_NOMEM); }
   cudaMemsetAsync(e->stats.p, 0, STAT_N * 8, e->cs);
   memset(e->h_stats, 0, STAT_N * 8);
-  int rc = table_setup(e, e->tab, lsize, M);
+  int rc = table_setup(e, e->tab, lsize, M, params->max_reprobe);
   if(rc) return bail(rc);
   part_configure(e);
   rc = reset_carry(e, e->cs);
@@ -1135,7 +1137,7 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
     PartDev pd = part_dev(e);
     TableDev T = table_dev(e, e->tab);
     const size_t smem = (size_t)e->nbytes * 256 * 8 + PMAX * 8;
-    const int grid = (int)std::min<uint64_t>((n + 1024ull * QSYM - 1) / (1024ull * QSYM), (uint64_t)e->n_sm);
+    const int grid = (int)std::min<uint64_t>((n + 1024ull * 32 - 1) / (1024ull * 32), (uint64_t)e->n_sm);
     if(e->kw == 1) {
       cudaFuncSetAttribute(stage_keys_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       stage_keys_kernel<1><<<grid, 1024, smem, st>>>(T, pd, e->tab.lut.as<uint64_t>(), e->nbytes, (const uint64_t*)dev_keys, n, nullptr);

@@ -860,12 +860,12 @@ __global__ void __launch_bounds__(1024, 1) stage_keys_kernel(TableDev T, PartDev
   }
   __syncthreads();
   const uint32_t hb = T.fbits - T.rbits;
-  // an iteration = QSYM keys per thread (the arrival rate the roll-over margin was sized for)
-  const uint64_t per_iter = (uint64_t)blockDim.x * QSYM;
+  // an iteration = 32 keys per thread (the arrival rate the roll-over margin was sized for)
+  const uint64_t per_iter = (uint64_t)blockDim.x * 32;
   const uint64_t iters = (n + per_iter * gridDim.x - 1) / (per_iter * gridDim.x);
   for(uint64_t it = 0; it < iters; ++it) {
     const uint64_t base_i = (it * gridDim.x + blockIdx.x) * per_iter;
-    for(uint32_t q = 0; q < (uint32_t)QSYM; ++q) {
+    for(uint32_t q = 0; q < 32u; ++q) {
       const uint64_t i = base_i + (uint64_t)q * blockDim.x + tid;       // coalesced key loads
       if(i >= n) break;
       uint64_t key[KW];

@@ -178,30 +178,45 @@ __global__ void __launch_bounds__(WIN_NTH) win_insert_kernel(TableDev T, PartDev
     uint4* sw = reinterpret_cast<uint4*>(win);
     for(uint32_t i = threadIdx.x; i < WIN_SLOTS / 4; i += WIN_NTH) sw[i] = __ldcs(gw + i);
     __syncthreads();
-    for(uint32_t i = b + threadIdx.x; i < e; i += WIN_NTH) {
-      const uint32_t rec = __ldcs(wd.wrec + i);
-      const uint32_t local = (hb < 32 ? rec >> hb : 0u) & (WIN_SLOTS - 1);
-      const uint32_t high = rec & hmask, kf0 = high << rb;
-      bool done = false;
-      for(uint32_t p = 0; p <= T.max_reprobe; ++p) {
-        const uint32_t at = local + (uint32_t)tri(p);
-        if(at >= WIN_SLOTS) {                          // leaves the window: the global path takes it after this kernel
+    // Every lane keeps one record in flight and performs ONE probe per trip of the loop; a lane whose record
+    // is settled takes the next record of its stride at once (the one after it is already on its way from
+    // memory), so lanes with long probe sequences do not idle the rest of the warp.
+    {
+      uint32_t i = b + threadIdx.x;
+      bool have = i < e;
+      uint32_t rec = have ? __ldcs(wd.wrec + i) : 0u;
+      bool have_n = have && i + WIN_NTH < e;
+      uint32_t nxt = have_n ? __ldcs(wd.wrec + i + WIN_NTH) : 0u;
+      uint32_t local = (hb < 32 ? rec >> hb : 0u) & (WIN_SLOTS - 1), high = rec & hmask, kf0 = high << rb;
+      uint32_t at = local, p = 0;
+      while(have) {
+        bool done = false;
+        if(at >= WIN_SLOTS) {                              // leaves the window: the global path takes it after this kernel
           const unsigned long long d = atomicAdd(wd.def_n, 1ull);
           if(d < wd.def_cap) { wd.def_pos[d] = slot_base + local; wd.def_high[d] = high; }
           else atomicAdd(&T.stats[STAT_POOL_FULL], 1ull);
           done = true;
-          break;
+        } else {
+          const uint32_t kf = kf0 | (p + 1);
+          const uint32_t o = atomicCAS(&win[at], 0u, kf | one);
+          if(o == 0u) { ++n_new; ++n_ins; n_rep += p; done = true; }
+          else if((o & fmask) == kf) {
+            const uint32_t o2 = atomicAdd(&win[at], one);
+            if((((o2 >> fb) + 1) >> cb) != 0) k2_carry(T.ovf_keys, T.ovf_vals, T.ovf_mask, T.stats, slot_base + at);
+            ++n_ins; n_rep += p; done = true;
+          } else if(p >= T.max_reprobe) {
+            k2_fail<KW>(T.shard_index, T.local_lsize, T.lsize, T.stats, T.fail_keys, T.fail_counts, T.fail_cap, slot_base + local, high, inv_lut_g, nbytes);
+            done = true;
+          } else { ++p; at += p; }                         // pos + i(i+1)/2
         }
-        const uint32_t kf = kf0 | (p + 1);
-        const uint32_t o = atomicCAS(&win[at], 0u, kf | one);
-        if(o == 0u) { ++n_new; ++n_ins; n_rep += p; done = true; break; }
-        if((o & fmask) == kf) {
-          const uint32_t o2 = atomicAdd(&win[at], one);
-          if((((o2 >> fb) + 1) >> cb) != 0) k2_carry(T.ovf_keys, T.ovf_vals, T.ovf_mask, T.stats, slot_base + at);
-          ++n_ins; n_rep += p; done = true; break;
+        if(done) {
+          rec = nxt; have = have_n; i += WIN_NTH;
+          have_n = have && i + WIN_NTH < e;
+          if(have_n) nxt = __ldcs(wd.wrec + i + WIN_NTH);
+          local = (hb < 32 ? rec >> hb : 0u) & (WIN_SLOTS - 1); high = rec & hmask; kf0 = high << rb;
+          at = local; p = 0;
         }
       }
-      if(!done) k2_fail<KW>(T.shard_index, T.local_lsize, T.lsize, T.stats, T.fail_keys, T.fail_counts, T.fail_cap, slot_base + local, high, inv_lut_g, nbytes);
     }
     __syncthreads();
     for(uint32_t i = threadIdx.x; i < WIN_SLOTS / 4; i += WIN_NTH) __stcs(gw + i, sw[i]);

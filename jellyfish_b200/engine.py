@@ -58,7 +58,7 @@ def canonical_int(v, k):
 class HashCounter(object):
     def __init__(self, size, val_len=7, k=None, canonical=False, reprobes=126, device=0,
                  shard_index=0, n_shards=1, allow_regrow=True, max_batch_bytes=0, matrix_skip=0,
-                 pool_bytes=0, no_partition=False, part_min_mb=0):
+                 pool_bytes=0, no_partition=False, part_min_mb=0, k2_mode=0, region_mb=0):
         if k is None:
             raise ValueError("k (mer length) is required")
         self._lib = L.load()
@@ -69,6 +69,7 @@ class HashCounter(object):
         p.canonical, p.allow_regrow, p.device = int(bool(canonical)), int(bool(allow_regrow)), device
         p.shard_index, p.n_shards, p.max_batch_bytes, p.matrix_skip = shard_index, n_shards, max_batch_bytes, matrix_skip
         p.pool_bytes, p.no_partition, p.part_min_mb = pool_bytes, int(bool(no_partition)), part_min_mb
+        p.k2_mode, p.region_mb = k2_mode, region_mb
         rc = self._lib.jfgpu_create(C.byref(p), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

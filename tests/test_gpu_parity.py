@@ -332,8 +332,6 @@ def test_if_passes_via_api(part, built, inputs):
         assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == g["header"]
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: not yet run on a device "
-                                        "(host-side matrix draw for > 30 rows is pinned on CPU in test_host.py)")
 @pytest.mark.parametrize("name", sorted(BIG_CASES))
 def test_cli_count_matches_reference_golden_large_table(name, built, workdir, inputs):
     """A table of 2^31 slots (8 GB of 32-bit slots): the matrix has 31 rows, where the reference's
@@ -349,10 +347,6 @@ def test_cli_count_matches_reference_golden_large_table(name, built, workdir, in
     assert jfutil.md5(b) == g["body_md5"]
 
 
-@pytest.mark.skip(reason="known divergences in tables grown from a few slots (DESIGN.md section 7a): the engine recomputes the "
-                         "reprobe limit after a doubling, keeps counter carries out of the slots and sorts the dump strictly. "
-                         "Found by the differential fuzzer after the last GPU run of round 1; tables this small were never run on "
-                         "a device, so the cases are not even attempted until the engine side is written and checked (round 2)")
 @pytest.mark.parametrize("name", sorted(EDGE_CASES))
 def test_cli_count_corner_cases_against_reference_golden(name, built, workdir, inputs):
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_edge.json")))
