@@ -67,7 +67,7 @@ typedef struct {
                               caller can reproduce a later point of the reference's
                               unseeded random() stream); normally 0                   */
   uint64_t bf_size;        /* --bf-size : expected number of k-mers, 0 = no filter     */
-  double   bf_fp;          /* --bf-fp                                                 */
+  double   bf_fp;          /* --bf-fp  (0 = the reference's default 0.01)              */
   uint64_t max_batch_bytes;/* device staging buffer size for jfgpu_feed (0 = default) */
   uint64_t pool_bytes;     /* HBM set aside for the k-mer record pool of the region-by-region
                               insertion (0 = 60% of the free memory, at most 64 GB)      */
@@ -78,8 +78,24 @@ typedef struct {
                               insert where the geometry allows it, else the L2 kernels), 1 = L2 kernels only,
                               2 = the generic L2 kernel only (no 32-bit specialisation); for tests/benchmarks */
   uint32_t region_mb;      /* target size of a table region of the region-by-region insertion (0 = default 32) */
-  uint64_t reserved[3];
+  uint32_t bloom_counter;  /* 1: this engine builds a Bloom counter instead of a hash table -- `jellyfish bc`
+                              (sub_commands/bc_main.cc:84-161): bf_size = expected number of k-mers (-s), bf_fp =
+                              false positive rate (-f); `size`, `counter_len`, `max_reprobe` are ignored.  Feed text as
+                              usual, then jfgpu_bloom_info_get / jfgpu_bloom_dump                                      */
+  uint32_t reserved32;
+  uint64_t reserved[2];
 } jfgpu_params;
+
+/* Description of the Bloom structure of an engine: what bc_main.cc:103-113 records in the "bloomcounter" header. */
+typedef struct {
+  uint32_t mode;           /* 0 none, 1 --bf-size prefilter, 2 Bloom counter being built, 3 loaded Bloom counter (--bc) */
+  uint32_t nb_hashes;      /* bloom_base::k()                                          */
+  uint64_t m;              /* bloom_base::m(): number of positions                     */
+  uint64_t nb_bytes;       /* bytes jfgpu_bloom_dump streams (bloom_counter2: ceil(m/5)) */
+  uint32_t matrix_r, matrix_c;     /* 64 x 2k                                          */
+  const uint64_t* matrix1; /* matrix_c columns each; owned by the engine              */
+  const uint64_t* matrix2;
+} jfgpu_bloom_info;
 
 /* What file_header::update_from_ary records (file_header.hpp:26-33). */
 typedef struct {
@@ -180,6 +196,18 @@ int  jfgpu_lookup(jfgpu_handle h, const uint64_t* keys, size_t n, uint64_t* vals
  *    the dump, sub_commands/histo_main.cc:33-45): hist[min(count,n_bins-1)]++ for every
  *    distinct k-mer of this shard.  hist: n_bins uint64 in HOST memory. */
 int  jfgpu_histogram(jfgpu_handle h, uint64_t* hist, uint32_t n_bins);
+
+/* -- Bloom structures in front of / instead of the table (count_main.cc:99-131,311-324; bc_main.cc) ---------------
+ *    jfgpu_params.bf_size != 0 (with bloom_counter == 0) puts the one-pass prefilter of `count --bf-size` in front of the
+ *    table: a k-mer reaches the table only when the filter has seen it before (bloom_filter.hpp:42-69).
+ *    jfgpu_bloom_load puts a Bloom counter written by `jellyfish bc` in front of the table (count --bc,
+ *    count_main.cc:191-206,110-120): `bytes` is the file body (five base-3 digits per byte), m / nb_hashes / the two
+ *    64 x 2k matrices come from its header.  jfgpu_bloom_dump streams the body of the counter an engine created with
+ *    bloom_counter = 1 has built (bloom_base::write_bits). */
+int  jfgpu_bloom_info_get(jfgpu_handle h, jfgpu_bloom_info* info);
+int  jfgpu_bloom_load(jfgpu_handle h, uint64_t m, uint32_t nb_hashes, const uint64_t* matrix1_cols, const uint64_t* matrix2_cols,
+                      const void* bytes, size_t nbytes);
+int  jfgpu_bloom_dump(jfgpu_handle h, jfgpu_sink_fn sink, void* ctx);
 
 /* -- helpers ------------------------------------------------------------------------ */
 /* The hash matrix the reference would draw as its (skip+1)-th matrix for a table of

@@ -17,6 +17,7 @@ SYMBOLS = [
     "jfgpu_table_info_get", "jfgpu_dump", "jfgpu_lookup", "jfgpu_histogram",
     "jfgpu_reference_matrix", "jfgpu_synth_fasta_bytes", "jfgpu_synth_fasta_device",
     "jfgpu_host_alloc", "jfgpu_host_free", "jfgpu_memcpy_h2d", "jfgpu_kernel_launches", "jfgpu_version",
+    "jfgpu_bloom_info_get", "jfgpu_bloom_load", "jfgpu_bloom_dump",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_FULL, ERR_FORMAT, ERR_STATE, ERR_NOMEM, ERR_SINK = range(8)
@@ -31,7 +32,7 @@ class Params(C.Structure):
         ("n_shards", C.c_uint32), ("matrix_skip", C.c_uint32), ("bf_size", C.c_uint64),
         ("bf_fp", C.c_double), ("max_batch_bytes", C.c_uint64), ("pool_bytes", C.c_uint64),
         ("no_partition", C.c_uint32), ("part_min_mb", C.c_uint32), ("k2_mode", C.c_uint32), ("region_mb", C.c_uint32),
-        ("reserved", C.c_uint64 * 3),
+        ("bloom_counter", C.c_uint32), ("reserved32", C.c_uint32), ("reserved", C.c_uint64 * 2),
     ]
 
 
@@ -50,6 +51,13 @@ class Stats(C.Structure):
         ("kmers", C.c_uint64), ("inserted", C.c_uint64), ("distinct", C.c_uint64), ("reprobes", C.c_uint64),
         ("overflowed", C.c_uint64), ("regrows", C.c_uint64), ("bytes", C.c_uint64), ("seconds_count", C.c_double),
         ("seconds_count_kernel", C.c_double), ("count_kernel_launches", C.c_uint64), ("seconds_drain", C.c_double),
+    ]
+
+
+class BloomInfo(C.Structure):
+    _fields_ = [
+        ("mode", C.c_uint32), ("nb_hashes", C.c_uint32), ("m", C.c_uint64), ("nb_bytes", C.c_uint64),
+        ("matrix_r", C.c_uint32), ("matrix_c", C.c_uint32), ("matrix1", C.POINTER(C.c_uint64)), ("matrix2", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -114,5 +122,11 @@ def load():
     lib.jfgpu_kernel_launches.restype = C.c_uint64
     lib.jfgpu_version.argtypes = []
     lib.jfgpu_version.restype = C.c_char_p
+    lib.jfgpu_bloom_info_get.argtypes = [H, C.POINTER(BloomInfo)]
+    lib.jfgpu_bloom_info_get.restype = C.c_int
+    lib.jfgpu_bloom_load.argtypes = [H, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.jfgpu_bloom_load.restype = C.c_int
+    lib.jfgpu_bloom_dump.argtypes = [H, SINK_FN, C.c_void_p]
+    lib.jfgpu_bloom_dump.restype = C.c_int
     _lib = lib
     return lib

@@ -8,6 +8,7 @@
 //
 // The flow of `count` mirrors count_main (sub_commands/count_main.cc:218-385): header
 // fill_standard + cmdline, build the table, stream the input files, dump, --timing.
+#include <errno.h>
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -116,7 +117,7 @@ struct db_reader {
     fd = ::open(path, O_RDONLY);
     if(fd < 0) die(std::string("Failed to open input file '") + path + "'");
     struct stat st;
-    fstat(fd, &st);
+    if(fstat(fd, &st) != 0) die(std::string("Can't stat file '") + path + "'");
     file_size = st.st_size;
     base = file_size ? (const unsigned char*)mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
     if(file_size && base == MAP_FAILED) die(std::string("Can't mmap file '") + path + "'");
@@ -160,6 +161,7 @@ struct count_args {
   uint64_t bf_size = 0, lower = 0, upper = 0;
   double bf_fp = 0.01;
   const char* timing = "";
+  const char* bc_path = nullptr;
   int device = 0;
   std::vector<const char*> files;
   std::vector<const char*> if_files;
@@ -183,6 +185,168 @@ int file_sink(void* ctx, const void* recs, size_t n) {
     line += ' '; line += std::to_string((unsigned long long)v); line += '\n';
     if(fwrite(line.data(), 1, line.size(), c->f) != line.size()) { c->ok = false; return 1; }
   }
+  return 0;
+}
+
+// ---- stream files through an engine: a reader thread fills pinned buffers, the caller's thread feeds them ----
+void stream_files(jfgpu_handle h, const std::vector<const char*>& file_list) {
+  const size_t BUF = (size_t)64 << 20;
+  struct chunk { char* data; size_t n; uint32_t flags; bool last; std::string error; };
+  const int NBUF = 3;
+  std::vector<char*> bufs(NBUF);
+  for(int i = 0; i < NBUF; ++i) { bufs[i] = (char*)jfgpu_host_alloc(BUF); if(!bufs[i]) die("pinned host allocation failed"); }
+  std::mutex mu; std::condition_variable cv;
+  std::queue<chunk> ready; std::queue<char*> freeb;
+  for(int i = 0; i < NBUF; ++i) freeb.push(bufs[i]);
+  std::thread reader([&] {
+    auto get_buf = [&]() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !freeb.empty(); }); char* b = freeb.front(); freeb.pop(); return b; };
+    auto put = [&](chunk c) { std::unique_lock<std::mutex> l(mu); ready.push(c); cv.notify_all(); };
+    for(size_t fi = 0; fi < file_list.size(); ++fi) {
+      int fd = ::open(file_list[fi], O_RDONLY);
+      if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + file_list[fi] + "'"}); return; }
+      bool first = true, eof = false;
+      char* cur = get_buf();
+      size_t have = 0;
+      // read one chunk ahead so that the last one can carry FILE_END
+      std::string io_error;
+      auto fill = [&](char* b) -> size_t {
+        size_t n = 0;
+        while(n < BUF) {
+          ssize_t r = ::read(fd, b + n, BUF - n);
+          if(r < 0 && errno == EINTR) continue;
+          if(r < 0) { io_error = std::string("Error reading file '") + file_list[fi] + "': " + strerror(errno); eof = true; break; }   // never a silent truncation
+          if(r == 0) { eof = true; break; }
+          n += r;
+        }
+        return n;
+      };
+      have = fill(cur);
+      while(true) {
+        char* nxt = nullptr; size_t nn = 0;
+        if(!eof) { nxt = get_buf(); nn = fill(nxt); }
+        if(!io_error.empty()) { ::close(fd); put(chunk{nullptr, 0, 0, true, io_error}); return; }
+        bool last_of_file = eof && nn == 0;
+        uint32_t fl = (first ? JFGPU_FILE_BEGIN : 0) | (last_of_file ? JFGPU_FILE_END : 0);
+        put(chunk{cur, have, fl, false, ""});
+        first = false;
+        if(last_of_file) { if(nxt) { std::unique_lock<std::mutex> l(mu); freeb.push(nxt); } break; }
+        cur = nxt; have = nn;
+      }
+      ::close(fd);
+    }
+    put(chunk{nullptr, 0, 0, true, ""});
+  });
+  std::string feed_error;
+  int feed_rc = 0;
+  while(true) {
+    chunk ck;
+    { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !ready.empty(); }); ck = ready.front(); ready.pop(); }
+    if(ck.last) { if(!ck.error.empty()) feed_error = ck.error; break; }
+    if(!feed_rc && feed_error.empty()) {
+      feed_rc = jfgpu_feed(h, ck.data, ck.n, ck.flags);
+      if(feed_rc) feed_error = jfgpu_last_error(h);
+    }
+    { std::unique_lock<std::mutex> l(mu); freeb.push(ck.data); cv.notify_all(); }
+  }
+  reader.join();
+  if(!feed_error.empty()) die(feed_error);
+  for(int i = 0; i < NBUF; ++i) jfgpu_host_free(bufs[i]);
+}
+
+// load_bloom_filter (sub_commands/count_main.cc:191-206): header checks, then the counter bytes go to the device
+void load_bloom_counter(jfgpu_handle h, const char* path, unsigned mer_len) {
+  int fd = ::open(path, O_RDONLY);
+  if(fd < 0) die(std::string("Failed to open bloom filter file '") + path + "'");
+  struct stat st;
+  if(fstat(fd, &st) != 0) die(std::string("Can't stat file '") + path + "'");
+  const size_t size = st.st_size;
+  const char* base = size ? (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+  if(size && base == MAP_FAILED) die(std::string("Can't mmap file '") + path + "'");
+  jfb::file_header hd;
+  if(!hd.read(base, size)) die(std::string("Failed to parse bloom filter file '") + path + "'");
+  if(hd.format() != "bloomcounter") die(std::string("Invalid format '") + hd.format() + "'. Expected 'bloomcounter'");
+  if(hd.key_len() != mer_len * 2) die("Invalid mer length in bloom filter");
+  const jfb::gf2_matrix m1 = hd.matrix(1), m2 = hd.matrix(2);
+  std::vector<uint64_t> c1(2 * mer_len), c2(2 * mer_len);
+  for(unsigned i = 0; i < 2 * mer_len; ++i) { c1[i] = m1[i]; c2[i] = m2[i]; }
+  if(jfgpu_bloom_load(h, hd.size(), (uint32_t)hd.nb_hashes(), c1.data(), c2.data(), base + hd.offset(), size - hd.offset()) != JFGPU_OK)
+    die(std::string("Bloom filter file is truncated or invalid: ") + jfgpu_last_error(h));
+  if(base) munmap((void*)base, size);
+  ::close(fd);
+}
+
+// ------------------------------------------------------------------------------------------
+// bc (sub_commands/bc_main.cc:84-161): build a Bloom counter of the k-mers of the input
+// ------------------------------------------------------------------------------------------
+int bc_main(int argc, char* argv[]) {
+  using clk = std::chrono::system_clock;
+  auto start_time = clk::now();
+  jfb::file_header header;
+  header.fill_standard();
+  header.set_cmdline(argc, argv);
+  uint32_t mer_len = 0; uint64_t size = 0; double fpr = 0.001; bool canonical = false, mer_given = false, size_given = false, timing_given = false;
+  const char* output = "mer_bloom_filter"; const char* timing = ""; int device = 0;
+  enum { O_TIMING = 1000, O_DEVICE };
+  static struct option longs[] = {
+    {"mer-len", required_argument, 0, 'm'}, {"size", required_argument, 0, 's'}, {"fpr", required_argument, 0, 'f'},
+    {"threads", required_argument, 0, 't'}, {"Files", required_argument, 0, 'F'}, {"output", required_argument, 0, 'o'},
+    {"canonical", no_argument, 0, 'C'}, {"timing", required_argument, 0, O_TIMING}, {"device", required_argument, 0, O_DEVICE}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "m:s:f:t:F:o:C", longs, 0)) != -1) switch(c) {
+    case 'm': mer_len = (uint32_t)parse_u64(optarg, false, "-m"); mer_given = true; break;
+    case 's': size = parse_u64(optarg, true, "-s"); size_given = true; break;
+    case 'f': fpr = atof(optarg); break;
+    case 't': case 'F': break;
+    case 'o': output = optarg; break;
+    case 'C': canonical = true; break;
+    case O_TIMING: timing = optarg; timing_given = true; break;
+    case O_DEVICE: device = atoi(optarg); break;
+    default: usage_error("Usage: jellyfish-b200 bc [options] file:path+");
+  }
+  std::vector<const char*> files;
+  for(int i = optind; i < argc; ++i) files.push_back(argv[i]);
+  if(!mer_given) usage_error("Missing required switch --mer-len");
+  if(!size_given) usage_error("Missing required switch --size");
+  if(mer_len < 1 || mer_len > 64) usage_error("jellyfish-b200 supports mer lengths 1..64");
+  jfgpu_params p;
+  memset(&p, 0, sizeof(p));
+  p.struct_size = sizeof(p);
+  p.k = mer_len; p.size = 1; p.counter_len = 7; p.canonical = canonical; p.device = device; p.n_shards = 1;
+  p.bloom_counter = 1; p.bf_size = size; p.bf_fp = fpr;
+  jfgpu_handle h = nullptr;
+  if(jfgpu_create(&p, &h) != JFGPU_OK) die(std::string("Failed to create the device Bloom counter: ") + jfgpu_last_error(nullptr));
+  jfgpu_bloom_info bi;
+  if(jfgpu_bloom_info_get(h, &bi) != JFGPU_OK) die(jfgpu_last_error(h));
+  header.canonical(canonical);
+  std::ofstream out(output, std::ios::binary);
+  if(!out.good()) die(std::string("Can't open output file '") + output + "'");
+  header.format("bloomcounter");
+  header.key_len(mer_len * 2);
+  header.matrix(jfb::gf2_matrix(bi.matrix_r, bi.matrix_c, bi.matrix1), 1);
+  header.matrix(jfb::gf2_matrix(bi.matrix_r, bi.matrix_c, bi.matrix2), 2);
+  header.size(bi.m);
+  header.nb_hashes(bi.nb_hashes);
+  header.write(out);
+  out.close();
+  auto after_init_time = clk::now();
+  stream_files(h, files);
+  if(jfgpu_finish(h, nullptr) != JFGPU_OK) die(jfgpu_last_error(h));
+  auto after_count_time = clk::now();
+  FILE* f = fopen(output, "ab");
+  if(!f) die(std::string("Can't open output file '") + output + "'");
+  sink_ctx sc = { f, true, false, mer_len, 0, 0 };
+  int rc = jfgpu_bloom_dump(h, file_sink, &sc);
+  fclose(f);
+  if(rc != JFGPU_OK || !sc.ok) die(std::string("Error while writing the Bloom counter: ") + jfgpu_last_error(h));
+  auto after_dump_time = clk::now();
+  if(timing_given) {
+    auto secs = [](clk::duration d) { return std::chrono::duration_cast<std::chrono::duration<double>>(d).count(); };
+    std::ofstream tf(timing);
+    tf << "Init     " << secs(after_init_time - start_time) << "\n"
+       << "Counting " << secs(after_count_time - after_init_time) << "\n"
+       << "Writing  " << secs(after_dump_time - after_count_time) << "\n";
+  }
+  jfgpu_destroy(h);
   return 0;
 }
 
@@ -224,7 +388,7 @@ int count_main(int argc, char* argv[]) {
     case 'c': a.counter_len = (uint32_t)parse_u64(optarg, false, "-c"); break;
     case O_OCL: a.out_counter_len = (uint32_t)parse_u64(optarg, false, "--out-counter-len"); break;
     case 'C': a.canonical = true; break;
-    case O_BC: a.bc_given = true; break;
+    case O_BC: a.bc_given = true; a.bc_path = optarg; break;
     case O_BFSIZE: a.bf_size = parse_u64(optarg, true, "--bf-size"); a.bf_size_given = true; break;
     case O_BFFP: a.bf_fp = atof(optarg); break;
     case O_IF: a.if_given = true; a.if_files.push_back(optarg); break;
@@ -249,7 +413,6 @@ int count_main(int argc, char* argv[]) {
   if(a.bc_given && a.bf_size_given) usage_error("Switches [--bf-size] and [--bc] conflict");
   if(a.sam_given) usage_error("SAM/BAM/CRAM not supported (missing htslib).");
   if(a.generator_given) usage_error("generators (-g) are not supported by jellyfish-b200");
-  if(a.bc_given || a.bf_size_given) usage_error("Bloom prefilters (--bc/--bf-size) are not implemented yet in jellyfish-b200");
   if(a.qual_given) usage_error("quality filtering (-Q/--min-quality) is not implemented yet in jellyfish-b200");
   if(a.disk) usage_error("--disk is not implemented in jellyfish-b200 (the table is doubled on the device instead)");
   if(a.mer_len < 1 || a.mer_len > 64) usage_error("jellyfish-b200 supports mer lengths 1..64");
@@ -260,69 +423,19 @@ int count_main(int argc, char* argv[]) {
   p.struct_size = sizeof(p);
   p.k = a.mer_len; p.size = a.size; p.counter_len = a.counter_len; p.max_reprobe = a.reprobes;
   p.canonical = a.canonical; p.allow_regrow = 1; p.device = a.device; p.shard_index = 0; p.n_shards = 1;
+  if(a.bf_size_given) { p.bf_size = a.bf_size; p.bf_fp = a.bf_fp; }       // count_main.cc:317-321
   jfgpu_handle h = nullptr;
   if(jfgpu_create(&p, &h) != JFGPU_OK) die(std::string("Failed to create the device hash: ") + jfgpu_last_error(nullptr));
   auto after_init_time = clk::now();
 
-  // ---- stream the files through the engine: a reader thread fills pinned buffers --------------
-  const size_t BUF = (size_t)64 << 20;
-  auto stream_files = [&](const std::vector<const char*>& file_list) {
-  struct chunk { char* data; size_t n; uint32_t flags; bool last; std::string error; };
-  const int NBUF = 3;
-  std::vector<char*> bufs(NBUF);
-  for(int i = 0; i < NBUF; ++i) { bufs[i] = (char*)jfgpu_host_alloc(BUF); if(!bufs[i]) die("pinned host allocation failed"); }
-  std::mutex mu; std::condition_variable cv;
-  std::queue<chunk> ready; std::queue<char*> freeb;
-  for(int i = 0; i < NBUF; ++i) freeb.push(bufs[i]);
-  std::thread reader([&] {
-    auto get_buf = [&]() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !freeb.empty(); }); char* b = freeb.front(); freeb.pop(); return b; };
-    auto put = [&](chunk c) { std::unique_lock<std::mutex> l(mu); ready.push(c); cv.notify_all(); };
-    for(size_t fi = 0; fi < file_list.size(); ++fi) {
-      int fd = ::open(file_list[fi], O_RDONLY);
-      if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + file_list[fi] + "'"}); return; }
-      bool first = true, eof = false;
-      char* cur = get_buf();
-      size_t have = 0;
-      // read one chunk ahead so that the last one can carry FILE_END
-      auto fill = [&](char* b) -> size_t { size_t n = 0; while(n < BUF) { ssize_t r = ::read(fd, b + n, BUF - n); if(r <= 0) { eof = true; break; } n += r; } return n; };
-      have = fill(cur);
-      while(true) {
-        char* nxt = nullptr; size_t nn = 0;
-        if(!eof) { nxt = get_buf(); nn = fill(nxt); }
-        bool last_of_file = eof && nn == 0;
-        uint32_t fl = (first ? JFGPU_FILE_BEGIN : 0) | (last_of_file ? JFGPU_FILE_END : 0);
-        put(chunk{cur, have, fl, false, ""});
-        first = false;
-        if(last_of_file) { if(nxt) { std::unique_lock<std::mutex> l(mu); freeb.push(nxt); } break; }
-        cur = nxt; have = nn;
-      }
-      ::close(fd);
-    }
-    put(chunk{nullptr, 0, 0, true, ""});
-  });
-  std::string feed_error;
-  int feed_rc = 0;
-  while(true) {
-    chunk ck;
-    { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !ready.empty(); }); ck = ready.front(); ready.pop(); }
-    if(ck.last) { if(!ck.error.empty()) feed_error = ck.error; break; }
-    if(!feed_rc && feed_error.empty()) {
-      feed_rc = jfgpu_feed(h, ck.data, ck.n, ck.flags);
-      if(feed_rc) feed_error = jfgpu_last_error(h);
-    }
-    { std::unique_lock<std::mutex> l(mu); freeb.push(ck.data); cv.notify_all(); }
-  }
-  reader.join();
-  if(!feed_error.empty()) die(feed_error);
-  for(int i = 0; i < NBUF; ++i) jfgpu_host_free(bufs[i]);
-  };
   // count_main.cc:288-295: with --if the keys of those files are primed first, then only they are counted
   if(a.if_given) {
     if(jfgpu_set_op(h, JFGPU_OP_PRIME) != JFGPU_OK) die(jfgpu_last_error(h));
-    stream_files(a.if_files);
+    stream_files(h, a.if_files);
     if(jfgpu_set_op(h, JFGPU_OP_UPDATE) != JFGPU_OK) die(jfgpu_last_error(h));
   }
-  stream_files(a.files);
+  if(a.bc_given) load_bloom_counter(h, a.bc_path, a.mer_len);                 // count_main.cc:311-315
+  stream_files(h, a.files);
   jfgpu_stats st;
   if(jfgpu_finish(h, &st) != JFGPU_OK) die(jfgpu_last_error(h));
   auto after_count_time = clk::now();
@@ -650,9 +763,10 @@ int merge_main(int argc, char* argv[]) {
 }  // namespace
 
 int main(int argc, char* argv[]) {
-  if(argc < 2) { std::cerr << "Too few arguments\nUsage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, dump, query, info, histo, stats, merge.\n"; return 1; }
+  if(argc < 2) { std::cerr << "Too few arguments\nUsage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, bc, dump, query, info, histo, stats, merge.\n"; return 1; }
   std::string cmd = argv[1];
   if(cmd == "count") return count_main(argc - 1, argv + 1);
+  if(cmd == "bc") return bc_main(argc - 1, argv + 1);
   if(cmd == "dump")  return dump_main(argc - 1, argv + 1);
   if(cmd == "query") return query_main(argc - 1, argv + 1);
   if(cmd == "info")  return info_main(argc - 1, argv + 1);
@@ -660,7 +774,7 @@ int main(int argc, char* argv[]) {
   if(cmd == "stats") return stats_main(argc - 1, argv + 1);
   if(cmd == "merge") return merge_main(argc - 1, argv + 1);
   if(cmd == "--version" || cmd == "-V") { std::cout << jfgpu_version() << std::endl; return 0; }
-  if(cmd == "--help" || cmd == "-h" || cmd == "help") { std::cout << "Usage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, dump, query, info, histo, stats, merge.\n"; return 0; }
+  if(cmd == "--help" || cmd == "-h" || cmd == "help") { std::cout << "Usage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, bc, dump, query, info, histo, stats, merge.\n"; return 0; }
   std::cerr << "Unknown command '" << cmd << "'\n";
   return 1;
 }

@@ -7,7 +7,7 @@
 //  * identity (no columns) when the table is as large as the key space: v & mask (:225)
 //  * the hash matrix of a table is the pseudo-inverse of a freshly drawn random
 //    matrix (lib/rectangular_binary_matrix.cc:160-210,240-247; large_hash_array.hpp:992-1002)
-// This is an independent implementation (row-reduction written against that contract).
+// Own implementation written against that contract (the inverse is a row-wise Gauss-Jordan, see pseudo_inverse).
 #ifndef JFB_MATRIX_HPP
 #define JFB_MATRIX_HPP
 #include <stdint.h>
@@ -76,33 +76,42 @@ public:
     for(unsigned i = 0; i < c_; ++i) col_[i] = rng.bits(64) & cmask();
   }
 
-  // The matrix is viewed as square (c x c) by stacking [I 0] on top of it: the
-  // top c-r rows copy the high c-r bits of the vector, the bottom r rows are this
-  // matrix.  Returns the bottom r rows of the inverse of that square matrix, i.e.
-  // N such that N * [high bits of v : this*v] = low r bits of v.
-  // Throws std::domain_error when singular.
+  // Pseudo-inverse.  Split the key v into its low s = min(r, c) bits vl and the rest vh, and the matrix
+  // accordingly: M v = Ml vl ^ Mh vh with Ml square (s x s).  The hash position w = M v together with the
+  // explicit high bits vh determines the key: vl = Ml^-1 (w ^ Mh vh).  The result is the matrix
+  // N = Ml^-1 [Mh | I] acting on y = [vh : w] (w in the low s bits, vh above them), i.e. N y = vl -- what the
+  // reference calls pseudo_inverse (it inverts the square matrix obtained by stacking an identity for vh on
+  // top of M and keeps the bottom rows; the inverse being unique, any elimination order gives the same N).
+  // Here: Gauss-Jordan on ROWS of the augmented system (Ml | Mh | I).  Throws std::domain_error when Ml is singular.
   gf2_matrix pseudo_inverse() const {
     if(identity_) return *this;
-    std::vector<uint64_t> piv(col_);
-    gf2_matrix res = low_identity(r_, c_);
-    const unsigned srow = std::min(r_, c_), scol = c_ - srow;
-    // forward elimination on columns scol..c-1, pivot rows from the top (bit srow-1) down
-    uint64_t mask = (uint64_t)1 << (srow - 1);
-    for(unsigned i = scol; i < c_; ++i, mask >>= 1) {
-      if(!(piv[i] & mask)) {
-        unsigned j = i + 1;
-        while(j < c_ && !(piv[j] & mask)) ++j;
-        if(j == c_) throw std::domain_error("Matrix is singular");
-        piv[i] ^= piv[j]; res.col_[i] ^= res.col_[j];
+    const unsigned s = std::min(r_, c_);
+    struct eq { uint64_t lo; uint64_t hi[2]; uint64_t w; };      // coefficients on vl, on vh, on w
+    std::vector<eq> R(s);
+    for(unsigned j = 0; j < s; ++j) {
+      eq q = { 0, { 0, 0 }, (uint64_t)1 << j };
+      for(unsigned i = 0; i < c_; ++i) {
+        const uint64_t bit = (col_[c_ - 1 - i] >> j) & 1;          // key bit i feeds column c-1-i
+        if(i < s) q.lo |= bit << i;
+        else q.hi[(i - s) >> 6] |= bit << ((i - s) & 63);
       }
-      for(unsigned j = i + 1; j < c_; ++j)
-        if(piv[j] & mask) { piv[j] ^= piv[i]; res.col_[j] ^= res.col_[i]; }
+      R[j] = q;
     }
-    // back substitution: clear the pivot rows in every column to the left
-    mask = (uint64_t)1 << (srow - 1);
-    for(unsigned i = scol; i < c_; ++i, mask >>= 1)
-      for(unsigned j = 0; j < i; ++j)
-        if(piv[j] & mask) { piv[j] ^= piv[i]; res.col_[j] ^= res.col_[i]; }
+    for(unsigned p = 0; p < s; ++p) {
+      unsigned q = p;
+      while(q < s && !((R[q].lo >> p) & 1)) ++q;
+      if(q == s) throw std::domain_error("hash matrix has no pseudo-inverse");
+      std::swap(R[p], R[q]);
+      for(unsigned t = 0; t < s; ++t)
+        if(t != p && ((R[t].lo >> p) & 1)) { R[t].lo ^= R[p].lo; R[t].hi[0] ^= R[p].hi[0]; R[t].hi[1] ^= R[p].hi[1]; R[t].w ^= R[p].w; }
+    }
+    // row p now reads  vl_p = hi . vh ^ w . (M v)
+    gf2_matrix res(r_, c_);
+    for(unsigned p = 0; p < s; ++p)
+      for(unsigned t = 0; t < c_; ++t) {
+        const uint64_t coef = t < s ? (R[p].w >> t) & 1 : (R[p].hi[(t - s) >> 6] >> ((t - s) & 63)) & 1;
+        if(coef) res.col_[c_ - 1 - t] |= (uint64_t)1 << p;
+      }
     return res;
   }
 

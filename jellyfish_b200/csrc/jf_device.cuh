@@ -20,7 +20,6 @@ namespace jfk {
 
 constexpr int HALO  = 256;          // bytes of the previous tile staged again in front of a tile
 constexpr int PRE   = 64;           // symbol slots kept in front of a window (>= k-1)
-constexpr int QSYM  = 36;           // symbols rolled per thread chunk (QSYM/4 odd: no bank conflicts)
 
 enum { ST_H = 0, ST_S = 1, ST_L = 2 };   // inside header line / inside sequence line / at line start
 constexpr uint32_t SYM_BREAK = 4;        // symbols 0..3 = A,C,G,T ; 4 = window reset
@@ -53,6 +52,25 @@ struct TableDev {
   uint64_t* fail_keys;             // keys that found no slot (reprobe limit hit)
   uint64_t* fail_counts;
   uint64_t  fail_cap;
+};
+
+// Bloom structures in front of the table (count_main.cc:99-131): `--bf-size` one-pass prefilter (bloom_filter.hpp:42-69),
+// `jellyfish bc` Bloom counter (bloom_counter2.hpp:56-107) and `count --bc` filtering by a loaded counter.
+// Positions of a key: base = h1 mod m, inc = h2 mod m, position i = (base + i*inc) mod m (h1, h2 = two 64-row GF(2)
+// products of the key, mer_dna_bloom_counter.hpp:20-34).
+enum { BLOOM_NONE = 0, BLOOM_FILTER = 1, BLOOM_COUNT = 2, BLOOM_CHECK = 3 };
+struct BloomDev {
+  uint32_t mode;               // BLOOM_*
+  uint32_t k;                  // number of positions per key
+  uint64_t m;                  // number of positions
+  uint64_t inv;                // floor(2^64 / m)
+  uint32_t* bits;              // FILTER: 1 bit per position; COUNT: 2 bits per position ("hit once", "hit twice");
+                               // CHECK: 1 bit per position (the base-3 digit of the loaded counter is 2)
+  uint32_t* locks;             // FILTER: per-key serialisation (2^lock_bits words)
+  uint32_t lock_mask;
+  uint32_t pad;
+  const uint64_t* lut1;        // byte tables of the two 64-row matrices (global memory; staged in shared memory by K1)
+  const uint64_t* lut2;
 };
 
 struct u128 { uint64_t lo, hi; };
@@ -153,6 +171,62 @@ __device__ __forceinline__ u128 key_high(const uint64_t (&key)[KW], uint32_t lsi
     else                 { r.lo = lsize >= 128 ? 0 : k1 >> (lsize - 64); r.hi = 0; }
   }
   return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Bloom filter / Bloom counter operations
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t bloom_mod(const BloomDev& B, uint64_t h) {
+  uint64_t r = h - __umul64hi(h, B.inv) * B.m;         // quotient estimate is off by one at most
+  while(r >= B.m) r -= B.m;
+  return r;
+}
+// bloom_filter_base::insert__ (bloom_filter.hpp:42-69): set the k bits, return whether all of them were set before.
+// Threads holding the SAME key are serialised through a small lock table, so that of n simultaneous occurrences of a
+// k-mer that is not in the filter yet exactly one is reported absent -- the sequential semantics of the reference
+// (filter_bf, count_main.cc:122-133: the first occurrence is dropped, later ones are counted).
+__device__ __forceinline__ bool bloom_test_and_set(const BloomDev& B, uint64_t h1, uint64_t h2) {
+  uint64_t pos = bloom_mod(B, h1);
+  const uint64_t inc = bloom_mod(B, h2);
+  uint32_t* lock = B.locks + (((uint32_t)h1 ^ (uint32_t)(h1 >> 32) ^ (uint32_t)h2) & B.lock_mask);
+  bool present = true, done = false;
+  while(!done) {
+    if(atomicCAS(lock, 0u, 1u) == 0u) {
+      for(uint32_t i = 0; i < B.k; ++i) {
+        const uint32_t bit = 1u << (pos & 31u);
+        const uint32_t old = atomicOr(&B.bits[pos >> 5], bit);
+        present = present && (old & bit);
+        pos += inc; if(pos >= B.m) pos -= B.m;
+      }
+      __threadfence();
+      atomicExch(lock, 0u);
+      done = true;
+    }
+  }
+  return present;
+}
+// bloom_counter2_base::insert__ (bloom_counter2.hpp:56-107): every position is a counter saturating at 2.  Held as two
+// bits ("hit", "hit again"), so the final state -- min(2, number of hits) -- does not depend on the order of the hits.
+__device__ __forceinline__ void bloom_count(const BloomDev& B, uint64_t h1, uint64_t h2) {
+  uint64_t pos = bloom_mod(B, h1);
+  const uint64_t inc = bloom_mod(B, h2);
+  for(uint32_t i = 0; i < B.k; ++i) {
+    const uint32_t sh = (uint32_t)(pos & 15u) * 2u;
+    uint32_t* w = &B.bits[pos >> 4];
+    const uint32_t old = atomicOr(w, 1u << sh);
+    if((old >> sh) & 1u) atomicOr(w, 2u << sh);
+    pos += inc; if(pos >= B.m) pos -= B.m;
+  }
+}
+// filter_bc (count_main.cc:110-120): bloom_counter2_base::check__ > 1, i.e. every position holds the digit 2
+__device__ __forceinline__ bool bloom_check(const BloomDev& B, uint64_t h1, uint64_t h2) {
+  uint64_t pos = bloom_mod(B, h1);
+  const uint64_t inc = bloom_mod(B, h2);
+  for(uint32_t i = 0; i < B.k; ++i) {
+    if(!((__ldg(&B.bits[pos >> 5]) >> (pos & 31u)) & 1u)) return false;
+    pos += inc; if(pos >= B.m) pos -= B.m;
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------

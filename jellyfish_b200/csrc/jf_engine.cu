@@ -61,7 +61,7 @@ std::vector<uint64_t> build_lut(const jfb::gf2_matrix& m, unsigned nbytes) {
 
 struct Table {
   unsigned lsize = 0, local_lsize = 0, max_reprobe = 0, rbits = 1, fbits = 1, slot_bits = 32, hb = 0;
-  uint64_t size = 0, local_size = 0, margin = 0, local_slots = 0;
+  uint64_t size = 0, local_size = 0, margin = 0, local_slots = 0, ovf_size = 0;
   jfb::gf2_matrix M, Minv;
   DevBuf slots, lut, inv_lut, ovf_keys, ovf_vals, lut11;
   uint64_t prow[8] = {0,0,0,0,0,0,0,0}; unsigned n_prow = 0; bool hash_fast = false;
@@ -73,19 +73,30 @@ struct Table {
 }  // namespace
 
 struct PartState {
-  uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0, margin = 0;
+  uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0, margin = 0, arena_chunks = 0, n_arenas = 0;
   DevBuf pool, dir, order, pool_next, cta_chunk, cta_fill, spill_keys, spill_counts, spill_n, hist, start, cursor, unit_cursor;
   uint64_t spill_cap = 0;
   // experimental window form of K2 (jf_window.cuh), JFGPU_K2_WINDOW only
   DevBuf w_start, w_cursor, w_rec, w_def_pos, w_def_high, w_def_n;
   uint64_t w_rec_cap = 0, w_def_cap = 0;
-  uint64_t bound_chunks = 0;     // host-side upper bound of chunks in use
+  uint64_t bound_chunks = 0;     // host-side upper bound of the chunks in use in any one arena
   bool pending = false;          // records sit in the pool
+};
+
+struct BloomState {
+  uint32_t mode = BLOOM_NONE, k = 0;
+  uint64_t m = 0, inv = 0, n_words = 0;
+  bool drawn = false;              // the two hash matrices have been drawn (lazily: after the --if pass, count_main.cc:288-321)
+  jfb::gf2_matrix M1, M2;
+  std::vector<uint64_t> cols1, cols2;
+  DevBuf bits, locks, lut1, lut2;
+  void release() { bits.free(); locks.free(); lut1.free(); lut2.free(); }
 };
 
 struct jfgpu_engine {
   jfgpu_params p;
   PartState part;
+  BloomState bloom;
   int device = 0;
   unsigned k = 0, kw = 1, nbytes = 0, shard_bits = 0;
   cudaStream_t cs = nullptr, hs = nullptr;
@@ -93,7 +104,7 @@ struct jfgpu_engine {
   jfb::glibc_random rng;
   Table tab;
   DevBuf stats, carry[2], fail_keys[2], fail_counts[2];
-  uint64_t ovf_size = 0, fail_cap = 0;
+  uint64_t fail_cap = 0;
   int carry_cur = 0, fail_cur = 0;
   unsigned long long* h_stats = nullptr;    // pinned mirror
   // staging for host feeds
@@ -143,7 +154,7 @@ TableDev table_dev(const jfgpu_engine* e, const Table& t) {
   d.op = e->op;
   d.ovf_keys = t.ovf_keys.as<unsigned long long>();
   d.ovf_vals = t.ovf_vals.as<unsigned long long>();
-  d.ovf_mask = e->ovf_size - 1;
+  d.ovf_mask = t.ovf_size - 1;
   d.stats = e->stats.as<unsigned long long>();
   d.fail_keys = e->fail_keys[e->fail_cur].as<uint64_t>();
   d.fail_counts = e->fail_counts[e->fail_cur].as<uint64_t>();
@@ -170,7 +181,8 @@ int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix
   for(unsigned i = 0; i <= limit; ++i) t.reprobes[i] = rp(i);
   t.rbits = bitsize(limit + 1);
   t.fbits = t.hb + t.rbits;
-  if(t.fbits <= 24) t.slot_bits = 32;
+  // at least 10 counter bits in a slot, so that only counts beyond ~1000 need the carry side table
+  if(t.fbits <= 22) t.slot_bits = 32;
   else if(t.fbits <= 56) t.slot_bits = 64;
   else if(t.fbits <= 120) t.slot_bits = 128;
   else return fail(e, JFGPU_ERR_ARG, "key too long for this table size (key field > 120 bits)");
@@ -187,10 +199,13 @@ int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix
   }
   t.slots.bytes = t.bytes();
   CUDA_OK(e, cudaMemsetAsync(t.slots.p, 0, t.bytes(), e->cs));
-  CUDA_OK(e, t.ovf_keys.alloc(e->ovf_size * 8));
-  CUDA_OK(e, t.ovf_vals.alloc(e->ovf_size * 8));
-  CUDA_OK(e, cudaMemsetAsync(t.ovf_keys.p, 0, e->ovf_size * 8, e->cs));
-  CUDA_OK(e, cudaMemsetAsync(t.ovf_vals.p, 0, e->ovf_size * 8, e->cs));
+  // counter-carry side table: one entry per slot whose counter field wrapped; sized with the table
+  t.ovf_size = (uint64_t)1 << 20;
+  while(t.ovf_size < ((uint64_t)1 << 26) && t.ovf_size * 64 < t.local_size) t.ovf_size <<= 1;
+  CUDA_OK(e, t.ovf_keys.alloc(t.ovf_size * 8));
+  CUDA_OK(e, t.ovf_vals.alloc(t.ovf_size * 8));
+  CUDA_OK(e, cudaMemsetAsync(t.ovf_keys.p, 0, t.ovf_size * 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(t.ovf_vals.p, 0, t.ovf_size * 8, e->cs));
   std::vector<uint64_t> l1 = build_lut(t.M, e->nbytes), l2 = build_lut(t.Minv, e->nbytes);
   CUDA_OK(e, t.lut.alloc(l1.size() * 8));
   CUDA_OK(e, t.inv_lut.alloc(l2.size() * 8));
@@ -246,8 +261,8 @@ int dispatch(jfgpu_engine* e, unsigned kw, unsigned sb, F&& f) {
 }
 
 template<int NTH>
-size_t count_smem_bytes(size_t lut_bytes, size_t stage_bytes) {
-  return ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + (stage_bytes ? PMAX * 4 + stage_bytes : 0);
+size_t count_smem_bytes(size_t lut_bytes, size_t stage_bytes, size_t bloom_bytes = 0) {
+  return ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + (stage_bytes ? PMAX * 4 + stage_bytes : 0) + bloom_bytes;
 }
 
 int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
@@ -271,7 +286,8 @@ PartDev part_dev(const jfgpu_engine* e) {
   d.P = ps.P; d.region_bits = ps.region_bits; d.rec_bytes = ps.rec_bytes; d.cap = ps.cap; d.flush_min = ps.flush_min;
   d.chunk_recs = CHUNK_BYTES / std::max(1u, ps.rec_bytes); d.n_chunks = ps.n_chunks; d.stage_bytes = ps.stage_bytes;
   d.margin = ps.margin;
-  d.pool = ps.pool.as<uint8_t>(); d.pool_next = ps.pool_next.as<unsigned int>(); d.dir = ps.dir.as<uint2>();
+  d.arena_chunks = ps.arena_chunks;
+  d.pool = ps.pool.as<uint8_t>(); d.pool_next = ps.pool_next.as<unsigned int>(); d.n_units = d.pool_next + ps.n_arenas; d.dir = ps.dir.as<uint2>();
   d.cta_chunk = ps.cta_chunk.as<uint32_t>(); d.cta_fill = ps.cta_fill.as<uint32_t>();
   d.spill_keys = ps.spill_keys.as<uint64_t>(); d.spill_counts = ps.spill_counts.as<uint64_t>();
   d.spill_n = ps.spill_n.as<unsigned long long>(); d.spill_cap = ps.spill_cap;
@@ -311,20 +327,23 @@ int part_alloc(jfgpu_engine* e) {
   size_t want = e->p.pool_bytes ? (size_t)e->p.pool_bytes : std::min<size_t>((size_t)(free_b * 0.6), (size_t)64 << 30);
   const size_t floor_b = (size_t)e->n_sm * ps.P * CHUNK_BYTES * 2;        // every CTA keeps one open chunk per region
   if(want < floor_b) want = floor_b;
-  ps.n_chunks = (uint32_t)std::min<size_t>(want / CHUNK_BYTES, 0xFFFFFFF0u);
+  // one arena per CTA of the staging kernels (persistent, one CTA per SM)
+  ps.n_arenas = (uint32_t)e->n_sm;
+  ps.arena_chunks = (uint32_t)std::min<size_t>(want / CHUNK_BYTES / ps.n_arenas, 0xFFFFFFF0u / ps.n_arenas);
+  ps.n_chunks = ps.arena_chunks * ps.n_arenas;
   ps.spill_cap = (uint64_t)16 << 20;
   bool ok = ps.pool.alloc((size_t)ps.n_chunks * CHUNK_BYTES) == cudaSuccess && ps.dir.alloc((size_t)ps.n_chunks * 8) == cudaSuccess &&
-            ps.order.alloc((size_t)ps.n_chunks * 4) == cudaSuccess && ps.pool_next.alloc(8) == cudaSuccess &&
+            ps.order.alloc((size_t)ps.n_chunks * 4) == cudaSuccess && ps.pool_next.alloc(((size_t)ps.n_arenas + 2) * 4) == cudaSuccess &&
             ps.cta_chunk.alloc((size_t)e->n_sm * PMAX * 4) == cudaSuccess && ps.cta_fill.alloc((size_t)e->n_sm * PMAX * 4) == cudaSuccess &&
             ps.spill_keys.alloc(ps.spill_cap * 8 * e->kw) == cudaSuccess && ps.spill_counts.alloc(ps.spill_cap * 8) == cudaSuccess &&
             ps.spill_n.alloc(8) == cudaSuccess && ps.hist.alloc(PMAX * 4) == cudaSuccess && ps.start.alloc(PMAX * 4) == cudaSuccess &&
             ps.cursor.alloc(PMAX * 4) == cudaSuccess && ps.unit_cursor.alloc(8) == cudaSuccess;
   if(!ok) { cudaGetLastError(); return fail(e, JFGPU_ERR_NOMEM, "device allocation of the record pool failed"); }
-  CUDA_OK(e, cudaMemsetAsync(ps.pool_next.p, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(ps.pool_next.p, 0, ps.pool_next.bytes, e->cs));
   CUDA_OK(e, cudaMemsetAsync(ps.spill_n.p, 0, 8, e->cs));
   CUDA_OK(e, cudaMemsetAsync(ps.cta_chunk.p, 0xFF, ps.cta_chunk.bytes, e->cs));
   CUDA_OK(e, cudaMemsetAsync(ps.cta_fill.p, 0, ps.cta_fill.bytes, e->cs));
-  ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
+  ps.bound_chunks = ps.P;
   ps.pending = false;
   CUDA_OK(e, cudaStreamSynchronize(e->cs));     // callers may continue on another stream
   return JFGPU_OK;
@@ -336,11 +355,13 @@ void part_release(jfgpu_engine* e) {
   ps.spill_keys.free(); ps.spill_counts.free(); ps.spill_n.free(); ps.hist.free(); ps.start.free(); ps.cursor.free(); ps.unit_cursor.free();
   ps.w_start.free(); ps.w_cursor.free(); ps.w_rec.free(); ps.w_def_pos.free(); ps.w_def_high.free(); ps.w_def_n.free();
   ps.w_rec_cap = ps.w_def_cap = 0;
-  ps.n_chunks = 0; ps.pending = false;
+  ps.n_chunks = 0; ps.arena_chunks = 0; ps.n_arenas = 0; ps.pending = false;
 }
 
 int regrow(jfgpu_engine* e);
 int read_stats(jfgpu_engine* e);
+int bloom_draw(jfgpu_engine* e);
+BloomDev bloom_dev(const jfgpu_engine* e);
 
 // EXPERIMENTAL (JFGPU_K2_WINDOW, never run on a device yet): the window form of K2, jf_window.cuh.
 // Processes whole regions in groups, starting at unit `*done` (which must be the first unit of a
@@ -447,7 +468,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   close_chunks_kernel<<<g, 256, 0, st>>>(pd, (uint32_t)e->n_sm); JF_LAUNCHED();
   CUDA_OK(e, cudaMemsetAsync(ps.hist.p, 0, PMAX * 4, st));
   chunk_hist_kernel<<<g, 256, 0, st>>>(pd, ps.hist.as<uint32_t>()); JF_LAUNCHED();
-  chunk_scan_kernel<<<1, 1024, 0, st>>>(pd.P, ps.hist.as<uint32_t>(), ps.start.as<uint32_t>(), ps.cursor.as<uint32_t>()); JF_LAUNCHED();
+  chunk_scan_kernel<<<1, 1024, 0, st>>>(pd.P, ps.hist.as<uint32_t>(), ps.start.as<uint32_t>(), ps.cursor.as<uint32_t>(), pd.n_units); JF_LAUNCHED();
   chunk_scatter_kernel<<<g, 256, 0, st>>>(pd, ps.cursor.as<uint32_t>(), ps.order.as<uint32_t>()); JF_LAUNCHED();
   CUDA_OK(e, cudaMemsetAsync(ps.unit_cursor.p, 0, 8, st));
   // geometry the records were written with (a regrow in the middle changes e->tab)
@@ -456,7 +477,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   const bool careful = e->p.allow_regrow != 0;
   unsigned int n_units = 0;
   if(careful) {
-    CUDA_OK(e, cudaMemcpyAsync(&n_units, ps.pool_next.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(e, cudaMemcpyAsync(&n_units, pd.n_units, 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(e, cudaStreamSynchronize(st));
     n_units = std::min(n_units, ps.n_chunks);
   }
@@ -467,7 +488,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   bool rebuilt = false;
   if(window_enabled(e, pd)) {
     if(!careful) {
-      CUDA_OK(e, cudaMemcpyAsync(&n_units, ps.pool_next.p, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(e, cudaMemcpyAsync(&n_units, pd.n_units, 4, cudaMemcpyDeviceToHost, st));
       CUDA_OK(e, cudaStreamSynchronize(st));
       n_units = std::min(n_units, ps.n_chunks);
     }
@@ -541,17 +562,28 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     });
     if(!rc) JF_LAUNCHED();
   }
-  cudaMemsetAsync(ps.pool_next.p, 0, 8, st);
+  cudaMemsetAsync(ps.pool_next.p, 0, ps.pool_next.bytes, st);
   cudaMemsetAsync(ps.spill_n.p, 0, 8, st);
   cudaEventRecord(e->ev_d1, st);
   cudaStreamSynchronize(st);
   { float ms = 0; if(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1) == cudaSuccess) e->drain_ms += ms; else cudaGetLastError(); }
   ps.pending = false;
   if(rebuilt) { cudaStreamSynchronize(st); old_inv.free(); part_configure(e); if(!e->part.P) part_release(e); }
-  ps.bound_chunks = (uint64_t)e->n_sm * ps.P;
+  ps.bound_chunks = ps.P;
   if(rc) return rc;
   CUDA_OK(e, cudaGetLastError());
   return JFGPU_OK;
+}
+
+// no more text per launch than an empty arena can take (small pools: tests, tables that leave little memory)
+size_t part_cap_len(const jfgpu_engine* e, size_t len) {
+  const PartState& ps = e->part;
+  if(!ps.P || !ps.arena_chunks) return len;
+  const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
+  const uint64_t room = ps.arena_chunks > ps.P + 8 ? ps.arena_chunks - ps.P - 8 : 1;
+  const uint64_t tiles_per_cta = std::max<uint64_t>(room * usable / (1024 * 32), 1);
+  const uint64_t cap = tiles_per_cta * (1024 * 32 - HALO) * (uint64_t)e->n_sm / 2;
+  return len > cap ? (size_t)std::max<uint64_t>(cap & ~(uint64_t)15, 16) : len;
 }
 
 // One batch of device-resident text through K0a, K0b, K1 on `stream`.
@@ -559,20 +591,26 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
               int mode, uint64_t* route_keys, unsigned long long* route_counts, uint64_t route_cap) {
   if(n == 0) return JFGPU_OK;
   PartState& ps = e->part;
-  const bool part = mode == 0 && ps.P != 0;
+  const bool bc_build = e->bloom.mode == BLOOM_COUNT;
+  const bool part = mode == 0 && ps.P != 0 && !bc_build;
   int rc;
+  if(e->bloom.mode != BLOOM_NONE && !e->bloom.drawn && (e->op != JFGPU_OP_PRIME || bc_build)) { rc = bloom_draw(e); if(rc) return rc; }
   if(part) {
     rc = part_alloc(e);
     if(rc) return rc;
-    // conservative host-side bound on pool usage: one record per input byte at most
+    // conservative host-side bound on the use of any one arena: a CTA sees ceil(tiles / CTAs) tiles, one record per
+    // input byte at most, plus the chunks its roll-over passes may leave nearly empty
     const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;         // records a closed chunk holds at least
-    const uint64_t need = n / usable + 2;
-    if(ps.bound_chunks + need > ps.n_chunks) {
+    const uint64_t tile_b = 1024 * 32 - HALO;
+    const uint64_t tiles = (n + tile_b - 1) / tile_b;
+    const uint64_t per_cta = (tiles + e->n_sm - 1) / e->n_sm * tile_b;
+    const uint64_t need = per_cta / usable + 2;
+    if(ps.bound_chunks + need > ps.arena_chunks) {
       rc = part_drain(e, stream);
       if(rc) return rc;
       if(!e->part.P) return run_batch(e, dev, n, n_look, stream, mode, route_keys, route_counts, route_cap);
     }
-    if(ps.bound_chunks + need > ps.n_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch");
+    if(ps.bound_chunks + need > ps.arena_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch");
     ps.bound_chunks += need;
     ps.pending = true;
   }
@@ -601,6 +639,9 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   for(unsigned i = 0; i < 8; ++i) a.prow[i] = e->tab.prow[i];
   a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode; a.format = (uint32_t)e->format;
   a.T = table_dev(e, e->tab);
+  a.bloom = bloom_dev(e);
+  const size_t bloom_smem = a.bloom.mode ? (size_t)e->nbytes * 256 * 8 * 2 : 0;
+  if(bc_build) { a.lut = nullptr; a.lut_bytes = 0; a.hash_fast = 0; }
   a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
   PartDev pd = part_dev(e);
   auto launch = [&](auto kern, int nth, size_t smem, bool one_per_sm) -> int {
@@ -620,15 +661,77 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   };
   rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
     constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
-    if(part)      return launch(extract_kernel<kw, sb, 2, 1024>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes), true);
-    if(mode == 1) return launch(extract_kernel<kw, sb, 1, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
-    return launch(extract_kernel<kw, sb, 0, 512>, 512, count_smem_bytes<512>(a.lut_bytes, 0), false);
+    if(part) {
+      // the all-32-bit tail: 11-bit-table hash with at most two parity rows, 4-byte records, one shard, region index and
+      // record fields inside 32 bits
+      const bool fast = kw == 1 && e->tab.hash_fast && e->tab.n_prow <= 2 && ps.rec_bytes == 4 && e->shard_bits == 0 &&
+                        ps.region_bits >= 2 && ps.region_bits < 32 && e->tab.lsize <= 34 && e->tab.lsize >= ps.region_bits;
+      if(kw == 1 && fast) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, bloom_smem), true);
+      return launch(extract_kernel<kw, sb, 2, 1024, false>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, bloom_smem), true);
+    }
+    if(mode == 1) return launch(extract_kernel<kw, sb, 1, 512, false>, 512, count_smem_bytes<512>(a.lut_bytes, 0, bloom_smem), false);
+    return launch(extract_kernel<kw, sb, 0, 512, false>, 512, count_smem_bytes<512>(a.lut_bytes, 0, bloom_smem), false);
   });
   if(rc) return rc;
   JF_LAUNCHED();
   CUDA_OK(e, cudaGetLastError());
   e->carry_cur ^= 1;
   return JFGPU_OK;
+}
+
+// ---- Bloom filter / counter ------------------------------------------------------------
+// bloom_base::opt_m / opt_k (bloom_common.hpp:62-67)
+int bloom_setup(jfgpu_engine* e, uint32_t mode, uint64_t n, double fp) {
+  BloomState& b = e->bloom;
+  if(fp <= 0.0) fp = mode == BLOOM_COUNT ? 0.001 : 0.01;          // bc_main_cmdline.yaggo / count_main_cmdline.yaggo defaults
+  if(fp >= 1.0) return fail(e, JFGPU_ERR_ARG, "false positive rate must be in (0, 1)");
+  const double LOG2 = 0.6931471805599453, LOG2_SQ = 0.4804530139182014;
+  b.m = n * (uint64_t)lrint(-log(fp) / LOG2_SQ);
+  b.k = (uint32_t)lrint(-log(fp) / LOG2);
+  if(b.m == 0 || b.k == 0) return fail(e, JFGPU_ERR_ARG, "empty Bloom filter (size and false positive rate give no bits)");
+  b.mode = mode;
+  b.inv = b.m == 1 ? ~(uint64_t)0 : (uint64_t)(((unsigned __int128)1 << 64) / b.m);
+  b.n_words = mode == BLOOM_COUNT ? (b.m + 15) / 16 : (b.m + 31) / 32;
+  if(b.bits.alloc((size_t)b.n_words * 4 + 16) != cudaSuccess) { cudaGetLastError(); return fail(e, JFGPU_ERR_NOMEM, "Failed to allocate the Bloom filter in device memory"); }
+  CUDA_OK(e, cudaMemsetAsync(b.bits.p, 0, b.bits.bytes, e->cs));
+  if(mode == BLOOM_FILTER) {
+    CUDA_OK(e, b.locks.alloc((size_t)4 << 20));
+    CUDA_OK(e, cudaMemsetAsync(b.locks.p, 0, b.locks.bytes, e->cs));
+  }
+  b.drawn = false;
+  return JFGPU_OK;
+}
+int bloom_upload_matrices(jfgpu_engine* e) {
+  BloomState& b = e->bloom;
+  std::vector<uint64_t> l1 = build_lut(b.M1, e->nbytes), l2 = build_lut(b.M2, e->nbytes);
+  CUDA_OK(e, b.lut1.alloc(l1.size() * 8));
+  CUDA_OK(e, b.lut2.alloc(l2.size() * 8));
+  CUDA_OK(e, cudaMemcpyAsync(b.lut1.p, l1.data(), l1.size() * 8, cudaMemcpyHostToDevice, e->cs));
+  CUDA_OK(e, cudaMemcpyAsync(b.lut2.p, l2.data(), l2.size() * 8, cudaMemcpyHostToDevice, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  b.cols1.assign(b.M1.c(), 0); b.cols2.assign(b.M2.c(), 0);
+  for(unsigned i = 0; i < b.M1.c(); ++i) { b.cols1[i] = b.M1[i]; b.cols2[i] = b.M2[i]; }
+  b.drawn = true;
+  return JFGPU_OK;
+}
+// hash_pair<mer_dna>() (mer_dna_bloom_counter.hpp:22-27): two 64 x 2k matrices, randomize() only, the next draws of the stream
+int bloom_draw(jfgpu_engine* e) {
+  BloomState& b = e->bloom;
+  if(b.drawn || b.mode == BLOOM_NONE) return JFGPU_OK;
+  b.M1 = jfb::gf2_matrix(64, 2 * e->k); b.M1.randomize(e->rng);
+  b.M2 = jfb::gf2_matrix(64, 2 * e->k); b.M2.randomize(e->rng);
+  return bloom_upload_matrices(e);
+}
+BloomDev bloom_dev(const jfgpu_engine* e) {
+  BloomDev d;
+  memset(&d, 0, sizeof(d));
+  const BloomState& b = e->bloom;
+  // the PRIME pass of --if is not filtered (count_main.cc:288-295 builds that counter without a filter)
+  if(b.mode == BLOOM_NONE || !b.drawn || (e->op == JFGPU_OP_PRIME && b.mode != BLOOM_COUNT)) return d;
+  d.mode = b.mode; d.k = b.k; d.m = b.m; d.inv = b.inv;
+  d.bits = b.bits.as<uint32_t>(); d.locks = b.locks.as<uint32_t>(); d.lock_mask = (uint32_t)(b.locks.bytes / 4 - 1);
+  d.lut1 = b.lut1.as<uint64_t>(); d.lut2 = b.lut2.as<uint64_t>();
+  return d;
 }
 
 int reset_carry(jfgpu_engine* e, cudaStream_t stream) {
@@ -858,7 +961,18 @@ int check_after_batches(jfgpu_engine* e) {
   int rc = read_stats(e);
   if(rc) return rc;
   if(e->h_stats[STAT_OVF_FULL]) return fail(e, JFGPU_ERR_FULL, "counter overflow side table is full");
-  if(e->h_stats[STAT_FAILED]) return regrow(e);
+  if(e->h_stats[STAT_FAILED]) {
+    // records staged against the CURRENT geometry must reach the table before it is rebuilt: the drain copes
+    // with a doubling in its middle (old inverse tables + rehash kernel), a plain regrow() would not
+    if(e->part.pending) {
+      rc = part_drain(e, e->cs);
+      if(rc) return rc;
+      rc = read_stats(e);
+      if(rc) return rc;
+      if(!e->h_stats[STAT_FAILED]) return JFGPU_OK;
+    }
+    return regrow(e);
+  }
   return JFGPU_OK;
 }
 
@@ -928,6 +1042,23 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
   for(int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming); }
 
+  if(params->bloom_counter) {
+    // `jellyfish bc`: no hash table at all; the two hash matrices are the FIRST draws of the random stream (bc_main.cc:103-106)
+    bool ok0 = e->stats.alloc(STAT_N * 8) == cudaSuccess && e->carry[0].alloc(sizeof(Carry)) == cudaSuccess && e->carry[1].alloc(sizeof(Carry)) == cudaSuccess &&
+               cudaHostAlloc((void**)&e->h_stats, STAT_N * 8, cudaHostAllocDefault) == cudaSuccess;
+    if(!ok0) { cudaGetLastError(); e->err = "device allocation failed"; return bail(JFGPU_ERR_NOMEM); }
+    cudaMemsetAsync(e->stats.p, 0, STAT_N * 8, e->cs);
+    memset(e->h_stats, 0, STAT_N * 8);
+    e->batch_bytes = params->max_batch_bytes ? (size_t)((params->max_batch_bytes + 15) & ~(uint64_t)15) : ((size_t)64 << 20);
+    e->tab.slot_bits = 64; e->tab.lsize = 0; e->tab.size = 0;
+    int rc0 = bloom_setup(e, BLOOM_COUNT, params->bf_size, params->bf_fp);
+    if(!rc0) rc0 = bloom_draw(e);
+    if(!rc0) rc0 = reset_carry(e, e->cs);
+    if(rc0) return bail(rc0);
+    *out = e;
+    return JFGPU_OK;
+  }
+
   // table geometry: size rounded up to a power of two, clipped to 4^k (large_hash_array.hpp:992-1002,150-153)
   const unsigned kbits = 2 * e->k;
   uint64_t req = params->size;
@@ -938,7 +1069,6 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   jfb::gf2_matrix M = draw_matrix(e, params->size, lsize);
 
   // side structures
-  e->ovf_size = (uint64_t)1 << 20;
   e->batch_bytes = params->max_batch_bytes ? (size_t)((params->max_batch_bytes + 15) & ~(uint64_t)15) : ((size_t)64 << 20);
   e->fail_cap = params->allow_regrow ? 2 * (uint64_t)e->batch_bytes : ((uint64_t)1 << 16);
   bool ok = e->stats.alloc(STAT_N * 8) == cudaSuccess && e->carry[0].alloc(sizeof(Carry)) == cudaSuccess &&
@@ -951,6 +1081,9 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   int rc = table_setup(e, e->tab, lsize, M, params->max_reprobe);
   if(rc) return bail(rc);
   part_configure(e);
+  // count --bf-size: mer_dna_bloom_filter(bf_fp, bf_size) in front of the table (count_main.cc:317-321); its matrices are
+  // drawn when the first unprimed text arrives
+  if(params->bf_size) { rc = bloom_setup(e, BLOOM_FILTER, params->bf_size, params->bf_fp); if(rc) return bail(rc); }
   rc = reset_carry(e, e->cs);
   if(rc) return bail(rc);
   *out = e;
@@ -964,6 +1097,7 @@ void jfgpu_destroy(jfgpu_handle e) {
   if(e->hs) cudaStreamSynchronize(e->hs);
   e->tab.release();
   part_release(e);
+  e->bloom.release();
   e->stats.free();
   for(int i = 0; i < 2; ++i) {
     e->carry[i].free(); e->fail_keys[i].free(); e->fail_counts[i].free(); e->stage[i].free();
@@ -1020,13 +1154,15 @@ int jfgpu_feed_device(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t 
   int rc = begin_feed(e, flags, first, st);
   if(rc) return rc;
   const uint8_t* p = (const uint8_t*)dev_bytes;
+  if(e->part.P) { rc = part_alloc(e); if(rc) return rc; }
   cudaEventRecord(e->ev_t0, st);
   for(size_t off = 0; off < n; ) {
     size_t len = std::min(e->part.P ? std::max<size_t>(e->batch_bytes, (size_t)512 << 20) : e->batch_bytes, n - off);
+    len = part_cap_len(e, len);
     rc = run_batch(e, p + off, len, n - off, st, 0, nullptr, nullptr, 0);
     if(rc) return rc;
     off += len;
-    if(e->p.allow_regrow && !e->part.P) {          // the failure list only holds two batches
+    if(e->p.allow_regrow && !e->part.P && e->tab.slots.p) {          // the failure list only holds two batches
       if(st != e->cs) CUDA_OK(e, cudaStreamSynchronize(st));
       rc = check_after_batches(e);
       if(rc) return rc;
@@ -1046,16 +1182,17 @@ int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
   int rc = begin_feed(e, flags, n ? (unsigned char)bytes[0] : -1, e->cs);
   if(rc) return rc;
   for(int i = 0; i < 2; ++i) if(!e->stage[i].p) CUDA_OK(e, e->stage[i].alloc(e->batch_bytes + 64));
+  if(e->part.P) { rc = part_alloc(e); if(rc) return rc; }
   cudaEventRecord(e->ev_t0, e->cs);
   size_t off = 0;
   while(off < n) {
-    size_t len = std::min(e->batch_bytes, n - off);
+    size_t len = part_cap_len(e, std::min(e->batch_bytes, n - off));
     // never end a chunk on '\r' unless it is the end of the data: the device looks one byte ahead
     if(off + len < n) { size_t l2 = len; while(l2 > 1 && bytes[off + l2 - 1] == '\r') --l2; if(l2 > 1) len = l2; }
     const int s = e->stage_cur;
     // the previous batch that used this staging buffer must be done before it is overwritten
     CUDA_OK(e, cudaEventSynchronize(e->ev_done[s]));
-    if(e->p.allow_regrow) {
+    if(e->p.allow_regrow && e->tab.slots.p) {
       // peek at the live failure counter without draining the compute stream
       CUDA_OK(e, cudaMemcpyAsync(e->h_stats + STAT_FAILED, e->stats.as<unsigned long long>() + STAT_FAILED, 8, cudaMemcpyDeviceToHost, e->hs));
       CUDA_OK(e, cudaStreamSynchronize(e->hs));
@@ -1075,14 +1212,14 @@ int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
   { float ms = 0; cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1); e->count_ms += ms; }
   resolve_kernel_events(e);
-  rc = check_after_batches(e);
-  if(rc) return rc;
+  if(e->tab.slots.p) { rc = check_after_batches(e); if(rc) return rc; }
   return end_feed(e, flags, e->cs);
 }
 
 int jfgpu_extract_route(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t flags, void* dev_keys, uint64_t capacity,
                         uint64_t* dev_counts, void* stream) {
   if(!e) return JFGPU_ERR_ARG;
+  if(!e->tab.slots.p || e->bloom.mode != BLOOM_NONE) return fail(e, JFGPU_ERR_STATE, "Bloom filters are not supported on the sharded path");
   if(((uintptr_t)dev_bytes & 15) != 0) return fail(e, JFGPU_ERR_ARG, "device text must be 16-byte aligned");
   cudaSetDevice(e->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
@@ -1115,6 +1252,7 @@ int jfgpu_extract_route(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_
 
 int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* stream) {
   if(!e) return JFGPU_ERR_ARG;
+  if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
   cudaSetDevice(e->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
   if(n == 0) return JFGPU_OK;
@@ -1126,13 +1264,14 @@ int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* st
     rc = part_alloc(e);
     if(rc) return rc;
     const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
-    const uint64_t need = n / usable + 2;
-    if(ps.bound_chunks + need > ps.n_chunks) { rc = part_drain(e, st); if(rc) return rc; }
-    if(ps.P && ps.bound_chunks + need > ps.n_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch of keys");
+    const uint64_t per_cta = (n + e->n_sm - 1) / e->n_sm + 1024 * 32;     // keys a CTA of stage_keys_kernel handles at most
+    const uint64_t need = per_cta / usable + 2;
+    if(ps.bound_chunks + need > ps.arena_chunks) { rc = part_drain(e, st); if(rc) return rc; }
+    if(ps.P && ps.bound_chunks + need > ps.arena_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch of keys");
   }
   if(ps.P) {
     const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
-    ps.bound_chunks += n / usable + 2;
+    ps.bound_chunks += ((n + e->n_sm - 1) / e->n_sm + 1024 * 32) / usable + 2;
     ps.pending = true;
     PartDev pd = part_dev(e);
     TableDev T = table_dev(e, e->tab);
@@ -1173,16 +1312,19 @@ int jfgpu_clear(jfgpu_handle e) {
   CUDA_OK(e, cudaStreamSynchronize(e->hs));
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
   resolve_kernel_events(e);
-  CUDA_OK(e, cudaMemsetAsync(e->tab.slots.p, 0, e->tab.bytes(), e->cs));
-  CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_keys.p, 0, e->ovf_size * 8, e->cs));
-  CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_vals.p, 0, e->ovf_size * 8, e->cs));
+  if(e->tab.slots.p) {
+    CUDA_OK(e, cudaMemsetAsync(e->tab.slots.p, 0, e->tab.bytes(), e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_keys.p, 0, e->tab.ovf_size * 8, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_vals.p, 0, e->tab.ovf_size * 8, e->cs));
+  }
+  if(e->bloom.bits.p && e->bloom.mode != BLOOM_CHECK) CUDA_OK(e, cudaMemsetAsync(e->bloom.bits.p, 0, e->bloom.bits.bytes, e->cs));
   CUDA_OK(e, cudaMemsetAsync(e->stats.p, 0, STAT_N * 8, e->cs));
   if(e->part.pool.p) {
-    CUDA_OK(e, cudaMemsetAsync(e->part.pool_next.p, 0, 8, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->part.pool_next.p, 0, e->part.pool_next.bytes, e->cs));
     CUDA_OK(e, cudaMemsetAsync(e->part.spill_n.p, 0, 8, e->cs));
     CUDA_OK(e, cudaMemsetAsync(e->part.cta_chunk.p, 0xFF, e->part.cta_chunk.bytes, e->cs));
     CUDA_OK(e, cudaMemsetAsync(e->part.cta_fill.p, 0, e->part.cta_fill.bytes, e->cs));
-    e->part.bound_chunks = (uint64_t)e->n_sm * e->part.P;
+    e->part.bound_chunks = e->part.P;
     e->part.pending = false;
   }
   e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0; e->drain_ms = 0;
@@ -1218,19 +1360,19 @@ int jfgpu_finish(jfgpu_handle e, jfgpu_stats* s) {
   if(rc) return rc;
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
   CUDA_OK(e, cudaGetLastError());
-  rc = check_after_batches(e);
+  rc = e->tab.slots.p ? check_after_batches(e) : read_stats(e);
   if(rc) return rc;
   if(e->h_stats[STAT_FORMAT_ERR]) return fail(e, JFGPU_ERR_FORMAT, "Invalid fastq sequence (the device parser reads 4-line FASTQ records: '@' header, sequence, '+', qualities)");
   if(e->h_stats[STAT_POOL_FULL]) return fail(e, JFGPU_ERR_NOMEM, "internal: k-mer record pool overflow");
   if(e->h_stats[STAT_ROUTE_DROPPED]) return fail(e, JFGPU_ERR_FULL, "route bucket capacity exceeded");
-  rc = direct_index_fixup(e);
-  if(rc) return rc;
+  if(e->tab.slots.p) { rc = direct_index_fixup(e); if(rc) return rc; }
   if(s) return jfgpu_get_stats(e, s);
   return JFGPU_OK;
 }
 
 int jfgpu_table_info_get(jfgpu_handle e, jfgpu_table_info* info) {
   if(!e || !info) return JFGPU_ERR_ARG;
+  if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
   const Table& t = e->tab;
   info->size = t.size; info->lsize = t.lsize; info->key_len = 2 * e->k; info->val_len = e->eff_val_len;
   info->max_reprobe = t.max_reprobe; info->matrix_r = t.M.r(); info->matrix_c = t.M.c();
@@ -1246,6 +1388,7 @@ int jfgpu_table_info_get(jfgpu_handle e, jfgpu_table_info* info) {
 
 int jfgpu_dump(jfgpu_handle e, uint64_t lower, uint64_t upper, uint32_t ocl, jfgpu_sink_fn sink, void* ctx, uint64_t* n_records) {
   if(!e || !sink) return JFGPU_ERR_ARG;
+  if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
   if(ocl < 1 || ocl > 8) return fail(e, JFGPU_ERR_ARG, "out_counter_len must be in [1, 8]");
   cudaSetDevice(e->device);
   int rc = jfgpu_finish(e, nullptr);
@@ -1303,6 +1446,7 @@ int jfgpu_dump(jfgpu_handle e, uint64_t lower, uint64_t upper, uint32_t ocl, jfg
 
 int jfgpu_lookup(jfgpu_handle e, const uint64_t* keys, size_t n, uint64_t* vals) {
   if(!e || (n && (!keys || !vals))) return JFGPU_ERR_ARG;
+  if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
   if(n == 0) return JFGPU_OK;
   cudaSetDevice(e->device);
   { int rc0 = jfgpu_finish(e, nullptr); if(rc0) return rc0; }
@@ -1330,6 +1474,7 @@ int jfgpu_lookup(jfgpu_handle e, const uint64_t* keys, size_t n, uint64_t* vals)
 
 int jfgpu_histogram(jfgpu_handle e, uint64_t* hist, uint32_t n_bins) {
   if(!e || !hist || n_bins == 0) return JFGPU_ERR_ARG;
+  if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
   cudaSetDevice(e->device);
   int rc = jfgpu_finish(e, nullptr);
   if(rc) return rc;
@@ -1350,6 +1495,78 @@ int jfgpu_histogram(jfgpu_handle e, uint64_t* hist, uint32_t n_bins) {
   dh.free();
   if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("histogram: ") + cudaGetErrorString(c));
   return JFGPU_OK;
+}
+
+int jfgpu_bloom_info_get(jfgpu_handle e, jfgpu_bloom_info* info) {
+  if(!e || !info) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  memset(info, 0, sizeof(*info));
+  BloomState& b = e->bloom;
+  info->mode = b.mode;
+  if(b.mode == BLOOM_NONE) return JFGPU_OK;
+  if(!b.drawn) { int rc = bloom_draw(e); if(rc) return rc; }
+  info->nb_hashes = b.k; info->m = b.m;
+  info->nb_bytes = b.mode == BLOOM_FILTER ? b.m / 8 + (b.m % 8 != 0) : b.m / 5 + (b.m % 5 != 0);
+  info->matrix_r = 64; info->matrix_c = 2 * e->k;
+  info->matrix1 = b.cols1.data(); info->matrix2 = b.cols2.data();
+  return JFGPU_OK;
+}
+
+int jfgpu_bloom_load(jfgpu_handle e, uint64_t m, uint32_t nb_hashes, const uint64_t* c1, const uint64_t* c2, const void* bytes, size_t nbytes) {
+  if(!e || !c1 || !c2 || !bytes) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
+  if(e->bloom.mode != BLOOM_NONE) return fail(e, JFGPU_ERR_STATE, "a Bloom filter is already attached to this engine");
+  if(m == 0 || nb_hashes == 0) return fail(e, JFGPU_ERR_ARG, "empty Bloom counter");
+  if(nbytes < m / 5 + (m % 5 != 0)) return fail(e, JFGPU_ERR_ARG, "Bloom filter file is truncated");
+  int rc = jfgpu_finish(e, nullptr);          // text fed so far is counted unfiltered
+  if(rc) return rc;
+  BloomState& b = e->bloom;
+  b.m = m; b.k = nb_hashes;
+  b.inv = m == 1 ? ~(uint64_t)0 : (uint64_t)(((unsigned __int128)1 << 64) / m);
+  b.n_words = (m + 31) / 32;
+  DevBuf raw;
+  const size_t nb = m / 5 + (m % 5 != 0);
+  if(b.bits.alloc((size_t)b.n_words * 4 + 16) != cudaSuccess || raw.alloc(nb + 16) != cudaSuccess) {
+    cudaGetLastError(); b.bits.free(); raw.free();
+    return fail(e, JFGPU_ERR_NOMEM, "Failed to allocate the Bloom counter in device memory");
+  }
+  CUDA_OK(e, cudaMemcpyAsync(raw.p, bytes, nb, cudaMemcpyHostToDevice, e->cs));
+  const int grid = (int)std::min<uint64_t>((b.n_words + 255) / 256, (uint64_t)e->n_sm * 16);
+  bloom_unpack_kernel<<<grid, 256, 0, e->cs>>>(raw.as<uint8_t>(), m, b.n_words, b.bits.as<uint32_t>()); JF_LAUNCHED();
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  raw.free();
+  b.M1 = jfb::gf2_matrix(64, 2 * e->k, c1); b.M2 = jfb::gf2_matrix(64, 2 * e->k, c2);
+  b.mode = BLOOM_CHECK;
+  return bloom_upload_matrices(e);
+}
+
+int jfgpu_bloom_dump(jfgpu_handle e, jfgpu_sink_fn sink, void* ctx) {
+  if(!e || !sink) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  BloomState& b = e->bloom;
+  if(b.mode != BLOOM_COUNT) return fail(e, JFGPU_ERR_STATE, "no Bloom counter has been built by this engine");
+  int rc = jfgpu_finish(e, nullptr);
+  if(rc) return rc;
+  const uint64_t nb = b.m / 5 + (b.m % 5 != 0);
+  const uint64_t piece = (uint64_t)64 << 20;
+  DevBuf out; uint8_t* hbuf = nullptr;
+  if(out.alloc(piece) != cudaSuccess || cudaHostAlloc((void**)&hbuf, piece, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError(); out.free();
+    return fail(e, JFGPU_ERR_NOMEM, "allocation of the Bloom counter staging buffers failed");
+  }
+  for(uint64_t off = 0; off < nb && !rc; off += piece) {
+    const uint64_t len = std::min(piece, nb - off);
+    const int grid = (int)std::min<uint64_t>((len + 255) / 256, (uint64_t)e->n_sm * 16);
+    // positions 5*off .. : the kernel takes the bit array shifted by whole words (5*off*2 bits; piece is a multiple of 16 bytes)
+    bloom_pack_kernel<<<grid, 256, 0, e->cs>>>(b.bits.as<uint32_t>() + (5 * off) / 16, b.m - 5 * off, len, out.as<uint8_t>()); JF_LAUNCHED();
+    cudaError_t c = cudaMemcpyAsync(hbuf, out.p, len, cudaMemcpyDeviceToHost, e->cs);
+    if(c == cudaSuccess) c = cudaStreamSynchronize(e->cs);
+    if(c != cudaSuccess) { rc = fail(e, JFGPU_ERR_CUDA, std::string("bloom dump: ") + cudaGetErrorString(c)); break; }
+    if(sink(ctx, hbuf, len) != 0) rc = fail(e, JFGPU_ERR_SINK, "dump sink failed");
+  }
+  cudaFreeHost(hbuf); out.free();
+  return rc;
 }
 
 uint64_t jfgpu_synth_fasta_bytes(uint64_t n_bases) {

@@ -74,7 +74,9 @@ __device__ __forceinline__ void squeeze(uint64_t& c, uint32_t& b, uint32_t del) 
   }
 }
 
-template<int KW, int SB, int MODE, int NTH>
+// FAST = the common geometry of the region-by-region path, everything in 32-bit arithmetic: one key word, the
+// 11-bit-table hash with at most two parity rows (tables of up to 2^34 slots), 4-byte records, a single shard.
+template<int KW, int SB, int MODE, int NTH, bool FAST>
 __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(const CountArgs a, const PartDev pd) {
   constexpr int WINB = NTH * 32;
   constexpr int TILEB = WINB - HALO;
@@ -85,6 +87,9 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15));
   uint32_t* st_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes);
   uint32_t* st_chunk = st_cnt + PMAX;
+  // byte tables of the two Bloom hash matrices, behind everything else
+  uint64_t* bl1 = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes + (MODE == 2 ? PMAX * 8 : 0));
+  uint64_t* bl2 = bl1 + a.nbytes * 256;
   const uint32_t* lut32 = reinterpret_cast<const uint32_t*>(lut);
   const uint64_t* rev64 = reinterpret_cast<const uint64_t*>(sm.rev);
 
@@ -93,14 +98,15 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   const uint64_t n = a.n;
 
   for(uint32_t i = tid; i < a.lut_bytes / 8; i += NTH) lut[i] = a.lut[i];
+  if(a.bloom.mode) for(uint32_t i = tid; i < a.nbytes * 256; i += NTH) { bl1[i] = a.bloom.lut1[i]; bl2[i] = a.bloom.lut2[i]; }
   uint32_t* my_chunk = MODE == 2 ? pd.cta_chunk + (size_t)blockIdx.x * pd.P : nullptr;
   uint32_t* my_fill  = MODE == 2 ? pd.cta_fill + (size_t)blockIdx.x * pd.P : nullptr;
   if(MODE == 2) {
     for(uint32_t p = tid; p < pd.P; p += NTH) {
       uint32_t c = my_chunk[p], f = my_fill[p];
       if(c == NO_CHUNK) {
-        c = atomicAdd(pd.pool_next, 1u); f = 0;
-        if(c >= pd.n_chunks) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); c = NO_CHUNK; f = pd.chunk_recs; }
+        c = alloc_chunk(pd, blockIdx.x); f = 0;
+        if(c == NO_CHUNK) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); f = pd.chunk_recs; }
       }
       st_chunk[p] = c; st_cnt[p] = f;
     }
@@ -125,6 +131,10 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   uint64_t t = blockIdx.x;
   if(t < a.n_tiles && tid == 0) issue(t);
 
+  // constants of the 32-bit tail (FAST)
+  const uint32_t f_rgb = pd.region_bits, f_hb = a.T.fbits - a.T.rbits, f_lsz = a.T.lsize;
+  const uint32_t f_relmask = f_rgb >= 32 ? 0xFFFFFFFFu : ((1u << f_rgb) - 1u);
+  const uint32_t f_p0lo = (uint32_t)a.prow[0], f_p0hi = (uint32_t)(a.prow[0] >> 32), f_p1lo = (uint32_t)a.prow[1], f_p1hi = (uint32_t)(a.prow[1] >> 32);
   // constants of the k-mer extraction
   const uint32_t kbits = 2 * k;
   const uint64_t kmask_lo = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1ull);
@@ -213,8 +223,17 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
     __syncthreads();
     { const uint64_t tn = t + gridDim.x; if(tn < a.n_tiles && tid == 0) issue(tn); }
     uint32_t entry = (t == 0) ? (a.format == 1 ? (a.carry_in->state & 3u) : a.carry_in->state) : (uint32_t)a.tile_state[t];
-    uint32_t wpre = FN_ID;
-    for(int i = 0; i < warp; ++i) wpre = fn_compose(wpre, sm.warp_fn[i]);
+    uint32_t wpre;
+    {   // composition of the functions of the warps in front of this one: every warp scans the NW partials itself
+      uint32_t g = lane < NW ? sm.warp_fn[lane] : FN_ID;
+#pragma unroll
+      for(int o = 1; o < NW; o <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, g, o);
+        if(lane >= o) g = fn_compose(up, g);
+      }
+      wpre = __shfl_sync(0xffffffffu, g, warp ? warp - 1 : 0);
+      if(warp == 0) wpre = FN_ID;
+    }
     uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
     if(lane == 0) excl = FN_ID;
     const uint32_t st_in = fn_apply(fn_compose(wpre, excl), entry);
@@ -289,8 +308,17 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
     if(lane == 31) sm.warp_cnt[warp] = cinc;
     if(tid == 0) sm.halo_break = 0;
     __syncthreads();
-    uint32_t woff = 0;
-    for(int i = 0; i < warp; ++i) woff += sm.warp_cnt[i];
+    uint32_t woff;
+    {
+      uint32_t g = lane < NW ? sm.warp_cnt[lane] : 0u;
+#pragma unroll
+      for(int o = 1; o < NW; o <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, g, o);
+        if(lane >= o) g += up;
+      }
+      woff = __shfl_sync(0xffffffffu, g, warp ? warp - 1 : 0);
+      if(warp == 0) woff = 0;
+    }
     const uint32_t off = woff + cinc - cnt;
     if(tid == HALO / 32) sm.idx0 = off;                // symbols emitted by the halo bytes
     if(tid == NTH - 1) sm.nsym = off + cnt;
@@ -443,6 +471,31 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
           }
 #pragma unroll
           for(int q = 0; q < KW; ++q) key[q] = use_rc ? rc[q] : m[q];
+          if(a.bloom.mode) {
+            const uint64_t h1 = gf2_hash<KW>(bl1, key, (int)a.nbytes), h2 = gf2_hash<KW>(bl2, key, (int)a.nbytes);
+            if(a.bloom.mode == BLOOM_COUNT) { bloom_count(a.bloom, h1, h2); ls.inserted++; continue; }   // `jellyfish bc`: no table
+            if(a.bloom.mode == BLOOM_FILTER ? !bloom_test_and_set(a.bloom, h1, h2) : !bloom_check(a.bloom, h1, h2)) continue;
+          }
+          if(FAST) {
+            // hash position: low 32 bits from four 11-bit tables, bits 32 and 33 from two parity rows (zero rows when unused)
+            const uint32_t klo = (uint32_t)key[0], khi = (uint32_t)(key[0] >> 32);
+            const uint32_t h32 = lut32[klo & 2047u] ^ lut32[2048 + ((klo >> 11) & 2047u)] ^
+                                 lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + (khi >> 1)];
+            const uint32_t ext = (__popc((klo & f_p0lo) ^ (khi & f_p0hi)) & 1u) | ((__popc((klo & f_p1lo) ^ (khi & f_p1hi)) & 1u) << 1);
+            const uint32_t p = (h32 >> f_rgb) | (ext << (32 - f_rgb));       // region
+            const uint32_t high = (uint32_t)(key[0] >> f_lsz);               // explicit key bits (f_hb of them)
+            const uint32_t rec = ((h32 & f_relmask) << f_hb) | high;
+            const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
+            if(slot < pd.chunk_recs) reinterpret_cast<uint32_t*>(pd.pool + (size_t)st_chunk[p] * CHUNK_BYTES)[slot] = rec;
+            else {             // this region's chunk filled up within one window (skewed input): direct insertion later
+              const uint64_t pos = (uint64_t)h32 | ((uint64_t)ext << 32);
+              unsigned long long at = atomicAdd(pd.spill_n, 1ull);
+              if(at < pd.spill_cap) { pd.spill_keys[at] = key[0]; pd.spill_counts[at] = 1; }
+              else if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;
+              else { ls.failed++; record_failure<KW>(a.T, key, 1); }
+            }
+            continue;
+          }
           uint64_t pos;
           if(KW == 1 && a.hash_fast) {
             const uint64_t kk = key[0];
@@ -505,8 +558,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
         if(c + pd.margin > pd.chunk_recs) {
           const uint32_t old = st_chunk[p];
           if(old != NO_CHUNK) pd.dir[old] = make_uint2(p, min(c, pd.chunk_recs));
-          uint32_t nc = atomicAdd(pd.pool_next, 1u);
-          if(nc >= pd.n_chunks) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
+          uint32_t nc = alloc_chunk(pd, blockIdx.x);
+          if(nc == NO_CHUNK) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
           else { st_chunk[p] = nc; st_cnt[p] = 0; }
         }
       }

@@ -192,7 +192,34 @@ struct CountArgs {
   uint32_t       lut_bytes;     // bytes of hash tables to stage in shared memory
   uint32_t       format;        // 0 = FASTA, 1 = FASTQ (4-line records)
   uint64_t       prow[8];
+  BloomDev       bloom;         // filter in front of the table (mode BLOOM_NONE: nothing)
 };
+
+// the Bloom counter as `jellyfish bc` writes it (bloom_counter2.hpp:34-36: five base-3 digits per byte) from the two-bit form
+__global__ void __launch_bounds__(256) bloom_pack_kernel(const uint32_t* __restrict__ bits, uint64_t m, uint64_t n_bytes, uint8_t* __restrict__ out) {
+  for(uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_bytes; j += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0, pw = 1;
+    for(uint32_t i = 0; i < 5; ++i, pw *= 3) {
+      const uint64_t pos = 5 * j + i;
+      if(pos < m) { const uint32_t f = (bits[pos >> 4] >> ((pos & 15u) * 2u)) & 3u; v += ((f & 1u) + (f >> 1)) * pw; }
+    }
+    out[j] = (uint8_t)v;
+  }
+}
+// ... and the "digit is 2" bitmap of a loaded counter (count --bc)
+__global__ void __launch_bounds__(256) bloom_unpack_kernel(const uint8_t* __restrict__ bytes, uint64_t m, uint64_t n_words, uint32_t* __restrict__ out) {
+  for(uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t x = 0;
+    for(uint32_t b = 0; b < 32; ++b) {
+      const uint64_t pos = 32 * w + b;
+      if(pos >= m) break;
+      uint32_t v = bytes[pos / 5];
+      for(uint32_t q = (uint32_t)(pos % 5); q; --q) v /= 3;
+      if(v % 3 == 2) x |= 1u << b;
+    }
+    out[w] = x;
+  }
+}
 
 // Slow path: walk backwards from byte position `end` (exclusive) of the batch collecting
 // the symbols emitted before it, newest first, until `need` symbols or a reset is found.
@@ -284,7 +311,6 @@ __device__ void backfill_fastq(const uint8_t* in, uint64_t n, const Carry* cin, 
 constexpr int PMAX        = 2048;          // partitions (table regions) at most
 constexpr int CHUNK_BYTES = 8192;          // granule of the record pool
 constexpr uint32_t NO_CHUNK = 0xFFFFFFFFu;
-constexpr int SUBROUNDS   = 1;
 
 struct PartDev {
   uint32_t  P;              // number of regions (power of two)
@@ -296,8 +322,11 @@ struct PartDev {
   uint32_t  n_chunks;       // chunks in the pool
   uint32_t  stage_bytes;    // shared-memory staging bytes per CTA
   uint32_t  margin;         // a chunk is closed once fewer than `margin` free records remain
+  uint32_t  arena_chunks;   // the pool is cut into one arena of this many chunks per CTA of the staging kernels: a CTA's open
+                            // chunks then lie within a few MB of each other (its own TLB reach) whatever the other CTAs do
   uint8_t*  pool;
-  unsigned int* pool_next;  // allocation cursor
+  unsigned int* pool_next;  // allocation cursor of every arena
+  unsigned int* n_units;    // chunks listed in `order` (written by chunk_scan_kernel)
   uint2*    dir;            // per chunk: { region, records } written when the chunk is closed
   uint32_t* cta_chunk;      // [grid][P] open chunk of each CTA for each region
   uint32_t* cta_fill;       // [grid][P] records already in it
@@ -307,16 +336,15 @@ struct PartDev {
   uint64_t  spill_cap;
 };
 
-template<int NTH>
-struct __align__(16) CountSmemT {
-  uint8_t  win[NTH * 32];            // TMA destination
-  uint8_t  sym[PRE + NTH * 32 + 16]; // carried prefix + compacted symbols of the window
-  uint64_t bar;
-  uint32_t warp_fn[NTH / 32];
-  uint32_t warp_cnt[NTH / 32];
-  uint32_t idx0, nsym, halo_break, total_state;
-  unsigned long long part[NTH / 32][4];
-};
+// take a fresh chunk from this CTA's arena; NO_CHUNK when the arena is exhausted
+__device__ __forceinline__ uint32_t alloc_chunk(const PartDev& pd, uint32_t arena) {
+  const uint32_t local = atomicAdd(&pd.pool_next[arena], 1u);
+  return local < pd.arena_chunks ? arena * pd.arena_chunks + local : NO_CHUNK;
+}
+__device__ __forceinline__ bool chunk_in_use(const PartDev& pd, uint32_t i) {
+  const uint32_t a = i / pd.arena_chunks;
+  return i - a * pd.arena_chunks < pd.pool_next[a];
+}
 
 __device__ __forceinline__ void store_rec(uint8_t* base, uint32_t rec_bytes, uint64_t idx, u128 r) {
   if(rec_bytes == 4) reinterpret_cast<uint32_t*>(base)[idx] = (uint32_t)r.lo;
@@ -331,381 +359,6 @@ __device__ __forceinline__ u128 load_rec(const uint8_t* base, uint32_t rec_bytes
   return r;
 }
 
-template<int KW, int SB, int MODE, int NTH>
-__global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) count_kernel(const CountArgs a, const PartDev pd) {
-  constexpr int WINB = NTH * 32;
-  constexpr int TILEB = WINB - HALO;
-  constexpr int NW = NTH / 32;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  CountSmemT<NTH>& sm = *reinterpret_cast<CountSmemT<NTH>*>(smem_raw);
-  uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(CountSmemT<NTH>) + 15) & ~(size_t)15));
-  // MODE 2 only, behind the hash tables: per region, fill count and id of this CTA's open chunk
-  uint32_t* st_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes);
-  uint32_t* st_chunk = st_cnt + PMAX;
-  const uint32_t* lut32 = reinterpret_cast<const uint32_t*>(lut);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t k = a.k;
-  const uint64_t n = a.n;
-
-  for(uint32_t i = tid; i < a.lut_bytes / 8; i += NTH) lut[i] = a.lut[i];
-  uint32_t* my_chunk = MODE == 2 ? pd.cta_chunk + (size_t)blockIdx.x * pd.P : nullptr;
-  uint32_t* my_fill  = MODE == 2 ? pd.cta_fill + (size_t)blockIdx.x * pd.P : nullptr;
-  if(MODE == 2) {
-    // every (CTA, region) pair always owns an open chunk: records are appended to it straight
-    // from the k-mer threads (a shared-memory counter hands out the slots)
-    for(uint32_t p = tid; p < pd.P; p += NTH) {
-      uint32_t c = my_chunk[p], f = my_fill[p];
-      if(c == NO_CHUNK) {
-        c = atomicAdd(pd.pool_next, 1u); f = 0;
-        if(c >= pd.n_chunks) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); c = NO_CHUNK; f = pd.chunk_recs; }
-      }
-      st_chunk[p] = c; st_cnt[p] = f;
-    }
-  }
-  if(tid == 0) mbar_init(&sm.bar, 1);
-  __syncthreads();
-
-  auto issue = [&](uint64_t t) {       // TMA copy of window t (thread 0 only)
-    long long h = (long long)(t * (uint64_t)TILEB) - HALO;
-    long long from = h < 0 ? 0 : h;
-    uint64_t avail = n - (uint64_t)from;
-    uint64_t want = (uint64_t)((h + WINB) - from);
-    uint32_t bytes = (uint32_t)((avail < want ? avail : want) & ~(uint64_t)15);
-    if(bytes) { mbar_expect_tx(&sm.bar, bytes); tma_load_1d(&sm.win[from - h], a.in + from, bytes, &sm.bar); }
-    else mbar_arrive(&sm.bar);
-  };
-  // chunk roll-over (MODE 2): a chunk that may overflow during the next iteration is closed
-  // (its record count goes to the directory) and a fresh one is taken from the pool
-  auto rollover_pass = [&]() {
-    __syncthreads();
-    for(uint32_t p = tid; p < pd.P; p += NTH) {
-      const uint32_t c = st_cnt[p];
-      if(c + pd.margin > pd.chunk_recs) {
-        const uint32_t old = st_chunk[p];
-        if(old != NO_CHUNK) pd.dir[old] = make_uint2(p, min(c, pd.chunk_recs));
-        uint32_t nc = atomicAdd(pd.pool_next, 1u);
-        if(nc >= pd.n_chunks) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
-        else { st_chunk[p] = nc; st_cnt[p] = 0; }
-      }
-    }
-    __syncthreads();
-  };
-
-  LocalStats ls = { 0, 0, 0, 0, 0 };
-  uint32_t phase = 0, since_roll = 0;
-  uint64_t t = blockIdx.x;
-  if(t < a.n_tiles && tid == 0) issue(t);
-
-  const uint64_t kmask_hi = (k * 2) % 64 ? ((1ull << ((k * 2) % 64)) - 1ull) : ~0ull;   // mask of the top key word
-  for(; t < a.n_tiles; t += gridDim.x) {
-    const long long h = (long long)(t * (uint64_t)TILEB) - HALO;      // global position of window byte 0
-    const long long wend_ll = (long long)n < h + WINB ? (long long)n : h + WINB;
-    {   // tail bytes that the 16-byte granular TMA copy left out
-      long long from = h < 0 ? 0 : h;
-      long long copied = ((wend_ll - from) & ~15ll);
-      long long g = from + copied + tid;
-      if(tid < 16 && g < wend_ll) sm.win[g - h] = a.in[g];
-    }
-    mbar_wait(&sm.bar, phase);
-    phase ^= 1;
-    __syncthreads();
-
-    // ---- phase B: 32 bytes per thread into registers, state transition function ----
-    uint32_t w[8];
-    {
-      const uint4* p4 = reinterpret_cast<const uint4*>(sm.win + tid * 32);
-      uint4 x0 = p4[0], x1 = p4[1];
-      w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
-    }
-    const long long g0 = h + (long long)tid * 32;       // global position of this thread's first byte
-    int vlo = g0 < 0 ? (int)(-g0 < 32 ? -g0 : 32) : 0;
-    int vhi = (wend_ll - g0) < 0 ? 0 : ((wend_ll - g0) > 32 ? 32 : (int)(wend_ll - g0));
-    if(vhi < vlo) vhi = vlo;
-
-    // FASTQ needs to know whether a thread's first byte starts a line: remember the byte before it
-    // now, while the window buffer is still intact (it is refilled right after the next barrier)
-    uint32_t prevb = 'x';
-    if(a.format == 1 && vhi > vlo) {
-      const long long gp = g0 + vlo - 1;
-      if(gp < 0) prevb = (a.carry_in->state & 4u) ? '\n' : 'x';
-      else if(tid * 32 + vlo - 1 >= 0) prevb = sm.win[tid * 32 + vlo - 1];
-      else prevb = a.in[gp];
-    }
-    uint32_t f;
-    if(a.format == 1) {
-      uint32_t nnl = 0;
-#pragma unroll
-      for(int i = 0; i < 32; ++i)
-        if(i >= vlo && i < vhi) nnl += (((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu) == '\n');
-      f = fn_rot(nnl);
-    } else {
-      uint32_t st = ST_L; bool seen_nl = false;
-#pragma unroll
-      for(int i = 0; i < 32; ++i) {
-        if(i >= vlo && i < vhi) {
-          uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-          if(b == '\n') { st = ST_L; seen_nl = true; }
-          else if(st == ST_L && b != '\r') st = (b == '>') ? ST_H : ST_S;
-        }
-      }
-      f = seen_nl ? fn_const(st) : ((uint32_t)ST_H | ((uint32_t)ST_S << 2) | (st << 4) | (3u << 6));
-      if(vhi == vlo) f = FN_ID;
-    }
-    uint32_t inc = f;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1) {
-      uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-      if(lane >= o) inc = fn_compose(up, inc);
-    }
-    if(lane == 31) sm.warp_fn[warp] = inc;
-    __syncthreads();
-    // every thread holds its bytes: the window buffer is free, fetch the next window now
-    { const uint64_t tn = t + gridDim.x; if(tn < a.n_tiles && tid == 0) issue(tn); }
-    uint32_t entry = (t == 0) ? (a.format == 1 ? (a.carry_in->state & 3u) : a.carry_in->state) : (uint32_t)a.tile_state[t];
-    uint32_t wpre = FN_ID;
-    for(int i = 0; i < warp; ++i) wpre = fn_compose(wpre, sm.warp_fn[i]);
-    uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
-    if(lane == 0) excl = FN_ID;
-    uint32_t st_in = fn_apply(fn_compose(wpre, excl), entry);
-    if(tid == NTH - 1) sm.total_state = fn_apply(fn_compose(wpre, inc), entry);
-
-    // ---- phase C: emit symbols (4 bits each, 32 max) ----
-    uint64_t pk0 = 0, pk1 = 0;
-    uint32_t cnt = 0; bool brk = false;
-    if(a.format == 1) {
-      // FASTQ, 4-line records (mer_overlap_sequence_parser.hpp:187-217): only sequence lines emit
-      // symbols; the start of a header line emits the window reset ('N' between reads, :205);
-      // '@' / '+' at the line starts are verified (else "Invalid fastq sequence", :304-306)
-      uint32_t ty = st_in; bool at_start = prevb == '\n';
-#pragma unroll
-      for(int i = 0; i < 32; ++i) {
-        if(i >= vlo && i < vhi) {
-          uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-          uint32_t sy = 8;
-          if(b == '\n') { ty = (ty + 1) & 3u; at_start = true; }
-          else {
-            if(at_start && b != '\r') {
-              at_start = false;
-              if(ty == 0) { sy = SYM_BREAK; if(b != '@') atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull); }
-              else if(ty == 2 && b != '+') atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull);
-            }
-            if(ty == 1) {
-              if(b == '\r') { if(!cr_dropped(a.in, (uint64_t)(g0 + i), a.n_look)) sy = SYM_BREAK; }
-              else sy = base_symbol(b);
-            }
-          }
-          if(sy != 8) {
-            if(cnt < 16) pk0 |= (uint64_t)sy << (4 * cnt); else pk1 |= (uint64_t)sy << (4 * (cnt - 16));
-            brk |= (sy == SYM_BREAK);
-            ++cnt;
-          }
-        }
-      }
-    } else {
-      uint32_t st = st_in;
-#pragma unroll
-      for(int i = 0; i < 32; ++i) {
-        if(i >= vlo && i < vhi) {
-          uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-          uint32_t sy = 8;   // 8 = nothing
-          if(st == ST_H) { if(b == '\n') st = ST_L; }
-          else if(b == '\n') st = ST_L;
-          else if(st == ST_L) {
-            if(b == '\r') { }
-            else if(b == '>') { st = ST_H; sy = SYM_BREAK; }
-            else { st = ST_S; sy = base_symbol(b); }
-          } else {           // ST_S
-            if(b == '\r') { if(!cr_dropped(a.in, (uint64_t)(g0 + i), a.n_look)) sy = SYM_BREAK; }
-            else sy = base_symbol(b);
-          }
-          if(sy != 8) {
-            if(cnt < 16) pk0 |= (uint64_t)sy << (4 * cnt); else pk1 |= (uint64_t)sy << (4 * (cnt - 16));
-            brk |= (sy == SYM_BREAK);
-            ++cnt;
-          }
-        }
-      }
-    }
-    uint32_t cinc = cnt;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1) {
-      uint32_t up = __shfl_up_sync(0xffffffffu, cinc, o);
-      if(lane >= o) cinc += up;
-    }
-    if(lane == 31) sm.warp_cnt[warp] = cinc;
-    if(tid == 0) sm.halo_break = 0;
-    __syncthreads();
-    uint32_t woff = 0;
-    for(int i = 0; i < warp; ++i) woff += sm.warp_cnt[i];
-    const uint32_t off = woff + cinc - cnt;
-    if(tid == HALO / 32) sm.idx0 = off;                // symbols emitted by the halo bytes
-    if(tid == NTH - 1) sm.nsym = off + cnt;
-    if(tid < HALO / 32 && brk) sm.halo_break = 1;
-    {
-      uint8_t* dst = sm.sym + PRE + off;
-      for(uint32_t j = 0; j < cnt; ++j) {
-        uint32_t sy = (uint32_t)((j < 16 ? pk0 >> (4 * j) : pk1 >> (4 * (j - 16))) & 0xF);
-        dst[j] = (uint8_t)sy;
-      }
-    }
-    __syncthreads();
-    const uint32_t idx0 = sm.idx0, nsym = sm.nsym;
-
-    // ---- phase D: the k-1 symbols that precede the window ----
-    if(warp == 0) {
-      if(t == 0) {
-        sm.sym[lane] = a.carry_in->sym[lane]; sm.sym[lane + 32] = a.carry_in->sym[lane + 32];
-      } else {
-        sm.sym[lane] = SYM_BREAK; sm.sym[lane + 32] = SYM_BREAK;
-        __syncwarp();
-        const bool in_seq = a.format == 1 ? (a.tile_state[t] == 1) : (a.tile_state[t] != ST_H);
-        if(lane == 0 && in_seq && idx0 < k - 1 && !sm.halo_break) {
-          // pathological input (very short lines / long runs of blank lines): exact slow path
-          if(a.format == 1) backfill_fastq(a.in, a.n_look, a.carry_in, h, PRE, sm.sym);
-          else backfill_symbols(a.in, a.n_look, a.carry_in, h, -2, PRE, sm.sym);
-        }
-      }
-    }
-    __syncthreads();
-
-    // hand the parser state to the next batch
-    if(t == a.n_tiles - 1 && warp == 1) {
-      uint8_t* cs = a.carry_out->sym;
-      const bool not_seq = a.format == 1 ? (a.tile_state[t] != 1) : (a.tile_state[t] == ST_H);
-      if(nsym >= (uint32_t)PRE || t == 0 || sm.halo_break || not_seq) {
-        cs[lane] = sm.sym[nsym + lane]; cs[lane + 32] = sm.sym[nsym + lane + 32];
-      } else if(lane == 0) {
-        if(a.format == 1) backfill_fastq(a.in, a.n_look, a.carry_in, (long long)n, PRE, cs);
-        else backfill_symbols(a.in, a.n_look, a.carry_in, (long long)n, -2, PRE, cs);
-      }
-      // FASTQ carries the line type plus "the batch ended right after a newline" (bit 2)
-      if(lane == 0) a.carry_out->state = a.format == 1 ? (sm.total_state | (a.in[n - 1] == '\n' ? 4u : 0u)) : sm.total_state;
-    }
-
-    // ---- phase E: roll canonical k-mers over the compacted symbols, hash, insert / stage ----
-    const uint32_t n_chunks = nsym > idx0 ? (nsym - idx0 + QSYM - 1) / QSYM : 0;
-    const uint32_t iters = (n_chunks + NTH - 1) / NTH;      // identical for every thread (block-wide flushes)
-    for(uint32_t it = 0; it < iters; ++it) {
-      const uint32_t c = it * NTH + tid;
-      const bool active = c < n_chunks;
-      const uint32_t j0 = idx0 + c * QSYM;
-      const uint32_t j1 = active ? min(nsym, j0 + (uint32_t)QSYM) : j0;
-      uint64_t m[KW], rc[KW];
-#pragma unroll
-      for(int q = 0; q < KW; ++q) { m[q] = 0; rc[q] = 0; }
-      uint32_t run = 0;
-      const uint8_t* sp = sm.sym + PRE + j0 - (k - 1);
-      const uint32_t total = active ? (k - 1) + (j1 - j0) : 0;
-      uint32_t j = 0;
-#pragma unroll 1
-      for(int round = 0; round < (MODE == 2 ? SUBROUNDS : 1); ++round) {
-        const uint32_t stop = (MODE == 2 && round < SUBROUNDS - 1) ? min(total, (k - 1) + (round + 1) * (QSYM / SUBROUNDS)) : total;
-        for(; j < stop; ++j) {
-          const uint32_t sy = sp[j];
-          if(sy < 4) {
-            // m = (m << 2 | sy) & mask ; rc = rc >> 2 | (3 - sy) << (2k - 2)   (mer_dna.hpp:322-370)
-            if(KW == 1) {
-              m[0] = ((m[0] << 2) | sy) & kmask_hi;
-              rc[0] = (rc[0] >> 2) | ((uint64_t)(3 - sy) << (2 * k - 2));
-            } else {
-              m[KW - 1] = ((m[KW - 1] << 2) | (m[0] >> 62)) & kmask_hi;
-              m[0] = (m[0] << 2) | sy;
-              rc[0] = (rc[0] >> 2) | (rc[KW - 1] << 62);
-              rc[KW - 1] = (rc[KW - 1] >> 2) | ((uint64_t)(3 - sy) << ((2 * k - 2) - 64));
-            }
-            ++run;
-          } else run = 0;
-          if(j >= k - 1 && run >= k) {
-            uint64_t key[KW];
-            bool use_rc = false;
-            if(a.canonical) {
-              if(KW == 1) use_rc = rc[0] < m[0];
-              else use_rc = (rc[KW - 1] < m[KW - 1]) || (rc[KW - 1] == m[KW - 1] && rc[0] < m[0]);
-            }
-#pragma unroll
-            for(int q = 0; q < KW; ++q) key[q] = use_rc ? rc[q] : m[q];
-            ls.kmers++;
-            uint64_t pos;
-            if(KW == 1 && a.hash_fast) {
-              const uint64_t kk = key[0];
-              uint32_t h32 = lut32[(uint32_t)kk & 2047u] ^ lut32[2048 + ((uint32_t)(kk >> 11) & 2047u)] ^
-                             lut32[4096 + ((uint32_t)(kk >> 22) & 2047u)] ^ lut32[6144 + (uint32_t)(kk >> 33)];
-              pos = h32;
-              for(uint32_t jb = 0; jb < a.n_prow; ++jb) pos |= (uint64_t)(__popcll(kk & a.prow[jb]) & 1) << (32 + jb);
-            } else pos = gf2_hash<KW>(lut, key, (int)a.nbytes);
-            if(MODE == 0) {
-              if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;
-              else { ls.failed++; record_failure<KW>(a.T, key, 1); }
-            } else if(MODE == 1) {
-              const uint32_t owner = a.shard_bits ? (uint32_t)(pos >> (a.T.lsize - a.shard_bits)) : 0u;
-              // warp-aggregated reservation: one atomic per (warp, owner) instead of one per k-mer
-              const uint32_t peers = __match_any_sync(__activemask(), owner);
-              const uint32_t leader = __ffs(peers) - 1;
-              unsigned long long at = 0;
-              if((uint32_t)lane == leader) at = atomicAdd(&a.route_counts[owner], (unsigned long long)__popc(peers));
-              at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
-              if(at < a.route_cap) {
-#pragma unroll
-                for(int q = 0; q < KW; ++q) a.route_keys[((uint64_t)owner * a.route_cap + at) * KW + q] = key[q];
-              } else atomicAdd(&a.T.stats[STAT_ROUTE_DROPPED], 1ull);
-            } else {
-              // record = (position inside the region << hb) | explicit key bits
-              const uint64_t lpos = pos & a.T.local_mask;
-              const uint32_t p = (uint32_t)(lpos >> pd.region_bits);
-              const uint64_t rel = lpos & ((1ull << pd.region_bits) - 1ull);
-              const u128 high = key_high<KW>(key, a.T.lsize);
-              const uint32_t hb = a.T.fbits - a.T.rbits;
-              u128 rec;
-              if(hb == 0)       { rec.lo = rel; rec.hi = 0; }
-              else if(hb < 64)  { rec.lo = high.lo | (rel << hb); rec.hi = high.hi | (rel >> (64 - hb)); }
-              else              { rec.lo = high.lo; rec.hi = high.hi | (rel << (hb - 64)); }
-              const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
-              if(slot < pd.chunk_recs) {
-                uint8_t* dst = pd.pool + (size_t)st_chunk[p] * CHUNK_BYTES;
-                if(pd.rec_bytes == 4) reinterpret_cast<uint32_t*>(dst)[slot] = (uint32_t)rec.lo;
-                else if(pd.rec_bytes == 8) reinterpret_cast<uint64_t*>(dst)[slot] = rec.lo;
-                else { reinterpret_cast<uint64_t*>(dst)[2 * slot] = rec.lo; reinterpret_cast<uint64_t*>(dst)[2 * slot + 1] = rec.hi; }
-              }
-              else {           // this region's chunk filled up within one iteration (skewed input): direct insertion later
-                unsigned long long at = atomicAdd(pd.spill_n, 1ull);
-                if(at < pd.spill_cap) {
-#pragma unroll
-                  for(int q = 0; q < KW; ++q) pd.spill_keys[at * KW + q] = key[q];
-                  pd.spill_counts[at] = 1;
-                } else if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;   // spill list full too: insert right here
-                else { ls.failed++; record_failure<KW>(a.T, key, 1); }
-              }
-            }
-          }
-        }
-      }
-      if(MODE == 2 && ((++since_roll) & 1) == 0) rollover_pass();
-    }
-    __syncthreads();     // all reads of sym[] done before the next window overwrites it
-  }
-  if(MODE == 2) {          // keep the open chunks for the next launch
-    __syncthreads();
-    for(uint32_t p = tid; p < pd.P; p += NTH) { my_chunk[p] = st_chunk[p]; my_fill[p] = min(st_cnt[p], pd.chunk_recs); }
-  }
-
-  // ---- statistics: one atomic per counter per CTA ----
-  unsigned long long v[4] = { ls.kmers, ls.inserted, ls.distinct, ls.reprobes };
-#pragma unroll
-  for(int q = 0; q < 4; ++q) {
-#pragma unroll
-    for(int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
-  }
-  if(lane == 0) { sm.part[warp][0] = v[0]; sm.part[warp][1] = v[1]; sm.part[warp][2] = v[2]; sm.part[warp][3] = v[3]; }
-  __syncthreads();
-  if(tid < 4) {
-    unsigned long long s = 0;
-    for(int i = 0; i < NW; ++i) s += sm.part[i][tid];
-    const int which = tid == 0 ? STAT_KMERS : tid == 1 ? STAT_INSERTED : tid == 2 ? STAT_DISTINCT : STAT_REPROBES;
-    if(s) atomicAdd(&a.T.stats[which], s);
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // K1b: partitioned insertion.  Chunks are visited region by region (order[] lists the chunk
 //      ids sorted by region), every CTA pulling the next chunk from a shared cursor, so that at
@@ -718,20 +371,21 @@ __global__ void close_chunks_kernel(PartDev pd, uint32_t n_cta) {
   }
 }
 __global__ void chunk_hist_kernel(PartDev pd, uint32_t* __restrict__ hist) {
-  const uint32_t n = min(*pd.pool_next, pd.n_chunks);
-  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&hist[pd.dir[i].x], 1u);
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n_chunks; i += gridDim.x * blockDim.x)
+    if(chunk_in_use(pd, i)) atomicAdd(&hist[pd.dir[i].x], 1u);
 }
-__global__ void __launch_bounds__(1024) chunk_scan_kernel(uint32_t P, const uint32_t* __restrict__ hist, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor) {
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(uint32_t P, const uint32_t* __restrict__ hist, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                                          unsigned int* __restrict__ n_units) {
   __shared__ uint32_t s[PMAX];
   for(uint32_t p = threadIdx.x; p < P; p += blockDim.x) s[p] = hist[p];
   __syncthreads();
-  if(threadIdx.x == 0) { uint32_t run = 0; for(uint32_t p = 0; p < P; ++p) { uint32_t x = s[p]; s[p] = run; run += x; } }
+  if(threadIdx.x == 0) { uint32_t run = 0; for(uint32_t p = 0; p < P; ++p) { uint32_t x = s[p]; s[p] = run; run += x; } *n_units = run; }
   __syncthreads();
   for(uint32_t p = threadIdx.x; p < P; p += blockDim.x) { start[p] = s[p]; cursor[p] = s[p]; }
 }
 __global__ void chunk_scatter_kernel(PartDev pd, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-  const uint32_t n = min(*pd.pool_next, pd.n_chunks);
-  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) order[atomicAdd(&cursor[pd.dir[i].x], 1u)] = i;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n_chunks; i += gridDim.x * blockDim.x)
+    if(chunk_in_use(pd, i)) order[atomicAdd(&cursor[pd.dir[i].x], 1u)] = i;
 }
 
 // A warp works on one 512-byte piece of a chunk at a time (32 lanes x one 128-bit streaming
@@ -748,7 +402,7 @@ template<int KW, int SB>
 __global__ void __launch_bounds__(512, 2) insert_chunks_kernel(TableDev T, PartDev pd, const uint32_t* __restrict__ order,
                                                                 unsigned int* __restrict__ piece_cursor, uint32_t from, uint32_t upto,
                                                                 const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
-  const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
+  const uint32_t n_units = min(*pd.n_units, upto);
   const uint32_t hb = T.fbits - T.rbits;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t per16 = 16 / pd.rec_bytes;                         // records per 16 bytes: 4, 2 or 1
@@ -853,8 +507,8 @@ __global__ void __launch_bounds__(1024, 1) stage_keys_kernel(TableDev T, PartDev
   for(uint32_t p = tid; p < pd.P; p += blockDim.x) {
     uint32_t c = my_chunk[p], f = my_fill[p];
     if(c == NO_CHUNK) {
-      c = atomicAdd(pd.pool_next, 1u); f = 0;
-      if(c >= pd.n_chunks) { atomicAdd(&T.stats[STAT_POOL_FULL], 1ull); c = NO_CHUNK; f = pd.chunk_recs; }
+      c = alloc_chunk(pd, blockIdx.x); f = 0;
+      if(c == NO_CHUNK) { atomicAdd(&T.stats[STAT_POOL_FULL], 1ull); f = pd.chunk_recs; }
     }
     st_chunk[p] = c; st_cnt[p] = f;
   }
@@ -901,8 +555,8 @@ __global__ void __launch_bounds__(1024, 1) stage_keys_kernel(TableDev T, PartDev
       if(c + pd.margin > pd.chunk_recs) {
         const uint32_t old = st_chunk[p];
         if(old != NO_CHUNK) pd.dir[old] = make_uint2(p, min(c, pd.chunk_recs));
-        uint32_t nc = atomicAdd(pd.pool_next, 1u);
-        if(nc >= pd.n_chunks) { atomicAdd(&T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
+        uint32_t nc = alloc_chunk(pd, blockIdx.x);
+        if(nc == NO_CHUNK) { atomicAdd(&T.stats[STAT_POOL_FULL], 1ull); st_chunk[p] = NO_CHUNK; st_cnt[p] = pd.chunk_recs; }
         else { st_chunk[p] = nc; st_cnt[p] = 0; }
       }
     }
@@ -973,7 +627,7 @@ template<int KW>
 __global__ void __launch_bounds__(768, 2) insert_chunks32_kernel(TableDev T, PartDev pd, const uint32_t* __restrict__ order,
                                                                    unsigned int* __restrict__ piece_cursor, uint32_t from, uint32_t upto,
                                                                    const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
-  const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
+  const uint32_t n_units = min(*pd.n_units, upto);
   const uint32_t fb = T.fbits, rb = T.rbits, hb = fb - rb;
   const uint32_t fmask = (1u << fb) - 1u, one = 1u << fb, cb = 32 - fb;
   const uint32_t hmask = hb ? ((1u << hb) - 1u) : 0u;
@@ -1061,7 +715,7 @@ __global__ void __launch_bounds__(512, 1) rehash_chunks_kernel(TableDev T, Table
   for(uint32_t i = threadIdx.x; i < nbytes * 256u; i += blockDim.x) { inv[i] = old_inv_g[i]; lut[i] = new_lut_g[i]; }
   __shared__ uint32_t s_unit;
   __syncthreads();
-  const uint32_t n_units = min(min(*pd.pool_next, pd.n_chunks), upto);
+  const uint32_t n_units = min(*pd.n_units, upto);
   const uint32_t hb = T0.fbits - T0.rbits;
   LocalStats ls = { 0, 0, 0, 0, 0 };
   for(;;) {

@@ -58,7 +58,8 @@ def canonical_int(v, k):
 class HashCounter(object):
     def __init__(self, size, val_len=7, k=None, canonical=False, reprobes=126, device=0,
                  shard_index=0, n_shards=1, allow_regrow=True, max_batch_bytes=0, matrix_skip=0,
-                 pool_bytes=0, no_partition=False, part_min_mb=0, k2_mode=0, region_mb=0):
+                 pool_bytes=0, no_partition=False, part_min_mb=0, k2_mode=0, region_mb=0, bf_size=0, bf_fp=0.0,
+                 bloom_counter=False):
         if k is None:
             raise ValueError("k (mer length) is required")
         self._lib = L.load()
@@ -70,6 +71,7 @@ class HashCounter(object):
         p.shard_index, p.n_shards, p.max_batch_bytes, p.matrix_skip = shard_index, n_shards, max_batch_bytes, matrix_skip
         p.pool_bytes, p.no_partition, p.part_min_mb = pool_bytes, int(bool(no_partition)), part_min_mb
         p.k2_mode, p.region_mb = k2_mode, region_mb
+        p.bf_size, p.bf_fp, p.bloom_counter = bf_size, bf_fp, int(bool(bloom_counter))
         rc = self._lib.jfgpu_create(C.byref(p), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()
@@ -203,6 +205,32 @@ class HashCounter(object):
         self._check(self._lib.jfgpu_histogram(self._h, hist, n_bins))
         return list(hist)
 
+    # -- Bloom structures (count --bf-size / --bc, `jellyfish bc`) ----------------------------------
+    def bloom_info(self):
+        bi = L.BloomInfo()
+        self._check(self._lib.jfgpu_bloom_info_get(self._h, C.byref(bi)))
+        d = {"mode": bi.mode, "nb_hashes": bi.nb_hashes, "m": bi.m, "nb_bytes": bi.nb_bytes}
+        if bi.mode:
+            d["matrix1"] = [bi.matrix1[i] for i in range(bi.matrix_c)]
+            d["matrix2"] = [bi.matrix2[i] for i in range(bi.matrix_c)]
+        return d
+
+    def load_bloom_counter(self, path):
+        """count --bc FILE (count_main.cc:191-206): filter by a Bloom counter written by `jellyfish bc`."""
+        with open(path, "rb") as f:
+            data = f.read()
+        hlen = int(data[:9])
+        hdr = json.loads(data[9:9 + hlen].rstrip(b"\0").decode())
+        if hdr.get("format") != "bloomcounter":
+            raise JellyfishError(L.ERR_FORMAT, "Invalid format '%s'. Expected 'bloomcounter'" % hdr.get("format"))
+        if hdr["key_len"] != 2 * self.k:
+            raise JellyfishError(L.ERR_ARG, "Invalid mer length in bloom filter")
+        body = data[9 + hlen:]
+        c = 2 * self.k
+        m1 = (C.c_uint64 * c)(*hdr["matrix1"]["columns"])
+        m2 = (C.c_uint64 * c)(*hdr["matrix2"]["columns"])
+        self._check(self._lib.jfgpu_bloom_load(self._h, hdr["size"], hdr["nb_hashes"], m1, m2, body, len(body)))
+
     # -- dumper ------------------------------------------------------------------------------
     def dump_records(self, lower=0, upper=UINT64_MAX, out_counter_len=4, sink=None):
         """Sorted (position, key) record stream of this shard; returns bytes when no sink is given."""
@@ -242,6 +270,58 @@ class HashCounter(object):
         with open(path, "wb") as f:
             write_header(f, self.header(out_counter_len, cmdline))
             return self.dump_records(lower, upper, out_counter_len, sink=f.write)
+
+
+class BloomCounter(object):
+    """`jellyfish bc` (sub_commands/bc_main.cc): a Bloom counter of the k-mers of some text, built on the device."""
+
+    def __init__(self, size, fpr=0.001, k=None, canonical=False, device=0, max_batch_bytes=0):
+        self.hc = HashCounter(1, 7, k=k, canonical=canonical, device=device, bf_size=size, bf_fp=fpr, bloom_counter=True,
+                              max_batch_bytes=max_batch_bytes)
+        self.k, self.canonical = k, bool(canonical)
+
+    def close(self):
+        self.hc.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def add_files(self, paths):
+        self.hc.add_files(paths)
+
+    def add_text(self, data, begin=True, end=True):
+        self.hc.add_text(data, begin=begin, end=end)
+
+    def info(self):
+        return self.hc.bloom_info()
+
+    def header(self, cmdline=()):
+        bi = self.info()
+        sde = os.environ.get("SOURCE_DATE_EPOCH")
+
+        def mat(cols):
+            return {"r": 64, "c": 2 * self.k, "identity": False, "columns": cols}
+        return {
+            "alignment": 8, "canonical": self.canonical, "cmdline": list(cmdline), "exe_path": os.path.realpath(L.LIB_PATH),
+            "format": "bloomcounter", "hostname": "hostname" if sde else os.uname().nodename, "key_len": 2 * self.k,
+            "matrix1": mat(bi["matrix1"]), "matrix2": mat(bi["matrix2"]), "nb_hashes": bi["nb_hashes"],
+            "pwd": "." if sde else os.getcwd(), "size": bi["m"],
+            "time": time.asctime(time.gmtime(int(sde))) if sde else time.asctime(),
+        }
+
+    def dump(self, path, cmdline=()):
+        """header + filter.write_bits (bc_main.cc:113,139)."""
+        with open(path, "wb") as f:
+            write_header(f, self.header(cmdline))
+
+            def _sink(ctx, ptr, n):
+                f.write(C.string_at(ptr, n))
+                return 0
+            cb = L.SINK_FN(_sink)
+            self.hc._check(self.hc._lib.jfgpu_bloom_dump(self.hc._h, cb, None))
 
 
 def write_header(f, header):

@@ -10,7 +10,7 @@ import random
 import pytest
 
 import jfutil
-from cases import BIG_CASES, CASES, EDGE_CASES
+from cases import BC_CASES, BF_CASES, BIG_CASES, CASES, EDGE_CASES
 
 pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
@@ -356,3 +356,76 @@ def test_cli_count_corner_cases_against_reference_golden(name, built, workdir, i
     assert jfutil.semantic(h) == g["header"]
     assert len(b) == g["body_len"]
     assert jfutil.md5(b) == g["body_md5"]
+
+
+GOLDEN_BC = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_bc.json")))
+GOLDEN_BF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_bf.json")))
+
+
+@pytest.mark.parametrize("name", sorted(BC_CASES))
+def test_bloom_counter_matches_reference_golden(name, built, workdir, inputs):
+    """`jellyfish bc` on the device (file byte for byte: the counter does not depend on the insertion order), then
+    `count --bc FILE` (bc_main.cc:84-161, count_main.cc:110-120,191-206) against the reference's goldens."""
+    bargs, bins, cargs, cins = BC_CASES[name]
+    g = GOLDEN_BC[name]
+    bc = os.path.join(workdir, "gpu_%s.bc" % name)
+    jfutil.run([jfutil.OUR_JF, "bc"] + bargs + ["-o", bc] + [inputs[i] for i in bins])
+    hb, bb = jfutil.split_db(bc)
+    assert {k: hb.get(k) for k in g["bc_header"]} == g["bc_header"]
+    assert len(bb) == g["bc_len"] and jfutil.md5(bb) == g["bc_md5"]
+    db = os.path.join(workdir, "gpu_%s_bc.jf" % name)
+    jfutil.run([jfutil.OUR_JF, "count"] + cargs + ["--bc", bc, "-o", db] + [inputs[i] for i in cins])
+    h, b = jfutil.split_db(db)
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"] and jfutil.md5(b) == g["body_md5"]
+
+
+def test_bloom_counter_python_api(built, workdir, inputs):
+    from jellyfish_b200 import BloomCounter, HashCounter
+    bargs, bins, cargs, cins = BC_CASES["bc_k21C"]
+    g = GOLDEN_BC["bc_k21C"]
+    bc = os.path.join(workdir, "api.bc")
+    with BloomCounter(400000, 0.001, k=21, canonical=True) as b:
+        b.add_files([inputs[i] for i in bins])
+        b.dump(bc)
+    hb, bb = jfutil.split_db(bc)
+    assert {k: hb.get(k) for k in g["bc_header"]} == g["bc_header"] and jfutil.md5(bb) == g["bc_md5"]
+    with HashCounter(1000000, 7, k=21, canonical=True) as hc:
+        hc.load_bloom_counter(bc)
+        hc.add_files([inputs[i] for i in cins])
+        st = hc.done()
+        assert st["inserted"] < st["kmers"]
+        assert jfutil.md5(hc.dump_records()) == g["body_md5"]
+
+
+@pytest.mark.parametrize("name", sorted(n for n in BF_CASES if "-Q" not in BF_CASES[n][0]))
+def test_bloom_prefilter_against_reference_golden(name, built, workdir, inputs):
+    """count --bf-size (count_main.cc:122-133,317-321).  Which first occurrences pass as false positives depends on the
+    insertion order (the reference's own output changes with -t), so the device path is held to: the same header as
+    the reference's -t 1 run, every count in {occ - 1, occ}, and a false-positive rate of the order asked for."""
+    args, ins = BF_CASES[name]
+    g = GOLDEN_BF[name]
+    db = os.path.join(workdir, "gpu_%s.jf" % name)
+    jfutil.run([jfutil.OUR_JF, "count"] + args + ["-o", db] + [inputs[i] for i in ins])
+    h, b = jfutil.split_db(db)
+    assert jfutil.semantic(h) == g["header"]
+    # occurrences: the same switches without the filter, through the restatement
+    plain = [a for a in args]
+    for sw in ("--bf-size", "--bf-fp"):
+        if sw in plain:
+            i = plain.index(sw); del plain[i:i + 2]
+    ref = os.path.join(workdir, "occ_%s.jf" % name)
+    jfutil.run([jfutil.ORACLE_C, "count"] + plain + ["-o", ref] + [inputs[i] for i in ins])
+    hr, br = jfutil.split_db(ref)
+    occ = dict(jfutil.records(hr, br))
+    got = dict(jfutil.records(h, b))
+    assert set(got) <= set(occ)
+    cap = (1 << (8 * h["counter_len"])) - 1
+    bad = [k for k, v in got.items() if v not in (min(occ[k], cap), min(occ[k] - 1, cap))]
+    assert not bad, "counts outside {occ-1, occ}: %d" % len(bad)
+    missing = [k for k in occ if k not in got and occ[k] > 1]
+    assert not missing, "k-mers seen more than once must be present: %d missing" % len(missing)
+    fp = float(args[args.index("--bf-fp") + 1]) if "--bf-fp" in args else 0.01
+    singles = [k for k in occ if occ[k] == 1]
+    passed = sum(1 for k in singles if k in got)
+    assert passed <= max(20, 3.0 * fp * len(singles)), "false positives: %d of %d singletons" % (passed, len(singles))
