@@ -14,11 +14,16 @@ insert/increment) over the whole synthetic input, into a zeroed table.
   cpu_baseline  the reference binary (oracle/_ref/jellyfish, all host threads) on a bounded
                 sample of the same workload
 
-Workload (N=1): BASELINE configs[1], k=21 canonical, 10 Gbp synthetic FASTA.  configs[1]
-names a "4 G-entry hash", which cannot hold the ~9.98e9 distinct 21-mers of 10 Gbp iid
+Workload (N=1, default --config k21): BASELINE configs[1], k=21 canonical, 10 Gbp synthetic FASTA.
+configs[1] names a "4 G-entry hash", which cannot hold the ~9.98e9 distinct 21-mers of 10 Gbp iid
 sequence: the reference doubles it twice to 2^34 slots.  The bench therefore sizes the table at
 its final size, -s 16G (2^34 slots), for both arms; set --size 4G to time the doubling too.
 Input is larger than L2 (10 GB text, 68 GB table), so no L2 flush is needed between steps.
+
+The other BASELINE configs are bench lines of their own (`--config`, results under profiles/):
+  k31   configs[2]  k=31 canonical, 10 Gbp over 8 GPUs = 1.25 Gbp and 2^31 slots (64-bit) per GPU
+  k63   configs[4]  k=63 canonical, 2 Gbp, 2^32 slots of 128 bits
+  bf    configs[3]  k=21 with the --bf-size 10G Bloom prefilter in front of the table
 """
 import argparse
 import ctypes as C
@@ -37,6 +42,23 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "k-mers counted/sec at k=21"
 UNIT = "k-mers/s"
+
+# per-GPU workloads of the BASELINE configs: k, bases, -s (table share of one GPU), Bloom prefilter size
+CONFIGS = {
+    "k21": {"k": 21, "bases": 10_000_000_000, "size": "16G", "bf": 0},
+    "k31": {"k": 31, "bases": 1_250_000_000, "size": "2G", "bf": 0},
+    "k63": {"k": 63, "bases": 2_000_000_000, "size": "4G", "bf": 0},
+    "bf":  {"k": 21, "bases": 10_000_000_000, "size": "16G", "bf": 10_000_000_000},
+}
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: identical in both arms (it names the workload, not the engine)."""
+    bf = (", --bf-size %d Bloom prefilter" % args.bf_size) if args.bf_size else ""
+    return {"workload": "k=%d canonical, %d bp synthetic FASTA per GPU (one record, 70-column lines: the shape generate_sequence writes), "
+                        "-s %s per GPU%s" % (args.k, args.bases, args.size, bf),
+            "l2": "text and table are far larger than L2 (126 MB): no flush between steps",
+            "parallelism": "1 GPU" if world == 1 else "table sharded by the top hash bits over %d GPUs" % world}
 
 
 def parse_size(s):

@@ -2,7 +2,6 @@
 // Host orchestration only: every byte of the hot path is processed by the kernels in
 // jf_kernels.cuh.  There is no CPU fallback; without a CUDA device every call fails.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -16,6 +15,7 @@
 #include "jf_kernels.cuh"
 #include "jf_extract.cuh"
 #include "jf_window.cuh"
+#include "jf_dump.cuh"
 
 using namespace jfk;
 
@@ -76,8 +76,8 @@ struct PartState {
   uint32_t P = 0, region_bits = 0, rec_bytes = 0, cap = 0, flush_min = 0, stage_bytes = 0, n_chunks = 0, margin = 0, arena_chunks = 0, n_arenas = 0;
   DevBuf pool, dir, order, pool_next, cta_chunk, cta_fill, spill_keys, spill_counts, spill_n, hist, start, cursor, unit_cursor;
   uint64_t spill_cap = 0;
-  // experimental window form of K2 (jf_window.cuh), JFGPU_K2_WINDOW only
-  DevBuf w_start, w_cursor, w_rec, w_def_pos, w_def_high, w_def_n;
+  // window form of K2 (jf_window.cuh)
+  DevBuf w_start, w_cursor, w_cnt, w_rec, w_def_pos, w_def_high, w_def_n;
   uint64_t w_rec_cap = 0, w_def_cap = 0;
   uint64_t bound_chunks = 0;     // host-side upper bound of the chunks in use in any one arena
   bool pending = false;          // records sit in the pool
@@ -128,6 +128,8 @@ struct jfgpu_engine {
   double kernel_ms = 0; uint64_t kernel_launches = 0;
   double drain_ms = 0; cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
   int count_smem = 0;
+  // failure counter watched one group behind (hash_counter::add -> handle_full_ary), without draining the stream
+  unsigned long long* h_watch = nullptr; cudaEvent_t ev_watch[2] = { nullptr, nullptr };
 };
 
 namespace {
@@ -353,7 +355,7 @@ void part_release(jfgpu_engine* e) {
   PartState& ps = e->part;
   ps.pool.free(); ps.dir.free(); ps.order.free(); ps.pool_next.free(); ps.cta_chunk.free(); ps.cta_fill.free();
   ps.spill_keys.free(); ps.spill_counts.free(); ps.spill_n.free(); ps.hist.free(); ps.start.free(); ps.cursor.free(); ps.unit_cursor.free();
-  ps.w_start.free(); ps.w_cursor.free(); ps.w_rec.free(); ps.w_def_pos.free(); ps.w_def_high.free(); ps.w_def_n.free();
+  ps.w_start.free(); ps.w_cursor.free(); ps.w_cnt.free(); ps.w_rec.free(); ps.w_def_pos.free(); ps.w_def_high.free(); ps.w_def_n.free();
   ps.w_rec_cap = ps.w_def_cap = 0;
   ps.n_chunks = 0; ps.arena_chunks = 0; ps.n_arenas = 0; ps.pending = false;
 }
@@ -363,10 +365,19 @@ int read_stats(jfgpu_engine* e);
 int bloom_draw(jfgpu_engine* e);
 BloomDev bloom_dev(const jfgpu_engine* e);
 
-// EXPERIMENTAL (JFGPU_K2_WINDOW, never run on a device yet): the window form of K2, jf_window.cuh.
+// The window form of K2 (jf_window.cuh): the default for 32-bit slots and 4-byte records.
 // Processes whole regions in groups, starting at unit `*done` (which must be the first unit of a
 // region), until every unit is inserted or -- with regrow enabled -- a group has reported keys that
 // found no slot.  Regions too large for the group buffer are left to the L2 kernel.
+// Post a copy of the live failure counter behind the work enqueued so far / wait for an earlier one.
+static void watch_post(jfgpu_engine* e, cudaStream_t st, int slot) {
+  cudaMemcpyAsync(e->h_watch + slot, e->stats.as<unsigned long long>() + STAT_FAILED, 8, cudaMemcpyDeviceToHost, st);
+  cudaEventRecord(e->ev_watch[slot], st);
+}
+static bool watch_failed(jfgpu_engine* e, int slot) {
+  cudaEventSynchronize(e->ev_watch[slot]);
+  return e->h_watch[slot] != 0;
+}
 static bool window_enabled(jfgpu_engine* e, const PartDev& pd) {
   return e->p.k2_mode == 0 && e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && pd.region_bits > WIN_LG &&
          pd.region_bits - WIN_LG <= 11 && CHUNK_BYTES == WIN_NTH * 16;
@@ -380,8 +391,8 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
   if(!ps.w_rec.p) {
     ps.w_rec_cap = (uint64_t)64 << 20;                       // records per group (256 MB)
     ps.w_def_cap = (uint64_t)16 << 20;
-    bool ok = ps.w_rec.alloc(ps.w_rec_cap * 4) == cudaSuccess && ps.w_start.alloc((((size_t)WIN_MAX_G << 11) + 1) * 4) == cudaSuccess &&
-              ps.w_cursor.alloc(((size_t)WIN_MAX_G << 11) * 4) == cudaSuccess && ps.w_def_pos.alloc(ps.w_def_cap * 8) == cudaSuccess &&
+    bool ok = ps.w_rec.alloc(ps.w_rec_cap * 4 + 64) == cudaSuccess && ps.w_start.alloc((((size_t)WIN_MAX_G << 11) + 1) * 4) == cudaSuccess &&
+              ps.w_cursor.alloc(((size_t)WIN_MAX_G << 11) * 4) == cudaSuccess && ps.w_cnt.alloc(((size_t)WIN_MAX_G << 11) * 4) == cudaSuccess && ps.w_def_pos.alloc(ps.w_def_cap * 8) == cudaSuccess &&
               ps.w_def_high.alloc(ps.w_def_cap * 4) == cudaSuccess && ps.w_def_n.alloc(8) == cudaSuccess;
     if(!ok) { cudaGetLastError(); return fail(e, JFGPU_ERR_NOMEM, "device allocation of the window buffers failed"); }
     CUDA_OK(e, cudaMemsetAsync(ps.w_def_n.p, 0, 8, st));
@@ -396,8 +407,9 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
   while(r0 < pd.P && start[r0] < *done) ++r0;
   const size_t scatter_smem = ((size_t)4 * ((size_t)1 << wpr_lg) + (size_t)WIN_TILE_UNITS * pd.chunk_recs) * 4;
   cudaFuncSetAttribute(win_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
-  const size_t insert_smem = (size_t)WIN_SLOTS * 4;
-  const uint64_t max_units = std::min<uint64_t>(ps.w_rec_cap / pd.chunk_recs, careful ? group_units : 0xFFFFFFFFu);
+  // (the runs of a group start on 16-byte boundaries: up to 3 padding records per window)
+  const uint64_t max_units = std::min<uint64_t>((ps.w_rec_cap - ((uint64_t)WIN_MAX_G << 13)) / pd.chunk_recs, careful ? group_units : 0xFFFFFFFFu);
+  uint32_t gi = 0;
   while(r0 < pd.P && *done < n_units) {
     WinDev wd;
     memset(&wd, 0, sizeof(wd));
@@ -421,7 +433,7 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
     } else {
       wd.tile_first[G] = tiles; wd.unit_first[G] = start[r0 + G];
       wd.g0 = r0; wd.G = G; wd.wpr_lg = wpr_lg; wd.n_tiles = tiles;
-      wd.wstart = ps.w_start.as<uint32_t>(); wd.wcursor = ps.w_cursor.as<uint32_t>();
+      wd.wstart = ps.w_start.as<uint32_t>(); wd.wcursor = ps.w_cursor.as<uint32_t>(); wd.wcnt = ps.w_cnt.as<uint32_t>();
       wd.wrec = ps.w_rec.as<uint32_t>(); wd.wrec_cap = ps.w_rec_cap;
       wd.def_pos = ps.w_def_pos.as<uint64_t>(); wd.def_high = ps.w_def_high.as<uint32_t>();
       wd.def_n = ps.w_def_n.as<unsigned long long>(); wd.def_cap = ps.w_def_cap;
@@ -432,12 +444,12 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
         win_scan_kernel<<<1, 1024, 0, st>>>(wd, T.stats); JF_LAUNCHED();
         win_scatter_kernel<<<tiles, WIN_NTH, scatter_smem, st>>>(pd, wd, ps.order.as<uint32_t>(), hb); JF_LAUNCHED();
         if(e->kw == 1) {
-          cudaFuncSetAttribute(win_insert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)insert_smem);
-          win_insert_kernel<1><<<e->n_sm * 3, WIN_NTH, insert_smem, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
+          cudaFuncSetAttribute(win_insert2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN2_SMEM);
+          win_insert2_kernel<1><<<e->n_sm, WIN2_NTH, WIN2_SMEM, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
           win_deferred_kernel<1><<<e->n_sm * 2, 256, 0, st>>>(T, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
         } else {
-          cudaFuncSetAttribute(win_insert_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)insert_smem);
-          win_insert_kernel<2><<<e->n_sm * 3, WIN_NTH, insert_smem, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
+          cudaFuncSetAttribute(win_insert2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN2_SMEM);
+          win_insert2_kernel<2><<<e->n_sm, WIN2_NTH, WIN2_SMEM, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
           win_deferred_kernel<2><<<e->n_sm * 2, 256, 0, st>>>(T, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
         }
         CUDA_OK(e, cudaMemsetAsync(ps.w_def_n.p, 0, 8, st));
@@ -445,12 +457,14 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
       *done = start[r0 + G]; r0 += G;
     }
     if(careful) {
-      if(st != e->cs) cudaStreamSynchronize(st);
-      int rc = read_stats(e);
-      if(rc) return rc;
-      if(e->h_stats[STAT_FAILED]) { *failed = true; return JFGPU_OK; }
+      // the failure counter is looked at one group late, so that the device never waits for the host: two groups of
+      // failed keys fit the failure list (group = fail_cap / 2 records)
+      watch_post(e, st, (int)(gi & 1));
+      if(gi > 0 && watch_failed(e, (int)((gi - 1) & 1))) { cudaStreamSynchronize(st); *failed = true; return JFGPU_OK; }
+      ++gi;
     }
   }
+  if(careful && gi > 0 && watch_failed(e, (int)((gi - 1) & 1))) { cudaStreamSynchronize(st); *failed = true; return JFGPU_OK; }
   CUDA_OK(e, cudaGetLastError());
   return JFGPU_OK;
 }
@@ -504,6 +518,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
       }
     }
   }
+  unsigned gq = 0;
   if(!rc && !(window_enabled(e, pd) && done >= n_units && !rebuilt))
   do {
     const unsigned upto = careful ? (unsigned)std::min<uint64_t>((uint64_t)done + group, n_units) : 0xFFFFFFFFu;
@@ -535,10 +550,16 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
     JF_LAUNCHED();
     if(!careful) break;
     done = upto;
-    if(st != e->cs) cudaStreamSynchronize(st);
-    rc = read_stats(e);
-    if(rc) break;
-    if(e->h_stats[STAT_FAILED]) {
+    // the failure counter is read one group late (two groups of failed keys fit the failure list), so the device
+    // does not idle while the host looks at it; the last group is checked right away
+    watch_post(e, st, (int)(gq & 1));
+    const bool last = done >= n_units;
+    bool failed_now = gq > 0 && watch_failed(e, (int)((gq - 1) & 1));
+    if(!failed_now && last) failed_now = watch_failed(e, (int)(gq & 1));
+    ++gq;
+    if(failed_now) {
+      cudaStreamSynchronize(st);
+      gq = 0;                    // the groups launched so far are complete: start the look-behind afresh
       if(!rebuilt) {            // keep a copy of the inverse tables the pending records were written against
         if(old_inv.alloc(e->tab.inv_lut.bytes) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "device allocation failed"); break; }
         cudaMemcpyAsync(old_inv.p, e->tab.inv_lut.p, e->tab.inv_lut.bytes, cudaMemcpyDeviceToDevice, e->cs);
@@ -769,37 +790,22 @@ int insert_keys_into(jfgpu_engine* e, Table& t, const uint64_t* keys, const uint
 }
 
 struct SegScratch {
-  DevBuf keys, counts, sort_lo, sort_lo2, sort_hi, sort_hi2, perm, perm2, n_out, cub_tmp, bytes;
+  DevBuf keys, counts, sort_lo, n_out;
   uint64_t cap = 0;
-  size_t cub_bytes = 0;
-  void free_all() { keys.free(); counts.free(); sort_lo.free(); sort_lo2.free(); sort_hi.free(); sort_hi2.free();
-                    perm.free(); perm2.free(); n_out.free(); cub_tmp.free(); bytes.free(); cap = 0; }
+  void free_all() { keys.free(); counts.free(); sort_lo.free(); n_out.free(); cap = 0; }
 };
 
-int seg_alloc(jfgpu_engine* e, SegScratch& s, uint64_t cap, bool want_sort, unsigned rec_bytes) {
+int seg_alloc(jfgpu_engine* e, SegScratch& s, uint64_t cap) {
   s.cap = cap;
   CUDA_OK(e, s.keys.alloc(cap * 8 * e->kw));
   CUDA_OK(e, s.counts.alloc(cap * 8));
   CUDA_OK(e, s.n_out.alloc(8));
   CUDA_OK(e, s.sort_lo.alloc(cap * 8));
-  if(want_sort) {
-    CUDA_OK(e, s.sort_lo2.alloc(cap * 8));
-    CUDA_OK(e, s.perm.alloc(cap * 4));
-    CUDA_OK(e, s.perm2.alloc(cap * 4));
-    if(e->kw == 2) { CUDA_OK(e, s.sort_hi.alloc(cap * 8)); CUDA_OK(e, s.sort_hi2.alloc(cap * 8)); }
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)cap, 0, 64, e->cs);
-    s.cub_bytes = tmp;
-    CUDA_OK(e, s.cub_tmp.alloc(tmp));
-    CUDA_OK(e, s.bytes.alloc(cap * rec_bytes + 16));
-  }
   return JFGPU_OK;
 }
 
 // Collect the records of local original positions [lo, hi) of table t; returns their number.
-int collect_segment(jfgpu_engine* e, Table& t, SegScratch& s, uint64_t lo, uint64_t hi, uint64_t lower, uint64_t upper,
-                    bool want_sort, uint64_t* n_rec) {
+int collect_segment(jfgpu_engine* e, Table& t, SegScratch& s, uint64_t lo, uint64_t hi, uint64_t lower, uint64_t upper, uint64_t* n_rec) {
   CollectArgs a;
   memset(&a, 0, sizeof(a));
   a.T = table_dev(e, t);
@@ -811,7 +817,7 @@ int collect_segment(jfgpu_engine* e, Table& t, SegScratch& s, uint64_t lo, uint6
   a.hb = t.hb;
   a.out_keys = s.keys.as<uint64_t>(); a.out_counts = s.counts.as<uint64_t>();
   a.out_sort_lo = s.sort_lo.as<uint64_t>();
-  a.out_sort_hi = (want_sort && e->kw == 2) ? s.sort_hi.as<uint64_t>() : nullptr;
+  a.out_sort_hi = nullptr;
   a.out_n = s.n_out.as<unsigned long long>();
   a.out_cap = s.cap;
   CUDA_OK(e, cudaMemsetAsync(s.n_out.p, 0, 8, e->cs));
@@ -863,10 +869,10 @@ int rebuild_table_impl(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, i
   CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_REPROBES, 0, 8, e->cs));
   SegScratch s;
   const uint64_t seg = pick_segment(e->tab);
-  rc = seg_alloc(e, s, seg + e->tab.margin + 8, false, 0);
+  rc = seg_alloc(e, s, seg + e->tab.margin + 8);
   for(uint64_t lo = 0; lo < e->tab.local_size && !rc; lo += seg) {
     uint64_t n = 0;
-    rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, false, &n);
+    rc = collect_segment(e, e->tab, s, lo, std::min(lo + seg, e->tab.local_size), 0, ~0ull, &n);
     if(!rc) rc = insert_keys_into(e, nt, s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), n, e->cs);
   }
   cudaStreamSynchronize(e->cs);
@@ -1040,6 +1046,8 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
   if(cudaStreamCreateWithFlags(&e->cs, cudaStreamNonBlocking) != cudaSuccess ||
      cudaStreamCreateWithFlags(&e->hs, cudaStreamNonBlocking) != cudaSuccess) { e->err = "stream creation failed"; return bail(JFGPU_ERR_CUDA); }
   cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
+  cudaHostAlloc((void**)&e->h_watch, 16, cudaHostAllocDefault);
+  for(int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&e->ev_watch[i], cudaEventDisableTiming);
   for(int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming); }
 
   if(params->bloom_counter) {
@@ -1106,6 +1114,8 @@ void jfgpu_destroy(jfgpu_handle e) {
   }
   e->nlA.free(); e->nlB.free(); e->cntA.free(); e->cntB.free(); e->tstate.free();
   if(e->h_stats) cudaFreeHost(e->h_stats);
+  if(e->h_watch) cudaFreeHost(e->h_watch);
+  for(int i = 0; i < 2; ++i) if(e->ev_watch[i]) cudaEventDestroy(e->ev_watch[i]);
   if(e->ev_t0) cudaEventDestroy(e->ev_t0);
   if(e->ev_t1) cudaEventDestroy(e->ev_t1);
   if(e->ev_d0) cudaEventDestroy(e->ev_d0);
@@ -1393,53 +1403,77 @@ int jfgpu_dump(jfgpu_handle e, uint64_t lower, uint64_t upper, uint32_t ocl, jfg
   cudaSetDevice(e->device);
   int rc = jfgpu_finish(e, nullptr);
   if(rc) return rc;
+  // Segment by segment, two buffers: while the host hands segment i to the sink, the device sorts and serialises segment
+  // i+1 (jf_dump.cuh: no global sort, every tile of 8192 positions is ordered in shared memory) and the copy engine brings
+  // it to pinned host memory.
   Table& t = e->tab;
-  const unsigned key_bytes = e->nbytes, rec = key_bytes + ocl;
-  const uint64_t seg = pick_segment(t);
-  SegScratch s;
-  rc = seg_alloc(e, s, seg + t.margin + 8, true, rec);
-  uint8_t* hbuf = nullptr;
-  if(!rc && cudaHostAlloc((void**)&hbuf, (seg + t.margin + 8) * rec + 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "pinned host allocation failed"); }
+  const unsigned rec = e->nbytes + ocl;
+  const uint64_t seg = std::min<uint64_t>(t.local_size, (uint64_t)1 << 24);
+  const uint64_t cap = seg + t.margin + 8;                    // records of a segment at most
+  const uint32_t max_tiles = (uint32_t)((seg + DUMP_TP - 1) / DUMP_TP);
+  DevBuf tile_cnt[2], out[2];
+  uint8_t* hbuf[2] = { nullptr, nullptr };
+  uint32_t* h_total = nullptr;
+  cudaEvent_t ev_emit[2] = { nullptr, nullptr }, ev_copy[2] = { nullptr, nullptr };
+  bool ok = cudaHostAlloc((void**)&h_total, 2 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
+  for(int i = 0; i < 2 && ok; ++i)
+    ok = tile_cnt[i].alloc(((size_t)max_tiles + 1) * 4) == cudaSuccess && out[i].alloc(cap * rec + 16) == cudaSuccess &&
+         cudaHostAlloc((void**)&hbuf[i], cap * rec + 16, cudaHostAllocDefault) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ev_emit[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming) == cudaSuccess;
+  if(!ok) { cudaGetLastError(); rc = fail(e, JFGPU_ERR_NOMEM, "allocation of the dump buffers failed"); }
+  const size_t smem = (size_t)e->nbytes * 256 * 8 + ((size_t)DUMP_TP + 1) * 4 + (size_t)DUMP_MAXC * 2 + (size_t)DUMP_NTH * rec;
   uint64_t total = 0;
-  const uint64_t relbits = ceil_log2(seg);   // original positions relative to the segment start are < seg
-  for(uint64_t lo = 0; lo < t.local_size && !rc; lo += seg) {
-    uint64_t n = 0;
-    rc = collect_segment(e, t, s, lo, std::min(lo + seg, t.local_size), lower, upper, true, &n);
-    if(rc || n == 0) continue;
-    const int g = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)e->n_sm * 8);
-    iota_u32_kernel<<<g, 256, 0, e->cs>>>(s.perm.as<uint32_t>(), n); JF_LAUNCHED();
-    size_t tmp = s.cub_bytes;
-    const uint32_t* perm_final = nullptr;
-    const unsigned total_bits = (unsigned)relbits + t.hb;
-    if(e->kw == 1 || total_bits <= 64) {
-      cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tmp, s.sort_lo.as<uint64_t>(), s.sort_lo2.as<uint64_t>(),
-                                      s.perm.as<uint32_t>(), s.perm2.as<uint32_t>(), (int64_t)n, 0, (int)std::max(1u, std::min(64u, total_bits)), e->cs);
-      JF_LAUNCHED();
-      perm_final = s.perm2.as<uint32_t>();
-    } else {
-      // 128-bit key: LSD in two stable passes, low word then high word
-      cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tmp, s.sort_lo.as<uint64_t>(), s.sort_lo2.as<uint64_t>(),
-                                      s.perm.as<uint32_t>(), s.perm2.as<uint32_t>(), (int64_t)n, 0, 64, e->cs);
-      JF_LAUNCHED();
-      gather_u64_kernel<<<g, 256, 0, e->cs>>>(s.sort_hi.as<uint64_t>(), s.perm2.as<uint32_t>(), s.sort_hi2.as<uint64_t>(), n); JF_LAUNCHED();
-      tmp = s.cub_bytes;
-      cub::DeviceRadixSort::SortPairs(s.cub_tmp.p, tmp, s.sort_hi2.as<uint64_t>(), s.sort_hi.as<uint64_t>(),
-                                      s.perm2.as<uint32_t>(), s.perm.as<uint32_t>(), (int64_t)n, 0, (int)std::max(1u, total_bits - 64), e->cs);
-      JF_LAUNCHED();
-      perm_final = s.perm.as<uint32_t>();
-    }
-    const size_t smem = (size_t)256 * rec;
-    if(e->kw == 1) serialize_kernel<1><<<g, 256, smem, e->cs>>>(s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), perm_final, n, key_bytes, ocl, s.bytes.as<uint8_t>());
-    else           serialize_kernel<2><<<g, 256, smem, e->cs>>>(s.keys.as<uint64_t>(), s.counts.as<uint64_t>(), perm_final, n, key_bytes, ocl, s.bytes.as<uint8_t>());
-    JF_LAUNCHED();
-    cudaError_t c = cudaMemcpyAsync(hbuf, s.bytes.p, n * rec, cudaMemcpyDeviceToHost, e->cs);
-    if(c == cudaSuccess) c = cudaStreamSynchronize(e->cs);
+  const uint64_t n_seg = (t.local_size + seg - 1) / seg;
+  auto launch = [&](uint64_t si) -> int {            // count, scan, emit of segment si on the compute stream; its total follows
+    const int b = (int)(si & 1);
+    DumpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = table_dev(e, t);
+    a.inv_lut = t.inv_lut.as<uint64_t>(); a.nbytes = e->nbytes; a.ocl = ocl;
+    a.seg_lo = si * seg; a.seg_hi = std::min(a.seg_lo + seg, t.local_size);
+    a.slots_end = t.local_size + t.margin; a.margin = t.margin;
+    a.lower = lower; a.upper = upper;
+    a.n_tiles = (uint32_t)((a.seg_hi - a.seg_lo + DUMP_TP - 1) / DUMP_TP);
+    a.tile_cnt = tile_cnt[b].as<uint32_t>(); a.out = out[b].as<uint8_t>(); a.out_cap = cap;
+    const int grid = (int)std::min<uint64_t>(a.n_tiles, (uint64_t)e->n_sm * 8);
+    return dispatch(e, e->kw, t.slot_bits, [&](auto KW, auto SB) -> int {
+      constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
+      dump_count_kernel<sb><<<grid, DUMP_NTH, 0, e->cs>>>(a); JF_LAUNCHED();
+      dump_scan_kernel<<<1, 1024, 0, e->cs>>>(a.tile_cnt, a.n_tiles); JF_LAUNCHED();
+      auto kern = dump_emit_kernel<kw, sb>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, DUMP_NTH, smem, e->cs>>>(a); JF_LAUNCHED();
+      CUDA_OK(e, cudaMemcpyAsync(h_total + b, a.tile_cnt + a.n_tiles, 4, cudaMemcpyDeviceToHost, e->cs));
+      CUDA_OK(e, cudaEventRecord(ev_emit[b], e->cs));
+      return JFGPU_OK;
+    });
+  };
+  uint64_t n_in_buf[2] = { 0, 0 };
+  if(!rc && n_seg) rc = launch(0);
+  for(uint64_t si = 0; si < n_seg && !rc; ++si) {
+    const int b = (int)(si & 1);
+    // the segment's size, then its bytes on the copy stream
+    cudaError_t c = cudaEventSynchronize(ev_emit[b]);
     if(c != cudaSuccess) { rc = fail(e, JFGPU_ERR_CUDA, std::string("dump: ") + cudaGetErrorString(c)); break; }
-    if(sink(ctx, hbuf, n * rec) != 0) { rc = fail(e, JFGPU_ERR_SINK, "dump sink failed"); break; }
-    total += n;
+    n_in_buf[b] = h_total[b];
+    if(n_in_buf[b] > cap) { rc = fail(e, JFGPU_ERR_STATE, "internal: segment overflow in dump"); break; }
+    if(n_in_buf[b]) cudaMemcpyAsync(hbuf[b], out[b].p, n_in_buf[b] * rec, cudaMemcpyDeviceToHost, e->hs);
+    cudaEventRecord(ev_copy[b], e->hs);
+    // the next segment is produced while this one is copied and written (its buffers were released two rounds ago)
+    if(si + 1 < n_seg) { rc = launch(si + 1); if(rc) break; }
+    c = cudaEventSynchronize(ev_copy[b]);
+    if(c != cudaSuccess) { rc = fail(e, JFGPU_ERR_CUDA, std::string("dump: ") + cudaGetErrorString(c)); break; }
+    if(n_in_buf[b] && sink(ctx, hbuf[b], n_in_buf[b] * rec) != 0) { rc = fail(e, JFGPU_ERR_SINK, "dump sink failed"); break; }
+    total += n_in_buf[b];
   }
-  if(hbuf) cudaFreeHost(hbuf);
-  s.free_all();
+  cudaStreamSynchronize(e->cs); cudaStreamSynchronize(e->hs);
+  for(int i = 0; i < 2; ++i) {
+    tile_cnt[i].free(); out[i].free();
+    if(hbuf[i]) cudaFreeHost(hbuf[i]);
+    if(ev_emit[i]) cudaEventDestroy(ev_emit[i]);
+    if(ev_copy[i]) cudaEventDestroy(ev_copy[i]);
+  }
+  if(h_total) cudaFreeHost(h_total);
   if(n_records) *n_records = total;
   return rc;
 }

@@ -74,6 +74,30 @@ __device__ __forceinline__ void squeeze(uint64_t& c, uint32_t& b, uint32_t del) 
   }
 }
 
+// A region's open chunk filled up inside one window (skewed input): the key goes to the spill list, which K2 inserts
+// directly after the regions; out of line, it is a cold path.
+template<int KW, int SB>
+__device__ __noinline__ void spill_record(const TableDev T, uint64_t* spill_keys, uint64_t* spill_counts, unsigned long long* spill_n, uint64_t spill_cap,
+                                          uint64_t k0, uint64_t k1, uint64_t pos) {
+  // (everything by value: taking the address of the kernel's parameter structures would move them to local memory)
+  uint64_t key[KW];
+  key[0] = k0; if(KW == 2) key[KW - 1] = k1;
+  unsigned long long at = atomicAdd(spill_n, 1ull);
+  if(at < spill_cap) {
+#pragma unroll
+    for(int q = 0; q < KW; ++q) spill_keys[at * KW + q] = key[q];
+    spill_counts[at] = 1;
+    return;
+  }
+  // the list is full as well: insert right here (statistics straight to the global counters: the caller's stay in registers)
+  LocalStats l = { 0, 0, 0, 0, 0 };
+  if(table_add<KW, SB>(T, key, pos, 1, l)) {
+    atomicAdd(&T.stats[STAT_INSERTED], 1ull);
+    if(l.distinct) atomicAdd(&T.stats[STAT_DISTINCT], (unsigned long long)l.distinct);
+    if(l.reprobes) atomicAdd(&T.stats[STAT_REPROBES], (unsigned long long)l.reprobes);
+  } else record_failure<KW>(T, key, 1);
+}
+
 // FAST = the common geometry of the region-by-region path, everything in 32-bit arithmetic: one key word, the
 // 11-bit-table hash with at most two parity rows (tables of up to 2^34 slots), 4-byte records, a single shard.
 template<int KW, int SB, int MODE, int NTH, bool FAST>
@@ -82,6 +106,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   constexpr int TILEB = WINB - HALO;
   constexpr int NW = NTH / 32;
   constexpr int PW = PRE / 32;                   // 64-bit stream words in front of the window (PRE symbols)
+  constexpr int SG = 4;                          // k-mers whose shared-memory round trips are kept in flight together (FAST tail)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ExtractSmemT<NTH>& sm = *reinterpret_cast<ExtractSmemT<NTH>*>(smem_raw);
   uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15));
@@ -221,7 +246,6 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
     }
     if(lane == 31) sm.warp_fn[warp] = inc;
     __syncthreads();
-    { const uint64_t tn = t + gridDim.x; if(tn < a.n_tiles && tid == 0) issue(tn); }
     uint32_t entry = (t == 0) ? (a.format == 1 ? (a.carry_in->state & 3u) : a.carry_in->state) : (uint32_t)a.tile_state[t];
     uint32_t wpre;
     {   // composition of the functions of the warps in front of this one: every warp scans the NW partials itself
@@ -258,10 +282,10 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
       // FASTQ, 4-line records (mer_overlap_sequence_parser.hpp:187-217): only sequence lines emit symbols; the
       // start of a header line emits the window reset; '@' / '+' at the line starts are verified
       uint32_t ty = st_in; bool at_start = prevb == '\n';
-#pragma unroll
-      for(int i = 0; i < 32; ++i) {
-        if(i >= vlo && i < vhi) {
-          const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+#pragma unroll 1
+      for(int i = vlo; i < vhi; ++i) {
+        {
+          const uint32_t b = sm.win[tid * 32 + i];
           uint32_t s = 8;
           if(b == '\n') { ty = (ty + 1) & 3u; at_start = true; }
           else {
@@ -280,10 +304,10 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
       }
     } else {
       uint32_t st = st_in;
-#pragma unroll
-      for(int i = 0; i < 32; ++i) {
-        if(i >= vlo && i < vhi) {
-          const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+#pragma unroll 1
+      for(int i = vlo; i < vhi; ++i) {
+        {
+          const uint32_t b = sm.win[tid * 32 + i];
           uint32_t s = 8;   // 8 = nothing
           if(st == ST_H) { if(b == '\n') st = ST_L; }
           else if(b == '\n') st = ST_L;
@@ -341,6 +365,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
       }
     }
     __syncthreads();
+    // the window's bytes are dead from here on (the per-byte paths above read them from shared memory): fetch the next one
+    { const uint64_t tn = t + gridDim.x; if(tn < a.n_tiles && tid == 0) issue(tn); }
     const uint32_t idx0 = sm.idx0, nsym = sm.nsym;
 
     // ---- phase D: the PRE symbols in front of the window (stream words 0 .. PW-1) ----
@@ -450,9 +476,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
           Y1 = bs ? ((v1 >> bs) | (v2 << (64 - bs))) : v1;
           if(KW == 2) Y2 = bs ? (v2 >> bs) : v2;
         }
-#pragma unroll
-        for(int j = 0; j < 8; ++j) {
-          if(!((vm8 >> j) & 1u)) continue;
+        // canonical (or forward) k-mer ending at symbol 8o+j
+        auto kmer_at = [&](const int j, uint64_t (&key)[KW]) {
           uint64_t m[KW], rc[KW];
           const int ms = 14 - 2 * j;                       // forward: end symbol 8o+j
           const int rs = 2 * j;                            // reverse: first symbol moves up by j
@@ -463,7 +488,6 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
             m[KW - 1]  = (ms ? ((X1 >> ms) | (X2 << (64 - ms))) : X1) & kmask_hi;
             rc[KW - 1] = ~(rs ? ((Y1 >> rs) | (Y2 << (64 - rs))) : Y1) & kmask_hi;
           }
-          uint64_t key[KW];
           bool use_rc = false;
           if(a.canonical) {
             if(KW == 1) use_rc = rc[0] < m[0];
@@ -471,6 +495,52 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
           }
 #pragma unroll
           for(int q = 0; q < KW; ++q) key[q] = use_rc ? rc[q] : m[q];
+        };
+        if(FAST && !a.bloom.mode) {
+          // Three passes over the 8 k-mers of the group so that the shared-memory round trips overlap: (1) keys, hashes and
+          // records -- 32 independent table loads in flight; (2) the slot reservations; (3) the record stores.
+          #pragma unroll
+          for(int hf = 0; hf < 8; hf += SG) {
+          uint32_t P[SG], R[SG];
+#pragma unroll
+          for(int jj = 0; jj < SG; ++jj) {
+            const int j = hf + jj;
+            // (computed for the masked-out positions as well: no branch per k-mer; kbits <= 44 keeps every table index in range)
+            uint64_t key[KW];
+            kmer_at(j, key);
+            const uint32_t klo = (uint32_t)key[0], khi = (uint32_t)(key[0] >> 32);
+            const uint32_t h32 = lut32[klo & 2047u] ^ lut32[2048 + ((klo >> 11) & 2047u)] ^
+                                 lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + ((khi >> 1) & 2047u)];
+            const uint32_t ext = (__popc((klo & f_p0lo) ^ (khi & f_p0hi)) & 1u) | ((__popc((klo & f_p1lo) ^ (khi & f_p1hi)) & 1u) << 1);
+            P[jj] = ((vm8 >> j) & 1u) ? ((h32 >> f_rgb) | (ext << (32 - f_rgb))) : 0xFFFFFFFFu;     // region
+            R[jj] = ((h32 & f_relmask) << f_hb) | (uint32_t)(key[0] >> f_lsz);                      // (position in the region, explicit key bits)
+          }
+          uint32_t S[SG], C[SG];
+#pragma unroll
+          for(int jj = 0; jj < SG; ++jj) {
+            S[jj] = 0; C[jj] = 0;
+            if(P[jj] != 0xFFFFFFFFu) { S[jj] = atomicAdd(&st_cnt[P[jj]], 1u); C[jj] = st_chunk[P[jj]]; }
+          }
+#pragma unroll
+          for(int jj = 0; jj < SG; ++jj) {
+            const int j = hf + jj;
+            if(P[jj] == 0xFFFFFFFFu) continue;
+            if(S[jj] < pd.chunk_recs) reinterpret_cast<uint32_t*>(pd.pool + (size_t)C[jj] * CHUNK_BYTES)[S[jj]] = R[jj];
+            else {             // this region's chunk filled up within one window (skewed input): direct insertion later
+              uint64_t key[KW];
+              kmer_at(j, key);
+              const uint64_t pos = ((uint64_t)P[jj] << f_rgb) | (R[jj] >> f_hb);
+              spill_record<KW, SB>(a.T, pd.spill_keys, pd.spill_counts, pd.spill_n, pd.spill_cap, key[0], key[KW - 1], pos);
+            }
+          }
+          }
+          continue;
+        }
+#pragma unroll
+        for(int j = 0; j < 8; ++j) {
+          if(!((vm8 >> j) & 1u)) continue;
+          uint64_t key[KW];
+          kmer_at(j, key);
           if(a.bloom.mode) {
             const uint64_t h1 = gf2_hash<KW>(bl1, key, (int)a.nbytes), h2 = gf2_hash<KW>(bl2, key, (int)a.nbytes);
             if(a.bloom.mode == BLOOM_COUNT) { bloom_count(a.bloom, h1, h2); ls.inserted++; continue; }   // `jellyfish bc`: no table
@@ -487,13 +557,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
             const uint32_t rec = ((h32 & f_relmask) << f_hb) | high;
             const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
             if(slot < pd.chunk_recs) reinterpret_cast<uint32_t*>(pd.pool + (size_t)st_chunk[p] * CHUNK_BYTES)[slot] = rec;
-            else {             // this region's chunk filled up within one window (skewed input): direct insertion later
-              const uint64_t pos = (uint64_t)h32 | ((uint64_t)ext << 32);
-              unsigned long long at = atomicAdd(pd.spill_n, 1ull);
-              if(at < pd.spill_cap) { pd.spill_keys[at] = key[0]; pd.spill_counts[at] = 1; }
-              else if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;
-              else { ls.failed++; record_failure<KW>(a.T, key, 1); }
-            }
+            else spill_record<KW, SB>(a.T, pd.spill_keys, pd.spill_counts, pd.spill_n, pd.spill_cap, key[0], key[KW - 1], (uint64_t)h32 | ((uint64_t)ext << 32));
             continue;
           }
           uint64_t pos;
@@ -535,15 +599,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
               if(pd.rec_bytes == 4) reinterpret_cast<uint32_t*>(dst)[slot] = (uint32_t)rec.lo;
               else if(pd.rec_bytes == 8) reinterpret_cast<uint64_t*>(dst)[slot] = rec.lo;
               else { reinterpret_cast<uint64_t*>(dst)[2 * slot] = rec.lo; reinterpret_cast<uint64_t*>(dst)[2 * slot + 1] = rec.hi; }
-            } else {           // this region's chunk filled up within one window (skewed input): direct insertion later
-              unsigned long long at = atomicAdd(pd.spill_n, 1ull);
-              if(at < pd.spill_cap) {
-#pragma unroll
-                for(int q = 0; q < KW; ++q) pd.spill_keys[at * KW + q] = key[q];
-                pd.spill_counts[at] = 1;
-              } else if(table_add<KW, SB>(a.T, key, pos, 1, ls)) ls.inserted++;
-              else { ls.failed++; record_failure<KW>(a.T, key, 1); }
-            }
+            } else spill_record<KW, SB>(a.T, pd.spill_keys, pd.spill_counts, pd.spill_n, pd.spill_cap, key[0], key[KW - 1], pos);    // this region's chunk filled up within one window (skewed input)
           }
         }
       }

@@ -2,12 +2,13 @@
 //
 //   K0a nl_scan_kernel      last '\n' of every tile (two ranges, see tile_state_kernel)
 //   K0b tile_state_kernel   parser state at the start of every staged window
-//   K1  count_kernel        fused: TMA-staged FASTA window -> classify -> compact symbols
-//                           -> rolling canonical k-mers -> GF(2) hash -> CAS insert/increment
-//                           (or, in ROUTE mode, bucket by owning shard for the all-to-all)
-//   K2  insert_keys_kernel  packed keys -> hash -> insert (multi-GPU receive side, regrow)
-//   K3  collect_kernel      table segment -> (key, count, sort key) records
-//   K4  serialize_kernel    sorted records -> on-disk record bytes
+//   K1  extract_kernel      (jf_extract.cuh) fused: TMA-staged text window -> word-parallel classification -> packed symbol
+//                           streams -> canonical k-mers -> GF(2) hash -> CAS insert (MODE 0), bucket by owning shard
+//                           (MODE 1) or compact region records appended to per-CTA chunk lists (MODE 2)
+//   K2  win_* kernels       (jf_window.cuh) region records -> table, one shared-memory window at a time;
+//       insert_chunks*      the L2 form of the same for slot widths the window form does not cover
+//   K2' insert_keys_kernel  packed keys -> hash -> insert (multi-GPU receive side, regrow, spilled records)
+//   K3  collect_kernel      table segment -> (key, count) pairs (regrow);  dump_* kernels (jf_dump.cuh): sorted record bytes
 //   K5  lookup / histogram / synth_fasta
 #ifndef JF_KERNELS_CUH
 #define JF_KERNELS_CUH
@@ -921,50 +922,6 @@ __global__ void __launch_bounds__(256) collect_kernel(const CollectArgs a) {
         }
       }
     }
-  }
-}
-
-// gather helper for the two-pass 128-bit sort
-__global__ void gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t* __restrict__ dst, uint64_t n) {
-  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    dst[i] = src[idx[i]];
-}
-__global__ void iota_u32_kernel(uint32_t* __restrict__ dst, uint64_t n) {
-  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    dst[i] = (uint32_t)i;
-}
-
-// ---------------------------------------------------------------------------------------
-// K4: record bytes = first ceil(2k/8) bytes of the little-endian key words, then
-//     min(count, 2^(8*ocl)-1) as ocl little-endian bytes (binary_dumper.hpp:36-40).
-//     A CTA assembles its records in shared memory and writes them with coalesced words.
-// ---------------------------------------------------------------------------------------
-template<int KW>
-__global__ void __launch_bounds__(256) serialize_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ counts,
-                                                        const uint32_t* __restrict__ perm, uint64_t n, uint32_t key_bytes,
-                                                        uint32_t ocl, uint8_t* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t stage[];
-  const uint32_t rec = key_bytes + ocl;
-  const uint64_t maxv = ocl >= 8 ? ~0ull : ((1ull << (8 * ocl)) - 1ull);
-  const uint64_t per_block = 256;
-  for(uint64_t b0 = (uint64_t)blockIdx.x * per_block; b0 < n; b0 += (uint64_t)gridDim.x * per_block) {
-    const uint64_t i = b0 + threadIdx.x;
-    if(i < n) {
-      const uint64_t src = perm ? perm[i] : i;
-      uint8_t* d = stage + threadIdx.x * rec;
-      uint64_t kw[KW];
-#pragma unroll
-      for(int q = 0; q < KW; ++q) kw[q] = keys[src * KW + q];
-      for(uint32_t b = 0; b < key_bytes; ++b) d[b] = (uint8_t)(kw[b >> 3] >> ((b & 7) * 8));
-      uint64_t c = counts[src]; if(c > maxv) c = maxv;
-      for(uint32_t b = 0; b < ocl; ++b) d[key_bytes + b] = (uint8_t)(c >> (8 * b));
-    }
-    __syncthreads();
-    const uint64_t nrec = min((uint64_t)per_block, n - b0);
-    const uint64_t nb = nrec * rec;
-    uint8_t* o = out + b0 * rec;
-    for(uint64_t j = threadIdx.x; j < nb; j += blockDim.x) o[j] = stage[j];
-    __syncthreads();
   }
 }
 

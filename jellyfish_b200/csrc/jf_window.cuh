@@ -1,19 +1,16 @@
-// jf_window.cuh -- EXPERIMENTAL second form of K2 ("window insert"), off unless JFGPU_K2_WINDOW is set.
+// jf_window.cuh -- K2, the shared-memory window insert (the default form of K2 for 32-bit slots and 4-byte records).
 //
-// Status: written at the end of round 1 after the GPU budget was spent -- compiled for sm_100a, never
-// run.  Nothing here is reachable in the default configuration; it is the starting point for round 2
-// ("what comes next").
-//
-// K2 today performs ~2 L2 operations per k-mer (first-probe CAS, reprobes, look-ahead loads) and sits
-// at the L2 ceiling for that mix.  Here the probing moves into shared memory:
+// The L2 form of K2 (insert_chunks32_kernel) performs ~2 L2 operations per k-mer (first-probe CAS, reprobes,
+// look-ahead loads).  Here the probing happens in shared memory:
 //   win_hist / win_scan / win_scatter  split the 4-byte records of a group of regions by WINDOW
 //        (2^WIN_LG slots = 64 KB of 32-bit slots) with a shared-memory staged tile sort, so that each
 //        window's records are contiguous (12 B of traffic per record);
-//   win_insert   one CTA per window: load the window's slots into shared memory, apply its records
-//        with shared-memory CAS/add along the reference's probe sequence pos + i(i+1)/2, store the
-//        window back (8 B of table traffic per slot + 4 B per record).  A probe that would leave the
-//        window is DEFERRED (position + key bits appended to a list); a counter carry goes to the
-//        side overflow table exactly as in the L2 kernels;
+//   win_insert2  persistent, one CTA per SM, two stages: while the CTA applies the records of one window with
+//        shared-memory CAS/add along the reference's probe sequence pos + i(i+1)/2, the TMA engine brings in the
+//        next window and its records (cp.async.bulk + mbarrier) and writes the previous window back
+//        (cp.async.bulk shared -> global): 8 B of table traffic per slot + 4 B per record, no global-memory
+//        latency inside the probing loop.  A probe that would leave the window is DEFERRED (position + key
+//        bits appended to a list); a counter carry goes to the side overflow table exactly as in the L2 kernels;
 //   win_deferred  the deferred records, with the ordinary global probe sequence, after win_insert
 //        of the same group has completed (stream order), so no slot is ever touched by a window CTA
 //        and by the global path at the same time.
@@ -37,6 +34,7 @@ struct WinDev {
   uint32_t unit_first[WIN_MAX_G + 1];              // first unit (index into `order`) of each region; [G] = end
   uint32_t* wstart;                                // [(G << wpr_lg) + 1] exclusive offsets into wrec after win_scan
   uint32_t* wcursor;                               // [G << wpr_lg] counts (win_hist), then write cursors (win_scatter)
+  uint32_t* wcnt;                                  // [G << wpr_lg] records per window (win_scan); runs start on 16-byte boundaries
   uint32_t* wrec; uint64_t wrec_cap;               // records grouped by (region, window)
   uint64_t* def_pos; uint32_t* def_high; unsigned long long* def_n; uint64_t def_cap;
 };
@@ -56,16 +54,23 @@ __global__ void __launch_bounds__(WIN_NTH) win_hist_kernel(PartDev pd, WinDev wd
   const uint32_t r = win_region_of_tile(wd, blockIdx.x);
   const uint32_t u0 = wd.unit_first[r] + (blockIdx.x - wd.tile_first[r]) * WIN_TILE_UNITS;
   const uint32_t u1 = min(u0 + WIN_TILE_UNITS, wd.unit_first[r + 1]);
-  for(uint32_t u = u0; u < u1; ++u) {
-    const uint32_t chunk = order[u];
-    const uint32_t n = pd.dir[chunk].y;
-    const uint32_t i = threadIdx.x * 4;
-    if(i < n) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk * CHUNK_BYTES) + threadIdx.x);
-      const uint32_t rec[4] = { v.x, v.y, v.z, v.w };
+  // the loads of the tile's chunks level by level (order -> directory -> records), so that they overlap
+  uint32_t chunk[WIN_TILE_UNITS], n[WIN_TILE_UNITS]; uint4 v[WIN_TILE_UNITS];
 #pragma unroll
-      for(uint32_t q = 0; q < 4; ++q) if(i + q < n) atomicAdd(&cnt[((rec[q] >> hb) >> WIN_LG) & (wpr - 1)], 1u);
-    }
+  for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) chunk[j] = u0 + j < u1 ? __ldg(order + u0 + j) : 0u;
+#pragma unroll
+  for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) n[j] = u0 + j < u1 ? __ldg(&pd.dir[chunk[j]].y) : 0u;
+#pragma unroll
+  for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) {
+    v[j] = make_uint4(0, 0, 0, 0);
+    if(threadIdx.x * 4 < n[j]) v[j] = __ldg(reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk[j] * CHUNK_BYTES) + threadIdx.x);
+  }
+#pragma unroll
+  for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) {
+    const uint32_t i = threadIdx.x * 4;
+    const uint32_t rec[4] = { v[j].x, v[j].y, v[j].z, v[j].w };
+#pragma unroll
+    for(uint32_t q = 0; q < 4; ++q) if(i + q < n[j]) atomicAdd(&cnt[((rec[q] >> hb) >> WIN_LG) & (wpr - 1)], 1u);
   }
   __syncthreads();
   for(uint32_t i = threadIdx.x; i < wpr; i += WIN_NTH) if(cnt[i]) atomicAdd(&wd.wcursor[(r << wd.wpr_lg) + i], cnt[i]);
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(1024) win_scan_kernel(WinDev wd, unsigned long
   const uint32_t per = (n + 1023) / 1024;
   const uint32_t b = threadIdx.x * per, e = min(b + per, n);
   uint32_t s = 0;
-  for(uint32_t i = b; i < e; ++i) s += wd.wcursor[i];
+  for(uint32_t i = b; i < e; ++i) s += (wd.wcursor[i] + 3u) & ~3u;
   part[threadIdx.x] = s;
   __syncthreads();
   for(uint32_t d = 1; d < 1024; d <<= 1) {
@@ -87,8 +92,13 @@ __global__ void __launch_bounds__(1024) win_scan_kernel(WinDev wd, unsigned long
     part[threadIdx.x] += v;
     __syncthreads();
   }
+  // every window's run starts on a 16-byte boundary (the TMA engine copies it): counts are rounded up to 4 records
   uint32_t run = part[threadIdx.x] - s;            // exclusive prefix of this thread's segment
-  for(uint32_t i = b; i < e; ++i) { const uint32_t c = wd.wcursor[i]; wd.wstart[i] = run; wd.wcursor[i] = run; run += c; }
+  for(uint32_t i = b; i < e; ++i) {
+    const uint32_t c = wd.wcursor[i];
+    wd.wstart[i] = run; wd.wcursor[i] = run; wd.wcnt[i] = c;
+    run += (c + 3u) & ~3u;
+  }
   if(threadIdx.x == 1023) {
     wd.wstart[n] = part[1023];
     if(part[1023] > wd.wrec_cap) atomicAdd(&stats[STAT_POOL_FULL], 1ull);   // the host sizes groups so that this cannot happen
@@ -108,19 +118,23 @@ __global__ void __launch_bounds__(WIN_NTH) win_scatter_kernel(PartDev pd, WinDev
   const uint32_t u0 = wd.unit_first[r] + (blockIdx.x - wd.tile_first[r]) * WIN_TILE_UNITS;
   const uint32_t u1 = min(u0 + WIN_TILE_UNITS, wd.unit_first[r + 1]);
   uint32_t rec[WIN_TILE_UNITS][4]; uint32_t nv[WIN_TILE_UNITS];
+  {
+    uint32_t chunk[WIN_TILE_UNITS], n[WIN_TILE_UNITS];
+#pragma unroll
+    for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) chunk[j] = u0 + j < u1 ? __ldg(order + u0 + j) : 0u;
+#pragma unroll
+    for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) n[j] = u0 + j < u1 ? __ldg(&pd.dir[chunk[j]].y) : 0u;
+#pragma unroll
+    for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) {
+      const uint32_t i = threadIdx.x * 4;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      nv[j] = i < n[j] ? min(4u, n[j] - i) : 0u;
+      if(nv[j]) v = __ldcs(reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk[j] * CHUNK_BYTES) + threadIdx.x);
+      rec[j][0] = v.x; rec[j][1] = v.y; rec[j][2] = v.z; rec[j][3] = v.w;
+    }
+  }
 #pragma unroll
   for(uint32_t j = 0; j < WIN_TILE_UNITS; ++j) {
-    nv[j] = 0;
-    if(u0 + j < u1) {
-      const uint32_t chunk = order[u0 + j];
-      const uint32_t n = pd.dir[chunk].y;
-      const uint32_t i = threadIdx.x * 4;
-      if(i < n) {
-        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(pd.pool + (size_t)chunk * CHUNK_BYTES) + threadIdx.x);
-        rec[j][0] = v.x; rec[j][1] = v.y; rec[j][2] = v.z; rec[j][3] = v.w;
-        nv[j] = min(4u, n - i);
-      }
-    }
 #pragma unroll
     for(uint32_t q = 0; q < 4; ++q) if(q < nv[j]) atomicAdd(&cnt[((rec[j][q] >> hb) >> WIN_LG) & (wpr - 1)], 1u);
   }
@@ -160,68 +174,117 @@ __global__ void __launch_bounds__(WIN_NTH) win_scatter_kernel(PartDev pd, WinDev
   }
 }
 
-// ---- one CTA per window: probe in shared memory -----------------------------------------------------
+// ---- persistent window insert: probe in shared memory, windows and records moved by the TMA engine -------------
+constexpr uint32_t WIN2_NTH = 1024;
+constexpr uint32_t WIN2_RB  = 10240;               // records per batch (a window of iid input holds ~0.6 * WIN_SLOTS)
+constexpr uint32_t WIN2_NONE = 0xFFFFFFFFu;
+constexpr size_t   WIN2_SMEM = (size_t)2 * WIN_SLOTS * 4 + (size_t)2 * WIN2_RB * 4;
+
+struct Win2Info { uint32_t task, b, n, pad; };
+
 template<int KW>
-__global__ void __launch_bounds__(WIN_NTH) win_insert_kernel(TableDev T, PartDev pd, WinDev wd, const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
-  extern __shared__ __align__(16) uint32_t win[];
+__global__ void __launch_bounds__(WIN2_NTH, 1) win_insert2_kernel(TableDev T, PartDev pd, WinDev wd, const uint64_t* __restrict__ inv_lut_g, uint32_t nbytes) {
+  extern __shared__ __align__(128) uint8_t w2smem[];
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t extra;
+  __shared__ Win2Info info[2];
+  __shared__ uint32_t cursor[2];                   // next unclaimed record of the batch in each stage
+  uint32_t* const winb0 = reinterpret_cast<uint32_t*>(w2smem);
+  uint32_t* const recb0 = winb0 + 2 * WIN_SLOTS;
   const uint32_t fb = T.fbits, rb = T.rbits, hb = fb - rb;
   const uint32_t fmask = (1u << fb) - 1u, one = 1u << fb, cb = 32 - fb;
   const uint32_t hmask = hb ? ((1u << hb) - 1u) : 0u;
   uint32_t* tab = (uint32_t*)T.slots;
   const uint32_t n_tasks = wd.G << wd.wpr_lg;
+  const uint32_t tid = threadIdx.x;
   uint32_t n_ins = 0, n_new = 0, n_rep = 0;
-  for(uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-    const uint32_t b = wd.wstart[task], e = wd.wstart[task + 1];
-    if(b == e) continue;                               // (uniform over the CTA)
-    const uint64_t slot_base = ((uint64_t)(wd.g0 + (task >> wd.wpr_lg)) << pd.region_bits) + ((uint64_t)(task & ((1u << wd.wpr_lg) - 1)) << WIN_LG);
-    uint4* gw = reinterpret_cast<uint4*>(tab + slot_base);
-    uint4* sw = reinterpret_cast<uint4*>(win);
-    for(uint32_t i = threadIdx.x; i < WIN_SLOTS / 4; i += WIN_NTH) sw[i] = __ldcs(gw + i);
-    __syncthreads();
-    // Every lane keeps one record in flight and performs ONE probe per trip of the loop; a lane whose record
-    // is settled takes the next record of its stride at once (the one after it is already on its way from
-    // memory), so lanes with long probe sequences do not idle the rest of the warp.
-    {
-      uint32_t i = b + threadIdx.x;
-      bool have = i < e;
-      uint32_t rec = have ? __ldcs(wd.wrec + i) : 0u;
-      bool have_n = have && i + WIN_NTH < e;
-      uint32_t nxt = have_n ? __ldcs(wd.wrec + i + WIN_NTH) : 0u;
-      uint32_t local = (hb < 32 ? rec >> hb : 0u) & (WIN_SLOTS - 1), high = rec & hmask, kf0 = high << rb;
+
+  auto slot_base_of = [&](uint32_t task) -> uint64_t {
+    return ((uint64_t)(wd.g0 + (task >> wd.wpr_lg)) << pd.region_bits) + ((uint64_t)(task & ((1u << wd.wpr_lg) - 1)) << WIN_LG);
+  };
+  // thread 0: the next non-empty window of this CTA's stride at or after `from`, and the copies that bring it into stage s
+  uint32_t next_from = blockIdx.x;                 // (thread 0 only)
+  auto prefetch = [&](uint32_t s) {
+    uint32_t t = next_from, c = 0;
+    while(t < n_tasks && (c = wd.wcnt[t]) == 0) t += gridDim.x;
+    if(t >= n_tasks) { info[s].task = WIN2_NONE; next_from = t; mbar_arrive(&full[s]); return; }
+    next_from = t + gridDim.x;
+    const uint32_t b = wd.wstart[t];
+    info[s].task = t; info[s].b = b; info[s].n = c; cursor[s] = WIN2_NTH;
+    const uint32_t rbytes = ((min(c, WIN2_RB) + 3u) & ~3u) * 4u;
+    mbar_expect_tx(&full[s], WIN_SLOTS * 4u + rbytes);
+    tma_load_1d(winb0 + s * WIN_SLOTS, tab + slot_base_of(t), WIN_SLOTS * 4u, &full[s]);
+    tma_load_1d(recb0 + s * WIN2_RB, wd.wrec + b, rbytes, &full[s]);
+  };
+  if(tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&extra, 1); }
+  __syncthreads();
+  if(tid == 0) { fence_proxy_async(); prefetch(0); prefetch(1); }
+
+  uint32_t xphase = 0;
+  for(uint32_t it = 0; ; ++it) {
+    const uint32_t s = it & 1u;
+    mbar_wait(&full[s], (it >> 1) & 1u);
+    const Win2Info inf = info[s];
+    if(inf.task == WIN2_NONE) break;               // (the same for every thread of the CTA)
+    uint32_t* const win = winb0 + s * WIN_SLOTS;
+    const uint32_t* const recs = recb0 + s * WIN2_RB;
+    const uint64_t slot_base = slot_base_of(inf.task);
+    for(uint32_t off = 0; off < inf.n; off += WIN2_RB) {
+      const uint32_t nb = min(WIN2_RB, inf.n - off);
+      if(off) {                                    // a window with more than one batch of records (skewed input)
+        __syncthreads();
+        if(tid == 0) {
+          const uint32_t rbytes = ((nb + 3u) & ~3u) * 4u;
+          cursor[s] = WIN2_NTH;
+          mbar_expect_tx(&extra, rbytes);
+          tma_load_1d(recb0 + s * WIN2_RB, wd.wrec + inf.b + off, rbytes, &extra);
+        }
+        mbar_wait(&extra, xphase);
+        xphase ^= 1u;
+      }
+      // Every lane keeps one record in flight and performs ONE probe per trip of the loop; a lane whose record is settled
+      // takes the next unclaimed record of the batch (shared cursor), so the lanes of a warp stay busy until the batch is
+      // exhausted whatever the lengths of their probe sequences.
+      uint32_t i = tid;
+      bool have = i < nb;
+      uint32_t rec = have ? recs[i] : 0u;
+      uint32_t local = (rec >> hb) & (WIN_SLOTS - 1), kf = ((rec & hmask) << rb) | 1u;
       uint32_t at = local, p = 0;
       while(have) {
-        bool done = false;
-        if(at >= WIN_SLOTS) {                              // leaves the window: the global path takes it after this kernel
-          const unsigned long long d = atomicAdd(wd.def_n, 1ull);
-          if(d < wd.def_cap) { wd.def_pos[d] = slot_base + local; wd.def_high[d] = high; }
-          else atomicAdd(&T.stats[STAT_POOL_FULL], 1ull);
-          done = true;
-        } else {
-          const uint32_t kf = kf0 | (p + 1);
+        bool fetch = true;
+        if(at < WIN_SLOTS) {
           const uint32_t o = atomicCAS(&win[at], 0u, kf | one);
-          if(o == 0u) { ++n_new; ++n_ins; n_rep += p; done = true; }
+          if(o == 0u) { ++n_new; ++n_ins; n_rep += p; }
           else if((o & fmask) == kf) {
             const uint32_t o2 = atomicAdd(&win[at], one);
             if((((o2 >> fb) + 1) >> cb) != 0) k2_carry(T.ovf_keys, T.ovf_vals, T.ovf_mask, T.stats, slot_base + at);
-            ++n_ins; n_rep += p; done = true;
-          } else if(p >= T.max_reprobe) {
-            k2_fail<KW>(T.shard_index, T.local_lsize, T.lsize, T.stats, T.fail_keys, T.fail_counts, T.fail_cap, slot_base + local, high, inv_lut_g, nbytes);
-            done = true;
-          } else { ++p; at += p; }                         // pos + i(i+1)/2
+            ++n_ins; n_rep += p;
+          } else if(p < T.max_reprobe) { ++p; at += p; ++kf; fetch = false; }          // pos + i(i+1)/2, reprobe field + 1
+          else k2_fail<KW>(T.shard_index, T.local_lsize, T.lsize, T.stats, T.fail_keys, T.fail_counts, T.fail_cap, slot_base + local, rec & hmask, inv_lut_g, nbytes);
+        } else {                                   // leaves the window: the global path takes it after this kernel
+          const unsigned long long d = atomicAdd(wd.def_n, 1ull);
+          if(d < wd.def_cap) { wd.def_pos[d] = slot_base + local; wd.def_high[d] = rec & hmask; }
+          else atomicAdd(&T.stats[STAT_POOL_FULL], 1ull);
         }
-        if(done) {
-          rec = nxt; have = have_n; i += WIN_NTH;
-          have_n = have && i + WIN_NTH < e;
-          if(have_n) nxt = __ldcs(wd.wrec + i + WIN_NTH);
-          local = (hb < 32 ? rec >> hb : 0u) & (WIN_SLOTS - 1); high = rec & hmask; kf0 = high << rb;
+        if(fetch) {
+          i = atomicAdd(&cursor[s], 1u);
+          have = i < nb;
+          rec = have ? recs[i] : 0u;
+          local = (rec >> hb) & (WIN_SLOTS - 1); kf = ((rec & hmask) << rb) | 1u;
           at = local; p = 0;
         }
       }
     }
+    fence_proxy_async();                           // this thread's writes to the window, before the TMA engine reads it
     __syncthreads();
-    for(uint32_t i = threadIdx.x; i < WIN_SLOTS / 4; i += WIN_NTH) __stcs(gw + i, sw[i]);
-    __syncthreads();
+    if(tid == 0) {
+      tma_store_1d(tab + slot_base, win, WIN_SLOTS * 4u);
+      tma_commit_group();
+      tma_wait_group_read0();                      // the stage may be overwritten
+      prefetch(s);
+    }
   }
+  if(tid == 0) tma_wait_group0();                  // every window is back in the table before the kernel ends
   unsigned long long v[3] = { n_ins, n_new, n_rep };
 #pragma unroll
   for(int q = 0; q < 3; ++q) {
