@@ -124,8 +124,16 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # the reference's own CPU path on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def write_sample_fasta(path, n_bases, seed=4242):
-    """Same shape as the device generator / generate_sequence: '>read1', 70 bases per line."""
+def write_sample_fasta(path, n_bases, seed=3141592653):
+    """The sample input: the reference's own generator (jellyfish/generate_sequence.cc, the seed of its test-suite) when
+    oracle/_ref was built; otherwise numpy iid ACGT in the same shape ('>read1', 70 bases per line)."""
+    import jfutil
+    if os.path.exists(jfutil.REF_GEN):
+        prefix = path[:-3] if path.endswith(".fa") else path
+        jfutil.run([jfutil.REF_GEN, "-o", prefix, "-s", str(seed), str(n_bases)])
+        if prefix + ".fa" != path:
+            os.rename(prefix + ".fa", path)
+        return "generate_sequence -s %d %d" % (seed, n_bases)
     import numpy as np
     rng = np.random.default_rng(seed)
     with open(path, "wb") as f:
@@ -143,17 +151,19 @@ def write_sample_fasta(path, n_bases, seed=4242):
             if n > full:
                 f.write(seq[full:].tobytes() + b"\n")
             left -= n
+    return "numpy iid ACGT, %d bases" % n_bases
 
 
-def cpu_reference_run(sample_fa, n_bases, k, size, threads, workdir):
+def cpu_reference_run(sample_fa, n_bases, k, size, threads, workdir, bf_size=0):
     """One timed run of the reference binary (or the C restatement) -> k-mers/s of its Counting phase."""
     import jfutil
     timing = os.path.join(workdir, "timing.txt")
     out = os.path.join(workdir, "ref.jf")
+    bf = ["--bf-size", str(bf_size)] if bf_size else []
     if os.path.exists(jfutil.REF_JF):
         kind = "reference"
         cmd = [jfutil.REF_JF, "count", "-m", str(k), "-s", str(size), "-t", str(threads), "-C", "--no-write",
-               "--timing", timing, "-o", out, sample_fa]
+               "--timing", timing, "-o", out] + bf + [sample_fa]
         t0 = time.perf_counter()
         subprocess.check_call(cmd, env=dict(os.environ, SOURCE_DATE_EPOCH="0"))
         wall = time.perf_counter() - t0
@@ -165,45 +175,55 @@ def cpu_reference_run(sample_fa, n_bases, k, size, threads, workdir):
     else:
         kind = "port"
         threads = 1
-        cmd = [jfutil.ORACLE_C, "count", "-m", str(k), "-s", str(size), "-C", "-o", out, sample_fa]
+        cmd = [jfutil.ORACLE_C, "count", "-m", str(k), "-s", str(size), "-C", "-o", out] + bf + [sample_fa]
         t0 = time.perf_counter()
         subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
         secs = time.perf_counter() - t0
     return (n_bases - k + 1) / secs, kind, threads, secs
 
 
+def cpu_sample_plan(args):
+    """Bounded sample of the workload for the CPU arm: bases and table size (final load ~0.37, no doubling)."""
+    import jfutil
+    sample = min(args.cpu_sample_bases, args.bases)
+    if not os.path.exists(jfutil.REF_JF):
+        sample = min(sample, 5_000_000)
+    size = 1 << max(10, (int(sample / 0.6) - 1).bit_length())
+    bf = int(args.bf_size * (sample / float(args.bases))) if args.bf_size else 0
+    return sample, size, bf
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import jfutil
-    k = 21
-    sample = args.cpu_sample_bases
+    k = args.k
     threads = os.cpu_count() or 1
-    have_ref = os.path.exists(jfutil.REF_JF)
-    if not have_ref:
-        sample = min(sample, 5_000_000)
-    size = 1 << max(10, (int(sample / 0.6) - 1).bit_length())   # final load ~0.3-0.6, no doubling
+    sample, size, bf = cpu_sample_plan(args)
     with tempfile.TemporaryDirectory() as d:
         fa = os.path.join(d, "sample.fa")
-        write_sample_fasta(fa, sample)
+        how = write_sample_fasta(fa, sample)
         with open(fa, "rb") as f:          # warm the page cache
             while f.read(1 << 24):
                 pass
         vals = []
         for i in range(args.warmup + args.steps):
-            v, kind, cores, secs = cpu_reference_run(fa, sample, k, size, threads, d)
+            v, kind, cores, secs = cpu_reference_run(fa, sample, k, size, threads, d, bf)
             if i >= args.warmup:
                 vals.append((v, secs))
-    value = sum(v for v, _ in vals) / len(vals)
+    rates = sorted(v for v, _ in vals)
+    value = sum(rates) / len(rates)
     ms = 1e3 * sum(s for _, s in vals) / len(vals)
-    sample_desc = "%d bp iid FASTA (70-col), jellyfish count -m 21 -s %d -t %d -C, Counting phase of --timing" % (sample, size, cores)
+    sample_desc = ("each step = %s (%d bp of the %d bp workload), jellyfish count -m %d -s %d%s -t %d -C --no-write, Counting phase of "
+                   "--timing; the table is sized for the sample (the workload's -s %s would be %d GB of host memory per step)"
+                   % (how, sample, args.bases, k, size, (" --bf-size %d" % bf) if bf else "", cores, args.size,
+                      parse_size(args.size) * 26 // 8 // 10**9))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "k=21 canonical, 10 Gbp synthetic FASTA (bounded CPU sample per step: %s)" % sample_desc},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
+        "impl": "reference", "metric": METRIC if k == 21 else "k-mers counted/sec at k=%d" % k, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc,
+                         "min": rates[0], "median": statistics.median(rates), "max": rates[-1]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,13 +239,21 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bases", type=int, default=10_000_000_000, help="bases of synthetic sequence per GPU")
-    ap.add_argument("--size", default="16G", help="-s of the per-GPU table share (global table = N x this)")
-    ap.add_argument("--k", type=int, default=21)
+    ap.add_argument("--config", default="k21", choices=sorted(CONFIGS), help="BASELINE config (see the module docstring)")
+    ap.add_argument("--bases", type=int, default=None, help="bases of synthetic sequence per GPU")
+    ap.add_argument("--size", default=None, help="-s of the per-GPU table share (global table = N x this)")
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--bf-size", type=int, default=None)
     ap.add_argument("--cpu-sample-bases", type=int, default=400_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump", action="store_true", help="also time one full sorted dump (Writing phase) to /dev/null-like sink")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.k = args.k or cfg["k"]
+    args.bases = args.bases or cfg["bases"]
+    args.size = args.size or cfg["size"]
+    args.bf_size = cfg["bf"] if args.bf_size is None else args.bf_size
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -267,13 +295,16 @@ def main():
         torch.cuda.synchronize()
 
     size = parse_size(args.size)
+    t_init = time.perf_counter()
     if world > 1:
         from jellyfish_b200.distributed import ShardedCounter
         counter = ShardedCounter(size * world, 7, k=k, canonical=True, rank=rank, world=world, device=local_rank)
         hc = counter.hc
     else:
         counter = None
-        hc = HashCounter(size, 7, k=k, canonical=True, device=local_rank)
+        hc = HashCounter(size, 7, k=k, canonical=True, device=local_rank, bf_size=args.bf_size)
+    torch.cuda.synchronize()
+    init_s = time.perf_counter() - t_init
     info = hc.info()
 
     def one_step_device():
@@ -284,7 +315,7 @@ def main():
             hc.add_device_text(text.data_ptr(), n_text)
         return hc.done()
 
-    # ---- value: device-resident input, CUDA events on the engine's stream, max over ranks ----
+    # ---- value: device-resident input; whole steps between synchronised barriers, max over ranks ----
     for _ in range(args.warmup):
         st = one_step_device()
     launches0 = lib.jfgpu_kernel_launches()
@@ -292,13 +323,16 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    dev_secs, kern_secs, kern_launches, drain_secs = 0.0, 0.0, 0, 0.0
+    acc = {"seconds_count": 0.0, "seconds_count_kernel": 0.0, "count_kernel_launches": 0, "seconds_drain": 0.0,
+           "seconds_win_hist": 0.0, "seconds_win_scatter": 0.0, "seconds_win_insert": 0.0}
+    step_secs = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         st = one_step_device()
-        dev_secs += st["seconds_count"]
-        kern_secs += st["seconds_count_kernel"]
-        kern_launches += st["count_kernel_launches"]
-        drain_secs += st["seconds_drain"]
+        torch.cuda.synchronize()
+        step_secs.append(time.perf_counter() - ts)
+        for key in acc:
+            acc[key] += st[key]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -306,65 +340,70 @@ def main():
     tot = torch.tensor([st["kmers"], st["inserted"], st["distinct"]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tot)          # keys are inserted by their owner: only the sums must agree
-    assert st["kmers"] == kmers_per_step and tot[0].item() == tot[1].item() == kmers_per_step * world, (st, tot.tolist())
+    assert st["kmers"] == kmers_per_step and tot[0].item() == kmers_per_step * world, (st, tot.tolist())
+    if not args.bf_size:
+        assert tot[0].item() == tot[1].item(), (st, tot.tolist())
     distinct_total = int(tot[2].item())
-    t = torch.tensor([dev_secs, wall], dtype=torch.float64, device=dev)
+    t = torch.tensor([acc["seconds_count"], wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_secs, wall = t.tolist()
-    # the timed quantity: whole steps (table clear + all kernels), wall clock between synchronised barriers
     ms_per_step = 1e3 * wall / args.steps
     value = kmers_per_step * world * args.steps / wall
 
-    # ---- roofline of the dominant kernel ----
-    # direct insertion:      K1 count_kernel does everything; B_alg = 71/70 + 32*p + 32 bytes per k-mer
-    # region-by-region mode: K1 (parse/hash/stage records) writes rec bytes per k-mer, K2
-    #   (insert_chunks_kernel) reads them and sweeps the table once: rec + 2*table_bytes/kmers
+    # ---- roofline: every kernel class of a step against the measured HBM peak, the dominant one on top ----
+    # algorithmic bytes per k-mer:
+    #   K1  extract: 71/70 text + rec written
+    #   K2  window form: win_hist reads rec; win_scatter reads + writes rec; win_insert reads rec and sweeps the table
+    #       once (read + write every slot); L2 form (insert_chunks): rec + table sweep
+    #   direct insertion (small tables / Bloom counter): the north star's 71/70 + 32 p + 32
     p_mean = 1.0 + st["reprobes"] / max(1, st["inserted"])
     peak, peak_src = measured_peak()
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic.json")
     tinfo = {}
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tfile):
         try:
             tinfo = json.load(open(tfile))
         except Exception:
             tinfo = {}
+    nk = float(kmers_per_step * args.steps)
     kernels = []
-    nk = kmers_per_step * args.steps
+
+    def add_kernel(name, secs, bpk, launches_=None, traffic_key=None):
+        if secs <= 0:
+            return
+        ach = nk * bpk / secs / 1e9
+        tr = tinfo.get(traffic_key) if traffic_key else None
+        kernels.append({"kernel": name, "seconds_per_step": secs / args.steps, "alg_bytes_per_kmer": bpk, "achieved": ach, "frac": ach / peak,
+                        "launches_per_step": (launches_ / args.steps) if launches_ else None,
+                        "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_note": (tr or {}).get("note")})
+
+    sweep = 2.0 * info["table_bytes"] / kmers_per_step
     if info["part_regions"]:
         rec = info["part_rec_bytes"]
-        b1 = 71.0 / 70.0 + rec
-        b2 = rec + 2.0 * info["table_bytes"] / kmers_per_step
-        kernels.append({"kernel": "count_kernel<1,%d,2,1024> (K1: parse+hash+stage records)" % info["slot_bits"], "seconds": kern_secs / args.steps,
-                        "alg_bytes_per_kmer": b1, "achieved": nk * b1 / kern_secs / 1e9 if kern_secs else None, "launches": kern_launches,
-                        "traffic": tinfo.get("k1_dram_bytes_per_launch")})
-        kernels.append({"kernel": "insert_chunks_kernel<1,%d> (K2: region-by-region insert)" % info["slot_bits"], "seconds": drain_secs / args.steps,
-                        "alg_bytes_per_kmer": b2, "achieved": nk * b2 / drain_secs / 1e9 if drain_secs else None,
-                        "traffic": tinfo.get("k2_dram_bytes_per_launch")})
+        add_kernel("extract_kernel (K1: parse, canonical k-mers, GF(2) hash, region records)", acc["seconds_count_kernel"], 71.0 / 70.0 + rec,
+                   acc["count_kernel_launches"], "extract_kernel")
+        if acc["seconds_win_insert"] > 0:
+            add_kernel("win_hist_kernel (K2a: records per window)", acc["seconds_win_hist"], rec, None, "win_hist_kernel")
+            add_kernel("win_scatter_kernel (K2b: records grouped by window)", acc["seconds_win_scatter"], 2.0 * rec, None, "win_scatter_kernel")
+            add_kernel("win_insert2_kernel (K2c: shared-memory window insert, table swept once)", acc["seconds_win_insert"], rec + sweep, None, "win_insert2_kernel")
+        else:
+            add_kernel("insert_chunks_kernel (K2, L2 form: region-by-region insert)", acc["seconds_drain"], rec + sweep, None, "insert_chunks_kernel")
     else:
-        b_alg = 71.0 / 70.0 + 32.0 * p_mean + 32.0
-        kernels.append({"kernel": "count_kernel<1,%d,0,512> (direct insert)" % info["slot_bits"], "seconds": kern_secs / args.steps,
-                        "alg_bytes_per_kmer": b_alg, "achieved": nk * b_alg / kern_secs / 1e9 if kern_secs else None, "launches": kern_launches,
-                        "traffic": tinfo.get("direct_dram_bytes_per_launch")})
-    dom = max(kernels, key=lambda x: x["seconds"] or 0)
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": (dom["achieved"] / peak) if dom["achieved"] else None, "traffic": dom.get("traffic"), "peak_source": peak_src,
-                "alg_bytes_per_kmer": dom["alg_bytes_per_kmer"], "mean_probes": p_mean, "avg_seconds_per_step": dom["seconds"],
-                "note": "HBM traffic of the region-by-region pipeline is near its algorithmic minimum (ncu, profiles/traffic.json); the "
-                        "kernels are bound by instruction issue (K1) and by L2 atomic/load throughput (K2), not by HBM", "kernels": kernels}
-    # the north star's own yardstick: k-mers/s x (71/70 + 32 p + 32) bytes against the HBM peak, i.e. what a
-    # table filled by random HBM accesses would have to move; and the measured random-atomic ceiling of this
-    # GPU (scripts/micro/atomics.cu: 20.5 G random 32-bit atomics/s over a 32 GB region)
+        add_kernel("extract_kernel (direct insert)", acc["seconds_count_kernel"], 71.0 / 70.0 + 32.0 * p_mean + 32.0, acc["count_kernel_launches"], "extract_kernel_direct")
+    dom = max(kernels, key=lambda x: x["seconds_per_step"])
+    step_bytes = sum(x["alg_bytes_per_kmer"] for x in kernels)
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": dom["traffic"], "peak_source": peak_src, "alg_bytes_per_kmer": dom["alg_bytes_per_kmer"], "mean_probes": p_mean,
+                "avg_seconds_per_step": dom["seconds_per_step"], "kernels": kernels,
+                "whole_step": {"alg_bytes_per_kmer": step_bytes, "achieved": value / world * step_bytes / 1e9,
+                               "frac": value / world * step_bytes / 1e9 / peak,
+                               "note": "all kernels of the step (table clear excluded from the bytes, included in the time)"}}
+    # the north star's own yardstick: k-mers/s x (71/70 + 32 p + 32) bytes against the HBM peak, i.e. what a table filled by
+    # random HBM accesses would have to move
     b_rand = 71.0 / 70.0 + 32.0 * p_mean + 32.0
-    roofline["random_access_model"] = {
-        "alg_bytes_per_kmer": b_rand, "achieved": value / world * b_rand / 1e9, "unit": "GB/s", "frac_of_hbm_peak": value / world * b_rand / 1e9 / peak,
-        "measured_random_atomic_ceiling_gops": 20.5, "ceiling_kmers_per_s": 20.5e9 / p_mean,
-        "vs_random_atomic_ceiling": (value / world) / (20.5e9 / p_mean)}
-    if info["part_regions"] and drain_secs:
-        # K2 against the measured L2 ceiling for its operation mix (scripts/micro/mix.cu: ~50 G keys/s at load 0.58)
-        roofline["l2_op_mix"] = {"achieved_gkeys_per_s": nk / drain_secs / 1e9, "measured_ceiling_gkeys_per_s": 50.0,
-                                 "frac": nk / drain_secs / 1e9 / 50.0}
+    roofline["random_access_model"] = {"alg_bytes_per_kmer": b_rand, "achieved": value / world * b_rand / 1e9, "unit": "GB/s",
+                                       "frac_of_hbm_peak": value / world * b_rand / 1e9 / peak}
 
     # ---- e2e: the public host API with pinned HOST buffers, copies inside the timed region ----
     e2e = None
@@ -399,40 +438,94 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall2 = t.item()
         e2e = {"value": kmers_per_step * world * args.steps / wall2, "unit": UNIT, "h2d_bytes_per_step": n_text * world,
-               "d2h_bytes_per_step": 80 * world, "ms_per_step": 1e3 * wall2 / args.steps}
+               "d2h_bytes_per_step": 104 * world, "ms_per_step": 1e3 * wall2 / args.steps}
         lib.jfgpu_host_free(hptr)
+
+    # ---- Writing phase: one full sorted dump of the resident table through the C ABI (bytes discarded by the sink) ----
+    writing = None
+    if args.dump and world == 1:
+        torch.cuda.synchronize()
+        tw = time.perf_counter()
+        nrec = hc.dump_records(sink="discard")
+        writing_s = time.perf_counter() - tw
+        out_bytes = nrec * ((2 * k + 7) // 8 + 4)
+        writing = {"seconds": writing_s, "records": nrec, "bytes": out_bytes, "GB_per_s": out_bytes / writing_s / 1e9,
+                   "note": "jfgpu_dump: records ordered tile by tile on the device, device->pinned host copies overlapped with the next "
+                           "segment; the sink discards the bytes (no file system in the timed region)"}
+
+    # ---- multi-GPU parity inside the bench: a committed golden case through the sharded path ----
+    parity_n = None
+    if world > 1:
+        parity_n = sharded_parity_check(world, rank, local_rank)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import jfutil
-        sample = args.cpu_sample_bases if os.path.exists(jfutil.REF_JF) else 5_000_000
-        csize = 1 << max(10, (int(sample / 0.6) - 1).bit_length())
+        sample, csize, cbf = cpu_sample_plan(args)
         with tempfile.TemporaryDirectory() as d:
             fa = os.path.join(d, "sample.fa")
-            write_sample_fasta(fa, sample)
-            v, kind, cores, secs = cpu_reference_run(fa, sample, k, csize, os.cpu_count() or 1, d)
+            how = write_sample_fasta(fa, sample)
+            v, kind, cores, secs = cpu_reference_run(fa, sample, k, csize, os.cpu_count() or 1, d, cbf)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "%d bp iid FASTA, jellyfish count -m 21 -s %d -t %d -C (Counting phase, %.1f s)" % (sample, csize, cores, secs)}
+               "sample": "%s; jellyfish count -m %d -s %d -t %d -C (Counting phase, %.1f s); table sized for the sample" % (how, k, csize, cores, secs)}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": {"workload": "k=%d canonical, %d bp synthetic FASTA per GPU (device-generated iid ACGT, 70-col lines, "
-                                   "shape of generate_sequence), -s %s per GPU -> global 2^%d slots (%d-bit slots, %.1f GB per GPU)"
-                                   % (k, n_bases, args.size, info["lsize"], info["slot_bits"], info["table_bytes"] / 1e9),
-                       "l2": "inputs (%.1f GB text, %.1f GB table) exceed L2; no flush needed" % (n_text / 1e9, info["table_bytes"] / 1e9),
-                       "timed_region": "table clear + all kernels of a step; inputs resident in HBM",
-                       "parallelism": "1 GPU" if world == 1 else "table sharded by top hash bits over %d GPUs, NCCL all-to-all" % world},
-            "device_seconds_per_step": dev_secs / args.steps,
+            "metric": METRIC if k == 21 else "k-mers counted/sec at k=%d" % k, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "engine": {"global_lsize": info["lsize"], "slot_bits": info["slot_bits"], "table_bytes_per_gpu": info["table_bytes"],
+                       "regions": info["part_regions"], "record_bytes": info["part_rec_bytes"], "text_bytes_per_gpu": n_text,
+                       "timed_region": "table clear + all kernels of a step; inputs resident in HBM; wall clock between synchronised barriers",
+                       "input": "device-generated iid ACGT (counter-based RNG), one '>read1' record, 70-column lines"},
+            "device_seconds_per_step": dev_secs / args.steps, "step_ms": {"min": 1e3 * min(step_secs), "median": 1e3 * statistics.median(step_secs), "max": 1e3 * max(step_secs)},
+            "init_s": init_s, "writing": writing,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "distinct": distinct_total, "load_factor": distinct_total / float(info["size"]),
+            "distinct": distinct_total, "load_factor": distinct_total / float(info["size"]), "parity_n": parity_n,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_parity_check(world, rank, local_rank):
+    """After the timed steps: the golden case `multi_files` counted through the sharded (NCCL) path, the rank-ordered
+    concatenation of the shard dumps compared with the reference's golden md5.  Returns the parity_n object (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    import gen
+    import jfutil
+    from cases import CASES
+    from jellyfish_b200.distributed import ShardedCounter, concat_shards
+    name = "multi_files"
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))[name]
+    args, ins = CASES[name]
+    k = int(args[args.index("-m") + 1])
+    v = args[args.index("-s") + 1]
+    size = int(v[:-1]) * {"k": 10**3, "M": 10**6, "G": 10**9}[v[-1]] if v[-1] in "kMG" else int(v)
+    tmp = os.path.join(tempfile.gettempdir(), "jf_parity_n")
+    if rank == 0:
+        os.makedirs(tmp, exist_ok=True)
+        gen.make_all(tmp)
+    dist.barrier()
+    inputs = {n: os.path.join(tmp, n) for n in os.listdir(tmp)}
+    os.environ["SOURCE_DATE_EPOCH"] = "0"
+    sc = ShardedCounter(size, 7, k=k, canonical="-C" in args, rank=rank, world=world, device=local_rank, batch_bytes=300000)
+    for j, nm in enumerate(ins):
+        data = open(inputs[nm], "rb").read() if (j % world) == rank else b""
+        buf = torch.frombuffer(bytearray(data + b"\0" * 16), dtype=torch.uint8).to(torch.device("cuda", local_rank))
+        sc.add_device_text(buf.data_ptr(), len(data))
+    sc.done()
+    out = os.path.join(tmp, "parity")
+    sc.dump_shard(out)
+    dist.barrier()
+    res = None
+    if rank == 0:
+        db = concat_shards(out, world, out + ".jf")
+        h, b = jfutil.split_db(db)
+        res = {"case": name, "world": world, "md5_ok": jfutil.md5(b) == golden["body_md5"], "header_ok": jfutil.semantic(h) == golden["header"]}
+    sc.hc.close()
+    return res
 
 
 if __name__ == "__main__":

@@ -77,7 +77,7 @@ typedef struct {
   uint32_t k2_mode;        /* how the staged records reach the table (K2): 0 = default (shared-memory window
                               insert where the geometry allows it, else the L2 kernels), 1 = L2 kernels only,
                               2 = the generic L2 kernel only (no 32-bit specialisation); for tests/benchmarks */
-  uint32_t region_mb;      /* target size of a table region of the region-by-region insertion (0 = default 32) */
+  uint32_t region_mb;      /* target size of a table region of the region-by-region insertion (0 = default 64) */
   uint32_t bloom_counter;  /* 1: this engine builds a Bloom counter instead of a hash table -- `jellyfish bc`
                               (sub_commands/bc_main.cc:84-161): bf_size = expected number of k-mers (-s), bf_fp =
                               false positive rate (-f); `size`, `counter_len`, `max_reprobe` are ignored.  Feed text as
@@ -129,6 +129,8 @@ typedef struct {
                               summed over its launches (CUDA events on the launch stream) */
   uint64_t count_kernel_launches;
   double   seconds_drain;  /* device time of the region-by-region insertion passes (CUDA events) */
+  double   seconds_win_hist, seconds_win_scatter, seconds_win_insert;   /* of which: the window kernels of K2 (jf_window.cuh),
+                              CUDA events around their launches; insert includes the deferred-record kernel */
 } jfgpu_stats;
 
 /* -- life cycle: hash_counter ctor / dtor (hash_counter.hpp:50-68) ------------------ */

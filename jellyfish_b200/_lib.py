@@ -51,6 +51,7 @@ class Stats(C.Structure):
         ("kmers", C.c_uint64), ("inserted", C.c_uint64), ("distinct", C.c_uint64), ("reprobes", C.c_uint64),
         ("overflowed", C.c_uint64), ("regrows", C.c_uint64), ("bytes", C.c_uint64), ("seconds_count", C.c_double),
         ("seconds_count_kernel", C.c_double), ("count_kernel_launches", C.c_uint64), ("seconds_drain", C.c_double),
+        ("seconds_win_hist", C.c_double), ("seconds_win_scatter", C.c_double), ("seconds_win_insert", C.c_double),
     ]
 
 

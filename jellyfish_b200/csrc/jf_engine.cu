@@ -128,6 +128,9 @@ struct jfgpu_engine {
   double kernel_ms = 0; uint64_t kernel_launches = 0;
   double drain_ms = 0; cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
   int count_smem = 0;
+  // CUDA events around the window kernels of a drain: [4 per group] hist begin, scatter begin, insert begin, insert end
+  std::vector<cudaEvent_t> wev; size_t wev_used = 0;
+  double win_ms[3] = { 0, 0, 0 };
   // failure counter watched one group behind (hash_counter::add -> handle_full_ary), without draining the stream
   unsigned long long* h_watch = nullptr; cudaEvent_t ev_watch[2] = { nullptr, nullptr };
 };
@@ -263,8 +266,9 @@ int dispatch(jfgpu_engine* e, unsigned kw, unsigned sb, F&& f) {
 }
 
 template<int NTH>
-size_t count_smem_bytes(size_t lut_bytes, size_t stage_bytes, size_t bloom_bytes = 0) {
-  return ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + (stage_bytes ? PMAX * 4 + stage_bytes : 0) + bloom_bytes;
+size_t count_smem_bytes(size_t lut_bytes, size_t stage_bytes, size_t bloom_bytes = 0, bool fast = false) {
+  const size_t part = fast ? (size_t)RING_P * 8 + (size_t)RING_P * RING * 4 : (stage_bytes ? PMAX * 4 + stage_bytes : 0);
+  return ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15) + lut_bytes + part + bloom_bytes;
 }
 
 int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
@@ -303,8 +307,9 @@ void part_configure(jfgpu_engine* e) {
   ps.P = 0;
   if(e->p.no_partition || t.bytes() < ((size_t)(e->p.part_min_mb ? e->p.part_min_mb : 256) << 20)) return;       // small tables live in L2 anyway
   uint32_t P = 256;
-  const size_t region_target = (size_t)(e->p.region_mb ? e->p.region_mb : 32) << 20;
-  while(P < (uint32_t)PMAX && (t.bytes() / P) > region_target) P <<= 1;
+  const size_t region_target = (size_t)(e->p.region_mb ? e->p.region_mb : 64) << 20;
+  const size_t owned_bytes = (size_t)t.local_size * (t.slot_bits / 8);           // (without the overflow margin)
+  while(P < (uint32_t)PMAX && (owned_bytes / P) > region_target) P <<= 1;
   for(;; P >>= 1) {
     if(P < 64 || t.local_lsize < 8 || (1u << (t.local_lsize - 8)) < P) return;
     const uint32_t region_bits = t.local_lsize - ceil_log2(P);
@@ -378,6 +383,21 @@ static bool watch_failed(jfgpu_engine* e, int slot) {
   cudaEventSynchronize(e->ev_watch[slot]);
   return e->h_watch[slot] != 0;
 }
+static cudaEvent_t win_event(jfgpu_engine* e, cudaStream_t st) {
+  if(e->wev_used == e->wev.size()) { cudaEvent_t ev; cudaEventCreate(&ev); e->wev.push_back(ev); }
+  cudaEvent_t ev = e->wev[e->wev_used++];
+  cudaEventRecord(ev, st);
+  return ev;
+}
+// fold the event quadruples of the finished drain into win_ms (the stream must be idle)
+static void resolve_win_events(jfgpu_engine* e) {
+  for(size_t i = 0; i + 3 < e->wev_used; i += 4)
+    for(int q = 0; q < 3; ++q) {
+      float ms = 0;
+      if(cudaEventElapsedTime(&ms, e->wev[i + q], e->wev[i + q + 1]) == cudaSuccess) e->win_ms[q] += ms; else cudaGetLastError();
+    }
+  e->wev_used = 0;
+}
 static bool window_enabled(jfgpu_engine* e, const PartDev& pd) {
   return e->p.k2_mode == 0 && e->op == 0 && e->tab.slot_bits == 32 && pd.rec_bytes == 4 && pd.region_bits > WIN_LG &&
          pd.region_bits - WIN_LG <= 11 && CHUNK_BYTES == WIN_NTH * 16;
@@ -405,7 +425,7 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
   for(uint32_t r = 0; r < pd.P; ++r) start[r] = std::min(start[r], n_units);
   uint32_t r0 = 0;
   while(r0 < pd.P && start[r0] < *done) ++r0;
-  const size_t scatter_smem = ((size_t)4 * ((size_t)1 << wpr_lg) + (size_t)WIN_TILE_UNITS * pd.chunk_recs) * 4;
+  const size_t scatter_smem = ((size_t)4 * ((size_t)1 << wpr_lg) + (size_t)WIN_ST_UNITS * pd.chunk_recs) * 4;
   cudaFuncSetAttribute(win_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
   // (the runs of a group start on 16-byte boundaries: up to 3 padding records per window)
   const uint64_t max_units = std::min<uint64_t>((ps.w_rec_cap - ((uint64_t)WIN_MAX_G << 13)) / pd.chunk_recs, careful ? group_units : 0xFFFFFFFFu);
@@ -413,12 +433,13 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
   while(r0 < pd.P && *done < n_units) {
     WinDev wd;
     memset(&wd, 0, sizeof(wd));
-    uint32_t G = 0, tiles = 0;
+    uint32_t G = 0, tiles = 0, stiles = 0;
     while(r0 + G < pd.P && G < WIN_MAX_G) {
       const uint32_t nu = start[r0 + G + 1] - start[r0 + G];
       if((uint64_t)(start[r0 + G + 1] - start[r0]) > max_units) break;
-      wd.tile_first[G] = tiles; wd.unit_first[G] = start[r0 + G];
+      wd.tile_first[G] = tiles; wd.stile_first[G] = stiles; wd.unit_first[G] = start[r0 + G];
       tiles += (nu + WIN_TILE_UNITS - 1) / WIN_TILE_UNITS;
+      stiles += (nu + WIN_ST_UNITS - 1) / WIN_ST_UNITS;
       ++G;
     }
     TableDev T = table_dev(e, e->tab);
@@ -431,7 +452,7 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
       JF_LAUNCHED();
       *done = upto; r0 += 1;
     } else {
-      wd.tile_first[G] = tiles; wd.unit_first[G] = start[r0 + G];
+      wd.tile_first[G] = tiles; wd.stile_first[G] = stiles; wd.unit_first[G] = start[r0 + G];
       wd.g0 = r0; wd.G = G; wd.wpr_lg = wpr_lg; wd.n_tiles = tiles;
       wd.wstart = ps.w_start.as<uint32_t>(); wd.wcursor = ps.w_cursor.as<uint32_t>(); wd.wcnt = ps.w_cnt.as<uint32_t>();
       wd.wrec = ps.w_rec.as<uint32_t>(); wd.wrec_cap = ps.w_rec_cap;
@@ -440,9 +461,12 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
       const uint32_t hb = e->tab.fbits - e->tab.rbits;
       if(tiles) {
         CUDA_OK(e, cudaMemsetAsync(ps.w_cursor.p, 0, ((size_t)G << wpr_lg) * 4, st));
+        win_event(e, st);
         win_hist_kernel<<<tiles, WIN_NTH, 0, st>>>(pd, wd, ps.order.as<uint32_t>(), hb); JF_LAUNCHED();
         win_scan_kernel<<<1, 1024, 0, st>>>(wd, T.stats); JF_LAUNCHED();
-        win_scatter_kernel<<<tiles, WIN_NTH, scatter_smem, st>>>(pd, wd, ps.order.as<uint32_t>(), hb); JF_LAUNCHED();
+        win_event(e, st);
+        win_scatter_kernel<<<stiles, WIN_ST_NTH, scatter_smem, st>>>(pd, wd, ps.order.as<uint32_t>(), hb); JF_LAUNCHED();
+        win_event(e, st);
         if(e->kw == 1) {
           cudaFuncSetAttribute(win_insert2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN2_SMEM);
           win_insert2_kernel<1><<<e->n_sm, WIN2_NTH, WIN2_SMEM, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
@@ -452,6 +476,7 @@ static int window_drain(jfgpu_engine* e, cudaStream_t st, const PartDev& pd, uns
           win_insert2_kernel<2><<<e->n_sm, WIN2_NTH, WIN2_SMEM, st>>>(T, pd, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
           win_deferred_kernel<2><<<e->n_sm * 2, 256, 0, st>>>(T, wd, e->tab.inv_lut.as<uint64_t>(), e->nbytes); JF_LAUNCHED();
         }
+        win_event(e, st);
         CUDA_OK(e, cudaMemsetAsync(ps.w_def_n.p, 0, 8, st));
       }
       *done = start[r0 + G]; r0 += G;
@@ -588,6 +613,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   cudaEventRecord(e->ev_d1, st);
   cudaStreamSynchronize(st);
   { float ms = 0; if(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1) == cudaSuccess) e->drain_ms += ms; else cudaGetLastError(); }
+  resolve_win_events(e);
   ps.pending = false;
   if(rebuilt) { cudaStreamSynchronize(st); old_inv.free(); part_configure(e); if(!e->part.P) part_release(e); }
   ps.bound_chunks = ps.P;
@@ -686,8 +712,9 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
       // the all-32-bit tail: 11-bit-table hash with at most two parity rows, 4-byte records, one shard, region index and
       // record fields inside 32 bits
       const bool fast = kw == 1 && e->tab.hash_fast && e->tab.n_prow <= 2 && ps.rec_bytes == 4 && e->shard_bits == 0 &&
-                        ps.region_bits >= 2 && ps.region_bits < 32 && e->tab.lsize <= 34 && e->tab.lsize >= ps.region_bits;
-      if(kw == 1 && fast) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, bloom_smem), true);
+                        ps.region_bits >= 2 && ps.region_bits < 32 && e->tab.lsize <= 34 && e->tab.lsize >= ps.region_bits &&
+                        ps.P <= RING_P && !a.bloom.mode;
+      if(kw == 1 && fast) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, 0, true), true);
       return launch(extract_kernel<kw, sb, 2, 1024, false>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, bloom_smem), true);
     }
     if(mode == 1) return launch(extract_kernel<kw, sb, 1, 512, false>, 512, count_smem_bytes<512>(a.lut_bytes, 0, bloom_smem), false);
@@ -1121,6 +1148,7 @@ void jfgpu_destroy(jfgpu_handle e) {
   if(e->ev_d0) cudaEventDestroy(e->ev_d0);
   if(e->ev_d1) cudaEventDestroy(e->ev_d1);
   for(cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
+  for(cudaEvent_t ev : e->wev) cudaEventDestroy(ev);
   if(e->cs) cudaStreamDestroy(e->cs);
   if(e->hs) cudaStreamDestroy(e->hs);
   delete e;
@@ -1337,7 +1365,7 @@ int jfgpu_clear(jfgpu_handle e) {
     e->part.bound_chunks = e->part.P;
     e->part.pending = false;
   }
-  e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0; e->drain_ms = 0;
+  e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0; e->drain_ms = 0; e->win_ms[0] = e->win_ms[1] = e->win_ms[2] = 0;
   e->eff_val_len = e->p.counter_len;
   return reset_carry(e, e->cs);
 }
@@ -1359,6 +1387,7 @@ int jfgpu_get_stats(jfgpu_handle e, jfgpu_stats* s) {
   s->seconds_count_kernel = e->kernel_ms * 1e-3;
   s->count_kernel_launches = e->kernel_launches;
   s->seconds_drain = e->drain_ms * 1e-3;
+  s->seconds_win_hist = e->win_ms[0] * 1e-3; s->seconds_win_scatter = e->win_ms[1] * 1e-3; s->seconds_win_insert = e->win_ms[2] * 1e-3;
   return JFGPU_OK;
 }
 

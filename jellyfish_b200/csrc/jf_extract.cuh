@@ -99,7 +99,13 @@ __device__ __noinline__ void spill_record(const TableDev T, uint64_t* spill_keys
 }
 
 // FAST = the common geometry of the region-by-region path, everything in 32-bit arithmetic: one key word, the
-// 11-bit-table hash with at most two parity rows (tables of up to 2^34 slots), 4-byte records, a single shard.
+// 11-bit-table hash with at most two parity rows (tables of up to 2^34 slots), 4-byte records, a single shard, at most
+// RING_P regions.  Its records do not go to the chunks one 4-byte store at a time (the GPU retires ~98 G scattered stores
+// per second whatever their width, scripts/micro/scatter_store.cu -- that alone would cap K1 at 98 G k-mers/s): every region
+// has a ring of RING records in shared memory, and after every SG k-mers per thread a pass over the regions writes the
+// complete groups of 8 records with two 16-byte stores (one 32-byte sector).
+constexpr uint32_t RING = 32;                     // records per region ring (power of two)
+constexpr uint32_t RING_P = 1024;                 // regions at most on the FAST path (shared memory: RING_P * RING * 4 bytes)
 template<int KW, int SB, int MODE, int NTH, bool FAST>
 __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(const CountArgs a, const PartDev pd) {
   constexpr int WINB = NTH * 32;
@@ -110,10 +116,14 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ExtractSmemT<NTH>& sm = *reinterpret_cast<ExtractSmemT<NTH>*>(smem_raw);
   uint64_t* lut = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(ExtractSmemT<NTH>) + 15) & ~(size_t)15));
+  // per region: records in the open chunk (FAST: low 16 bits = records handed out, high 16 bits = records already written to
+  // the chunk) and the open chunk's id; FAST: the rings behind them
   uint32_t* st_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes);
-  uint32_t* st_chunk = st_cnt + PMAX;
+  uint32_t* st_chunk = st_cnt + (FAST ? RING_P : PMAX);
+  uint32_t* ring = st_chunk + RING_P;            // (FAST only)
   // byte tables of the two Bloom hash matrices, behind everything else
-  uint64_t* bl1 = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes + (MODE == 2 ? PMAX * 8 : 0));
+  uint64_t* bl1 = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + a.lut_bytes +
+                                              (MODE == 2 ? (FAST ? (size_t)RING_P * 8 + (size_t)RING_P * RING * 4 : (size_t)PMAX * 8) : 0));
   uint64_t* bl2 = bl1 + a.nbytes * 256;
   const uint32_t* lut32 = reinterpret_cast<const uint32_t*>(lut);
   const uint64_t* rev64 = reinterpret_cast<const uint64_t*>(sm.rev);
@@ -133,9 +143,39 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
         c = alloc_chunk(pd, blockIdx.x); f = 0;
         if(c == NO_CHUNK) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); f = pd.chunk_recs; }
       }
-      st_chunk[p] = c; st_cnt[p] = f;
+      st_chunk[p] = c; st_cnt[p] = FAST ? (f | (f << 16)) : f;
     }
   }
+  // FAST: one pass over the regions -- write the complete groups of 8 records of every ring to its chunk, close chunks that are
+  // nearly full.  Between two barriers; `finish` also writes the incomplete group (end of the launch).
+  auto flush_rings = [&](const bool finish) {
+    for(uint32_t p = tid; p < pd.P; p += NTH) {
+      const uint32_t v = st_cnt[p];
+      uint32_t cnt = v & 0xFFFFu, fl = v >> 16;
+      const uint32_t lim = min(fl + RING, pd.chunk_recs);
+      if(cnt > lim) cnt = lim;                    // the slots beyond went to the spill list: hand them out again
+      const uint32_t c = st_chunk[p];
+      if(c == NO_CHUNK) continue;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(pd.pool + (size_t)c * CHUNK_BYTES);
+      const uint32_t* rg = ring + p * RING;
+      while((fl & 7u) && fl < cnt) { dst[fl] = rg[fl & (RING - 1)]; ++fl; }          // (only after a launch that ended inside a group)
+      while(cnt - fl >= 8u) {
+        const uint4 x0 = *reinterpret_cast<const uint4*>(rg + (fl & (RING - 1))), x1 = *reinterpret_cast<const uint4*>(rg + (fl & (RING - 1)) + 4);
+        *reinterpret_cast<uint4*>(dst + fl) = x0; *reinterpret_cast<uint4*>(dst + fl + 4) = x1;
+        fl += 8;
+      }
+      const bool close = cnt + RING > pd.chunk_recs;
+      if(close || finish) for(; fl < cnt; ++fl) dst[fl] = rg[fl & (RING - 1)];
+      if(close) {
+        pd.dir[c] = make_uint2(p, cnt);
+        const uint32_t nc = alloc_chunk(pd, blockIdx.x);
+        st_chunk[p] = nc;
+        if(nc == NO_CHUNK) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); cnt = fl = pd.chunk_recs; }
+        else cnt = fl = 0;
+      }
+      st_cnt[p] = cnt | (fl << 16);
+    }
+  };
   for(uint32_t i = tid; i < 2 * (NTH + 4); i += NTH) sm.rev[i] = 0;
   for(uint32_t i = tid; i < NTH + 4; i += NTH) sm.brk[i] = 0;
   if(tid == 0) mbar_init(&sm.bar, 1);
@@ -417,7 +457,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
 
     // ---- phase E: thread c owns stream word PW + c: the k-mers ending at its 32 symbols ----
     const uint32_t n_words = (nsym + 31) / 32;
-    for(uint32_t c = tid; c < n_words; c += NTH) {
+    // (FAST: every thread makes exactly one trip, with an empty mask if it owns no word -- the ring passes below are block-wide)
+    for(uint32_t c = tid; c < (FAST ? (uint32_t)NTH : n_words); c += NTH) {
       const uint32_t W = PW + c;
       // which of the 32 end positions carry a k-mer: inside [idx0, nsym), no reset among the last k symbols
       const int lo_i = (int)idx0 - (int)(32 * c), hi_i = (int)nsym - (int)(32 * c);
@@ -445,7 +486,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
           vmask &= ~(uint32_t)(x >> 32);
         }
       }
-      if(!vmask) continue;
+      if(c >= n_words) vmask = 0;
+      if(!FAST && !vmask) continue;
       ls.kmers += __popc(vmask);
       // forward strand: pair-reversed words (first base most significant), reverse strand: the words as they are
       const uint64_t R0 = rev64[W], R1 = rev64[W - 1], R2 = KW == 2 ? rev64[W - 2] : 0ull;
@@ -453,7 +495,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
 #pragma unroll 1
       for(int o = 0; o < 4; ++o) {
         const uint32_t vm8 = (vmask >> (8 * o)) & 0xFFu;
-        if(!vm8) continue;
+        if(!FAST && !vm8) continue;
         // X = forward words shifted so that end symbol 8o+7 sits at bits 0..1; Y = reverse words shifted so that the
         // first symbol of the k-mer ending at symbol 8o sits at bits 0..1
         const uint32_t fs = 48 - 16 * o;                   // 62 - 2(8o+7)
@@ -496,46 +538,48 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
 #pragma unroll
           for(int q = 0; q < KW; ++q) key[q] = use_rc ? rc[q] : m[q];
         };
-        if(FAST && !a.bloom.mode) {
-          // Three passes over the 8 k-mers of the group so that the shared-memory round trips overlap: (1) keys, hashes and
-          // records -- 32 independent table loads in flight; (2) the slot reservations; (3) the record stores.
-          #pragma unroll
-          for(int hf = 0; hf < 8; hf += SG) {
-          uint32_t P[SG], R[SG];
-#pragma unroll
-          for(int jj = 0; jj < SG; ++jj) {
-            const int j = hf + jj;
-            // (computed for the masked-out positions as well: no branch per k-mer; kbits <= 44 keeps every table index in range)
-            uint64_t key[KW];
-            kmer_at(j, key);
-            const uint32_t klo = (uint32_t)key[0], khi = (uint32_t)(key[0] >> 32);
-            const uint32_t h32 = lut32[klo & 2047u] ^ lut32[2048 + ((klo >> 11) & 2047u)] ^
-                                 lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + ((khi >> 1) & 2047u)];
-            const uint32_t ext = (__popc((klo & f_p0lo) ^ (khi & f_p0hi)) & 1u) | ((__popc((klo & f_p1lo) ^ (khi & f_p1hi)) & 1u) << 1);
-            P[jj] = ((vm8 >> j) & 1u) ? ((h32 >> f_rgb) | (ext << (32 - f_rgb))) : 0xFFFFFFFFu;     // region
-            R[jj] = ((h32 & f_relmask) << f_hb) | (uint32_t)(key[0] >> f_lsz);                      // (position in the region, explicit key bits)
-          }
-          uint32_t S[SG], C[SG];
-#pragma unroll
-          for(int jj = 0; jj < SG; ++jj) {
-            S[jj] = 0; C[jj] = 0;
-            if(P[jj] != 0xFFFFFFFFu) { S[jj] = atomicAdd(&st_cnt[P[jj]], 1u); C[jj] = st_chunk[P[jj]]; }
-          }
-#pragma unroll
-          for(int jj = 0; jj < SG; ++jj) {
-            const int j = hf + jj;
-            if(P[jj] == 0xFFFFFFFFu) continue;
-            if(S[jj] < pd.chunk_recs) reinterpret_cast<uint32_t*>(pd.pool + (size_t)C[jj] * CHUNK_BYTES)[S[jj]] = R[jj];
-            else {             // this region's chunk filled up within one window (skewed input): direct insertion later
+        if constexpr(FAST) {
+          // a record into its region's ring (slot numbers are handed out by one shared-memory atomic on the packed counter);
+          // a ring or a chunk that is full sends the k-mer to the spill list, the ring pass hands the slot out again
+          auto ring_append = [&](const uint32_t p, const uint32_t rec, const int j) {
+            const uint32_t v = atomicAdd(&st_cnt[p], 1u);
+            const uint32_t slot = v & 0xFFFFu, fl = v >> 16;
+            if(slot - fl < RING && slot < pd.chunk_recs) ring[p * RING + (slot & (RING - 1))] = rec;
+            else {
               uint64_t key[KW];
               kmer_at(j, key);
-              const uint64_t pos = ((uint64_t)P[jj] << f_rgb) | (R[jj] >> f_hb);
+              const uint64_t pos = ((uint64_t)p << f_rgb) | (rec >> f_hb);
               spill_record<KW, SB>(a.T, pd.spill_keys, pd.spill_counts, pd.spill_n, pd.spill_cap, key[0], key[KW - 1], pos);
             }
+          };
+#pragma unroll
+          for(int hf = 0; hf < 8; hf += SG) {
+            const uint32_t vm4 = (vm8 >> hf) & ((1u << SG) - 1u);
+            if(vm4) {          // (the host launches the FAST form only without a Bloom filter in front of the table)
+              // two passes over the SG k-mers so that the shared-memory round trips overlap: keys, hashes and records (4 SG
+              // independent table loads in flight), then the slot reservations and the ring stores
+              uint32_t P[SG], R[SG];
+#pragma unroll
+              for(int jj = 0; jj < SG; ++jj) {
+                const int j = hf + jj;
+                // (computed for the masked-out positions as well: no branch per k-mer; kbits <= 44 keeps every table index in range)
+                uint64_t key[KW];
+                kmer_at(j, key);
+                const uint32_t klo = (uint32_t)key[0], khi = (uint32_t)(key[0] >> 32);
+                const uint32_t h32 = lut32[klo & 2047u] ^ lut32[2048 + ((klo >> 11) & 2047u)] ^
+                                     lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + ((khi >> 1) & 2047u)];
+                const uint32_t ext = (__popc((klo & f_p0lo) ^ (khi & f_p0hi)) & 1u) | ((__popc((klo & f_p1lo) ^ (khi & f_p1hi)) & 1u) << 1);
+                P[jj] = (h32 >> f_rgb) | (ext << (32 - f_rgb));                       // region
+                R[jj] = ((h32 & f_relmask) << f_hb) | (uint32_t)(key[0] >> f_lsz);    // (position in the region, explicit key bits)
+              }
+#pragma unroll
+              for(int jj = 0; jj < SG; ++jj) if((vm4 >> jj) & 1u) ring_append(P[jj], R[jj], hf + jj);
+            }
+            __syncthreads();
+            flush_rings(false);
+            __syncthreads();
           }
-          }
-          continue;
-        }
+        } else {
 #pragma unroll
         for(int j = 0; j < 8; ++j) {
           if(!((vm8 >> j) & 1u)) continue;
@@ -545,20 +589,6 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
             const uint64_t h1 = gf2_hash<KW>(bl1, key, (int)a.nbytes), h2 = gf2_hash<KW>(bl2, key, (int)a.nbytes);
             if(a.bloom.mode == BLOOM_COUNT) { bloom_count(a.bloom, h1, h2); ls.inserted++; continue; }   // `jellyfish bc`: no table
             if(a.bloom.mode == BLOOM_FILTER ? !bloom_test_and_set(a.bloom, h1, h2) : !bloom_check(a.bloom, h1, h2)) continue;
-          }
-          if(FAST) {
-            // hash position: low 32 bits from four 11-bit tables, bits 32 and 33 from two parity rows (zero rows when unused)
-            const uint32_t klo = (uint32_t)key[0], khi = (uint32_t)(key[0] >> 32);
-            const uint32_t h32 = lut32[klo & 2047u] ^ lut32[2048 + ((klo >> 11) & 2047u)] ^
-                                 lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + (khi >> 1)];
-            const uint32_t ext = (__popc((klo & f_p0lo) ^ (khi & f_p0hi)) & 1u) | ((__popc((klo & f_p1lo) ^ (khi & f_p1hi)) & 1u) << 1);
-            const uint32_t p = (h32 >> f_rgb) | (ext << (32 - f_rgb));       // region
-            const uint32_t high = (uint32_t)(key[0] >> f_lsz);               // explicit key bits (f_hb of them)
-            const uint32_t rec = ((h32 & f_relmask) << f_hb) | high;
-            const uint32_t slot = atomicAdd(&st_cnt[p], 1u);
-            if(slot < pd.chunk_recs) reinterpret_cast<uint32_t*>(pd.pool + (size_t)st_chunk[p] * CHUNK_BYTES)[slot] = rec;
-            else spill_record<KW, SB>(a.T, pd.spill_keys, pd.spill_counts, pd.spill_n, pd.spill_cap, key[0], key[KW - 1], (uint64_t)h32 | ((uint64_t)ext << 32));
-            continue;
           }
           uint64_t pos;
           if(KW == 1 && a.hash_fast) {
@@ -602,13 +632,14 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
             } else spill_record<KW, SB>(a.T, pd.spill_keys, pd.spill_counts, pd.spill_n, pd.spill_cap, key[0], key[KW - 1], pos);    // this region's chunk filled up within one window (skewed input)
           }
         }
+        }
       }
     }
     __syncthreads();     // all reads of the streams done
     // clear the stream words this window used (the next window ORs into them) and roll full chunks over
     for(uint32_t i = tid; i < 2 * (n_words + PW) + 3; i += NTH) sm.rev[i] = 0;
     for(uint32_t i = tid; i < n_words + PW + 2; i += NTH) sm.brk[i] = 0;
-    if(MODE == 2) {
+    if(MODE == 2 && !FAST) {
       for(uint32_t p = tid; p < pd.P; p += NTH) {
         const uint32_t c = st_cnt[p];
         if(c + pd.margin > pd.chunk_recs) {
@@ -623,7 +654,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
     __syncthreads();
   }
   if(MODE == 2) {          // keep the open chunks for the next launch
-    for(uint32_t p = tid; p < pd.P; p += NTH) { my_chunk[p] = st_chunk[p]; my_fill[p] = min(st_cnt[p], pd.chunk_recs); }
+    if(FAST) { flush_rings(true); __syncthreads(); }
+    for(uint32_t p = tid; p < pd.P; p += NTH) { my_chunk[p] = st_chunk[p]; my_fill[p] = min(FAST ? (st_cnt[p] & 0xFFFFu) : st_cnt[p], pd.chunk_recs); }
   }
 
   // ---- statistics: one atomic per counter per CTA ----

@@ -62,3 +62,20 @@ def generate(prefix, seed, *lengths, extra=()):
 def subst(args, files):
     """'@name' in a case's switches stands for the path of that generated input (e.g. --if @multi2.fa)."""
     return [files[a[1:]] if a.startswith("@") else a for a in args]
+
+
+def hash_pos(header, key):
+    """Original position of a key: RectangularBinaryMatrix::times (bit i of the key selects columns[c-1-i],
+    rectangular_binary_matrix.hpp:223-261) modulo the table size."""
+    m = header["matrix1"]
+    size = header["size"]
+    if m.get("identity"):
+        return key & (size - 1)
+    cols, c = m["columns"], m["c"]
+    h, i = 0, 0
+    while key:
+        if key & 1:
+            h ^= cols[c - 1 - i]
+        key >>= 1
+        i += 1
+    return h & (size - 1)
