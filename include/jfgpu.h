@@ -164,6 +164,30 @@ int  jfgpu_extract_route(jfgpu_handle h, const void* dev_bytes, size_t n, uint32
  * stream-ordered (returns without synchronising). */
 int  jfgpu_insert_keys(jfgpu_handle h, const void* dev_keys, uint64_t n, void* stream);
 
+/* Sharded counting, record exchange (the default for the geometries it covers -- k <= 21 with 32-bit slots; otherwise the
+ * key exchange above).  K1 writes 4-byte records for the regions of the GLOBAL table into a SEND pool whose chunk arenas
+ * belong to the owning shards: `jfgpu_shard_extract`.  `jfgpu_shard_pack` closes the open chunks and returns, per destination
+ * d, the number of 8 KB chunks that sit at send_pool + (bank*n_shards + d)*send_arena_chunks*8192 (directory entries, 8 bytes
+ * per chunk, at send_dir + the same index): the caller moves them (NCCL all-to-all) into the RECEIVE pool, source s at
+ * recv_pool + s*recv_seg_chunks*8192 / recv_dir + s*recv_seg_chunks*8, and hands the counts to `jfgpu_shard_unpack`, which
+ * turns them into records of this shard's own regions (restage_kernel); jfgpu_finish drains them into the table.
+ * The pools are caller-owned device buffers (two send banks, so that the extraction of one round overlaps the exchange of
+ * the previous one).  All calls are stream-ordered except jfgpu_shard_pack, which synchronises `stream`. */
+typedef struct {
+  void*    send_pool;          /* 2 * n_shards * send_arena_chunks * 8192 bytes */
+  void*    send_dir;           /* 2 * n_shards * send_arena_chunks * 8 bytes    */
+  uint64_t send_arena_chunks;
+  void*    recv_pool;          /* n_shards * recv_seg_chunks * 8192 bytes        */
+  void*    recv_dir;           /* n_shards * recv_seg_chunks * 8 bytes           */
+  uint64_t recv_seg_chunks;    /* >= send_arena_chunks                           */
+} jfgpu_shard_buffers;
+int  jfgpu_shard_setup(jfgpu_handle h, const jfgpu_shard_buffers* buffers);   /* JFGPU_ERR_ARG: geometry not covered; with all
+                                                                                pointers NULL the call only answers that question */
+uint64_t jfgpu_shard_round_bytes(jfgpu_handle h);   /* text bytes one round (one bank) takes at most */
+int  jfgpu_shard_extract(jfgpu_handle h, const void* dev_bytes, size_t n, uint32_t flags, uint32_t bank, void* stream);
+int  jfgpu_shard_pack(jfgpu_handle h, uint32_t bank, uint64_t* chunks_per_dest /* [n_shards], host */, void* stream);
+int  jfgpu_shard_unpack(jfgpu_handle h, const uint64_t* chunks_per_src /* [n_shards], host */, void* stream);
+
 /* -- mer_counter_base's operation (sub_commands/count_main.cc:133,152-184): JFGPU_OP_COUNT adds
  *    (hash_counter::add), JFGPU_OP_PRIME inserts keys with count 0 (hash_counter::set, the first pass
  *    of `count --if`), JFGPU_OP_UPDATE adds only to keys already present (update_add, the second pass).

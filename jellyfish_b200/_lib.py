@@ -18,6 +18,7 @@ SYMBOLS = [
     "jfgpu_reference_matrix", "jfgpu_synth_fasta_bytes", "jfgpu_synth_fasta_device",
     "jfgpu_host_alloc", "jfgpu_host_free", "jfgpu_memcpy_h2d", "jfgpu_kernel_launches", "jfgpu_version",
     "jfgpu_bloom_info_get", "jfgpu_bloom_load", "jfgpu_bloom_dump",
+    "jfgpu_shard_setup", "jfgpu_shard_round_bytes", "jfgpu_shard_extract", "jfgpu_shard_pack", "jfgpu_shard_unpack",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_FULL, ERR_FORMAT, ERR_STATE, ERR_NOMEM, ERR_SINK = range(8)
@@ -52,6 +53,13 @@ class Stats(C.Structure):
         ("overflowed", C.c_uint64), ("regrows", C.c_uint64), ("bytes", C.c_uint64), ("seconds_count", C.c_double),
         ("seconds_count_kernel", C.c_double), ("count_kernel_launches", C.c_uint64), ("seconds_drain", C.c_double),
         ("seconds_win_hist", C.c_double), ("seconds_win_scatter", C.c_double), ("seconds_win_insert", C.c_double),
+    ]
+
+
+class ShardBuffers(C.Structure):
+    _fields_ = [
+        ("send_pool", C.c_void_p), ("send_dir", C.c_void_p), ("send_arena_chunks", C.c_uint64),
+        ("recv_pool", C.c_void_p), ("recv_dir", C.c_void_p), ("recv_seg_chunks", C.c_uint64),
     ]
 
 
@@ -129,5 +137,15 @@ def load():
     lib.jfgpu_bloom_load.restype = C.c_int
     lib.jfgpu_bloom_dump.argtypes = [H, SINK_FN, C.c_void_p]
     lib.jfgpu_bloom_dump.restype = C.c_int
+    lib.jfgpu_shard_setup.argtypes = [H, C.POINTER(ShardBuffers)]
+    lib.jfgpu_shard_setup.restype = C.c_int
+    lib.jfgpu_shard_round_bytes.argtypes = [H]
+    lib.jfgpu_shard_round_bytes.restype = C.c_uint64
+    lib.jfgpu_shard_extract.argtypes = [H, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.jfgpu_shard_extract.restype = C.c_int
+    lib.jfgpu_shard_pack.argtypes = [H, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p]
+    lib.jfgpu_shard_pack.restype = C.c_int
+    lib.jfgpu_shard_unpack.argtypes = [H, C.POINTER(C.c_uint64), C.c_void_p]
+    lib.jfgpu_shard_unpack.restype = C.c_int
     _lib = lib
     return lib

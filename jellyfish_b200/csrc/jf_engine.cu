@@ -16,6 +16,7 @@
 #include "jf_extract.cuh"
 #include "jf_window.cuh"
 #include "jf_dump.cuh"
+#include "jf_shard.cuh"
 
 using namespace jfk;
 
@@ -25,6 +26,8 @@ static thread_local std::string g_create_error;
 #define JF_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 namespace {
+
+constexpr unsigned SHARD_RESERVED_SMS = 16;   // SMs K1 leaves to NCCL while an exchange runs beside it
 
 unsigned ceil_log2(uint64_t x) { unsigned l = 0; while(l < 64 && ((uint64_t)1 << l) < x) ++l; return l; }
 unsigned bitsize(uint64_t x) { unsigned b = 0; while(x) { ++b; x >>= 1; } return b ? b : 1; }
@@ -83,6 +86,17 @@ struct PartState {
   bool pending = false;          // records sit in the pool
 };
 
+// Sharded counting, record exchange (jf_shard.cuh): the send pool (global regions, one chunk arena per owning shard, two
+// banks) and the receive pool live in buffers the caller registers (they are the NCCL send / receive buffers).
+struct ShardState {
+  bool on = false;
+  uint32_t P = 0, sbits = 0, own_regions = 0, split_lg = 0, owner_shift = 0;
+  uint64_t arena_chunks = 0, seg_chunks = 0;
+  uint8_t* send_pool = nullptr; uint2* send_dir = nullptr; uint8_t* recv_pool = nullptr; uint2* recv_dir = nullptr;
+  DevBuf pool_next[2], cta_chunk, cta_fill;
+  unsigned int* h_counts = nullptr;       // pinned
+};
+
 struct BloomState {
   uint32_t mode = BLOOM_NONE, k = 0;
   uint64_t m = 0, inv = 0, n_words = 0;
@@ -96,6 +110,7 @@ struct BloomState {
 struct jfgpu_engine {
   jfgpu_params p;
   PartState part;
+  ShardState sh;
   BloomState bloom;
   int device = 0;
   unsigned k = 0, kw = 1, nbytes = 0, shard_bits = 0;
@@ -285,6 +300,12 @@ int ensure_scratch(jfgpu_engine* e, uint64_t n_tiles) {
 }
 
 // ---- partitioned insertion: geometry, pool, drain --------------------------------------
+// the ring memory of the staging kernels (RING_P * RING records) shared out among P regions
+uint32_t ring_len_for(uint32_t P) {
+  uint32_t p2 = 1; while(p2 < P) p2 <<= 1;
+  const uint32_t len = p2 >= RING_P ? RING : RING * (RING_P / p2);
+  return std::min<uint32_t>(len, 1024);
+}
 PartDev part_dev(const jfgpu_engine* e) {
   PartDev d;
   memset(&d, 0, sizeof(d));
@@ -293,10 +314,30 @@ PartDev part_dev(const jfgpu_engine* e) {
   d.chunk_recs = CHUNK_BYTES / std::max(1u, ps.rec_bytes); d.n_chunks = ps.n_chunks; d.stage_bytes = ps.stage_bytes;
   d.margin = ps.margin;
   d.arena_chunks = ps.arena_chunks;
+  d.ring_len = ring_len_for(ps.P ? ps.P : 1);
   d.pool = ps.pool.as<uint8_t>(); d.pool_next = ps.pool_next.as<unsigned int>(); d.n_units = d.pool_next + ps.n_arenas; d.dir = ps.dir.as<uint2>();
   d.cta_chunk = ps.cta_chunk.as<uint32_t>(); d.cta_fill = ps.cta_fill.as<uint32_t>();
   d.spill_keys = ps.spill_keys.as<uint64_t>(); d.spill_counts = ps.spill_counts.as<uint64_t>();
   d.spill_n = ps.spill_n.as<unsigned long long>(); d.spill_cap = ps.spill_cap;
+  return d;
+}
+
+// The send pool of sharded counting as K1 sees it: regions of the GLOBAL table, arenas by owning shard.
+PartDev shard_send_dev(const jfgpu_engine* e, int bank) {
+  PartDev d;
+  memset(&d, 0, sizeof(d));
+  const ShardState& sh = e->sh;
+  const uint32_t G = e->p.n_shards;
+  d.P = sh.P; d.region_bits = sh.sbits; d.rec_bytes = 4; d.chunk_recs = CHUNK_BYTES / 4;
+  d.n_chunks = (uint32_t)(sh.arena_chunks * G); d.arena_chunks = (uint32_t)sh.arena_chunks;
+  d.by_owner = 1; d.owner_shift = sh.owner_shift;
+  d.ring_len = ring_len_for(sh.P);
+  // a chunk is closed once it might not take the records of one more ring pass (4 k-mers per thread of K1)
+  { const double mean = 4096.0 / sh.P; d.margin = std::max<uint32_t>(2 * RING, (uint32_t)(mean + 6.0 * sqrt(mean) + 8.0)); }
+  d.pool = sh.send_pool + (size_t)bank * G * sh.arena_chunks * CHUNK_BYTES;
+  d.dir = sh.send_dir + (size_t)bank * G * sh.arena_chunks;
+  d.pool_next = sh.pool_next[bank].as<unsigned int>(); d.n_units = d.pool_next + G;
+  d.cta_chunk = sh.cta_chunk.as<uint32_t>(); d.cta_fill = sh.cta_fill.as<uint32_t>();
   return d;
 }
 
@@ -661,7 +702,8 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     ps.bound_chunks += need;
     ps.pending = true;
   }
-  const uint32_t tile = (part ? 1024 : 512) * 32 - HALO;
+  const bool shard_send = mode == 3;            // K1 writes region records of the GLOBAL table into the send pool (bank = route_cap)
+  const uint32_t tile = (part || shard_send ? 1024 : 512) * 32 - HALO;
   const uint64_t n_tiles = (n + tile - 1) / tile;
   rc = ensure_scratch(e, n_tiles);
   if(rc) return rc;
@@ -684,13 +726,13 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   a.hash_fast = e->tab.hash_fast ? 1 : 0; a.n_prow = e->tab.n_prow;
   a.lut_bytes = e->tab.hash_fast ? 4 * 2048 * 4 : e->nbytes * 256 * 8;
   for(unsigned i = 0; i < 8; ++i) a.prow[i] = e->tab.prow[i];
-  a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)mode; a.format = (uint32_t)e->format;
+  a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)(shard_send ? 2 : mode); a.format = (uint32_t)e->format;
   a.T = table_dev(e, e->tab);
   a.bloom = bloom_dev(e);
   const size_t bloom_smem = a.bloom.mode ? (size_t)e->nbytes * 256 * 8 * 2 : 0;
   if(bc_build) { a.lut = nullptr; a.lut_bytes = 0; a.hash_fast = 0; }
   a.route_keys = route_keys; a.route_counts = route_counts; a.route_cap = route_cap; a.shard_bits = e->shard_bits;
-  PartDev pd = part_dev(e);
+  PartDev pd = shard_send ? shard_send_dev(e, (int)route_cap) : part_dev(e);
   auto launch = [&](auto kern, int nth, size_t smem, bool one_per_sm) -> int {
     cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if(c != cudaSuccess) return fail(e, JFGPU_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(c));
@@ -698,7 +740,9 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     // persistent CTAs: exactly as many as are resident at once (a multiple of the SM count)
     int per_sm = 1;
     if(!one_per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nth, smem) != cudaSuccess || per_sm < 1)) { cudaGetLastError(); per_sm = 1; }
-    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * per_sm);
+    // (sharded counting leaves a few SMs to the collective that runs beside K1)
+    const int sms = shard_send && e->n_sm > 32 ? e->n_sm - (int)SHARD_RESERVED_SMS : e->n_sm;
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)sms * per_sm);
     if(e->kev_used + 2 > e->kev.size()) { cudaEvent_t a0, a1; cudaEventCreate(&a0); cudaEventCreate(&a1); e->kev.push_back(a0); e->kev.push_back(a1); }
     cudaEventRecord(e->kev[e->kev_used], stream);
     kern<<<grid, nth, smem, stream>>>(a, pd);
@@ -708,11 +752,15 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   };
   rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
     constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
+    if(shard_send) {
+      if(kw == 1) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, 0, 0, true), true);
+      return fail(e, JFGPU_ERR_STATE, "internal: record exchange with a two-word key");
+    }
     if(part) {
       // the all-32-bit tail: 11-bit-table hash with at most two parity rows, 4-byte records, one shard, region index and
       // record fields inside 32 bits
-      const bool fast = kw == 1 && e->tab.hash_fast && e->tab.n_prow <= 2 && ps.rec_bytes == 4 && e->shard_bits == 0 &&
-                        ps.region_bits >= 2 && ps.region_bits < 32 && e->tab.lsize <= 34 && e->tab.lsize >= ps.region_bits &&
+      const bool fast = kw == 1 && e->tab.hash_fast && e->tab.n_prow <= 6 && ps.rec_bytes == 4 && e->shard_bits == 0 &&
+                        ps.region_bits >= 2 && ps.region_bits < 32 && e->tab.lsize <= 38 && e->tab.lsize >= ps.region_bits &&
                         ps.P <= RING_P && !a.bloom.mode;
       if(kw == 1 && fast) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, 0, true), true);
       return launch(extract_kernel<kw, sb, 2, 1024, false>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, bloom_smem), true);
@@ -1133,6 +1181,8 @@ void jfgpu_destroy(jfgpu_handle e) {
   e->tab.release();
   part_release(e);
   e->bloom.release();
+  e->sh.pool_next[0].free(); e->sh.pool_next[1].free(); e->sh.cta_chunk.free(); e->sh.cta_fill.free();
+  if(e->sh.h_counts) cudaFreeHost(e->sh.h_counts);
   e->stats.free();
   for(int i = 0; i < 2; ++i) {
     e->carry[i].free(); e->fail_keys[i].free(); e->fail_counts[i].free(); e->stage[i].free();
@@ -1288,6 +1338,134 @@ int jfgpu_extract_route(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_
   return JFGPU_OK;
 }
 
+int jfgpu_shard_setup(jfgpu_handle e, const jfgpu_shard_buffers* b) {
+  if(!e || !b) return JFGPU_ERR_ARG;
+  cudaSetDevice(e->device);
+  const uint32_t G = e->p.n_shards;
+  ShardState& sh = e->sh;
+  sh.on = false;
+  // geometry the record exchange covers: one key word, the 32-bit hash tail, 4-byte records of the GLOBAL regions, the
+  // receiver's own partition in 4-byte records drained by the window kernels
+  const Table& t = e->tab;
+  if(G < 2 || G > 8 || !t.slots.p || e->kw != 1 || !t.hash_fast || t.n_prow > 6 || t.lsize > 38 || t.slot_bits != 32 || e->bloom.mode != BLOOM_NONE ||
+     !e->part.P || e->part.rec_bytes != 4 || e->part.P > RING_P)
+    return fail(e, JFGPU_ERR_ARG, "this table geometry is not covered by the record exchange (use the key exchange)");
+  uint32_t P = RING_P;
+  while(P > G && t.lsize < ceil_log2(P) + 14) P >>= 1;
+  const uint32_t sbits = t.lsize - ceil_log2(P);
+  if(sbits + t.hb > 32 || P < G || sbits < e->part.region_bits || (P / G) > e->part.P)
+    return fail(e, JFGPU_ERR_ARG, "this table geometry is not covered by the record exchange (use the key exchange)");
+  if(!b->send_pool && !b->recv_pool) return JFGPU_OK;          // geometry probe only
+  if(!b->send_pool || !b->send_dir || !b->recv_pool || !b->recv_dir || b->send_arena_chunks < 2 * (uint64_t)e->n_sm * (P / G) || b->recv_seg_chunks < b->send_arena_chunks)
+    return fail(e, JFGPU_ERR_ARG, "exchange buffers too small: an arena must hold the open chunks of every CTA twice over");
+  sh.P = P; sh.sbits = sbits; sh.own_regions = P / G; sh.owner_shift = ceil_log2(P / G); sh.split_lg = sbits - e->part.region_bits;
+  sh.arena_chunks = b->send_arena_chunks; sh.seg_chunks = b->recv_seg_chunks;
+  sh.send_pool = (uint8_t*)b->send_pool; sh.send_dir = (uint2*)b->send_dir; sh.recv_pool = (uint8_t*)b->recv_pool; sh.recv_dir = (uint2*)b->recv_dir;
+  bool ok = sh.pool_next[0].alloc(((size_t)G + 2) * 4) == cudaSuccess && sh.pool_next[1].alloc(((size_t)G + 2) * 4) == cudaSuccess &&
+            sh.cta_chunk.alloc((size_t)e->n_sm * RING_P * 4) == cudaSuccess && sh.cta_fill.alloc((size_t)e->n_sm * RING_P * 4) == cudaSuccess &&
+            (sh.h_counts || cudaHostAlloc((void**)&sh.h_counts, 16 * sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess);
+  if(!ok) { cudaGetLastError(); return fail(e, JFGPU_ERR_NOMEM, "device allocation failed"); }
+  for(int i = 0; i < 2; ++i) CUDA_OK(e, cudaMemsetAsync(sh.pool_next[i].p, 0, sh.pool_next[i].bytes, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(sh.cta_chunk.p, 0xFF, sh.cta_chunk.bytes, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(sh.cta_fill.p, 0, sh.cta_fill.bytes, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  sh.on = true;
+  return JFGPU_OK;
+}
+
+uint64_t jfgpu_shard_round_bytes(jfgpu_handle e) {
+  if(!e || !e->sh.on) return 0;
+  // every byte gives at most one record; iid keys spread evenly over the shards, a third of an arena is kept as slack, and
+  // every CTA parks one open chunk per region in the arena of its owner
+  const ShardState& sh = e->sh;
+  const uint64_t open = (uint64_t)e->n_sm * sh.own_regions;
+  const uint64_t room = sh.arena_chunks > open ? sh.arena_chunks - open : 0;
+  const uint64_t recs = room * (CHUNK_BYTES / 4 - 2 * RING) * 3 / 4;
+  const uint64_t bytes = recs * e->p.n_shards;
+  return bytes & ~(uint64_t)0xFFFFF;
+}
+
+int jfgpu_shard_extract(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t flags, uint32_t bank, void* stream) {
+  if(!e) return JFGPU_ERR_ARG;
+  if(!e->sh.on || bank > 1) return fail(e, JFGPU_ERR_STATE, "jfgpu_shard_setup has not been called");
+  if(((uintptr_t)dev_bytes & 15) != 0) return fail(e, JFGPU_ERR_ARG, "device text must be 16-byte aligned");
+  cudaSetDevice(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  int first = -1;
+  if((flags & JFGPU_FILE_BEGIN) && n) {
+    unsigned char b = 0;
+    CUDA_OK(e, cudaMemcpyAsync(&b, dev_bytes, 1, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(e, cudaStreamSynchronize(st));
+    first = b;
+  }
+  int rc = begin_feed(e, flags, first, st);
+  if(rc) return rc;
+  const uint8_t* p = (const uint8_t*)dev_bytes;
+  for(size_t off = 0; off < n; ) {
+    const size_t len = std::min<size_t>((size_t)512 << 20, n - off);
+    rc = run_batch(e, p + off, len, n - off, st, 3, nullptr, nullptr, bank);
+    if(rc) return rc;
+    off += len;
+  }
+  e->bytes_fed += n;
+  if(flags & JFGPU_FILE_END) { CUDA_OK(e, cudaStreamSynchronize(st)); return end_feed(e, flags, st); }
+  return JFGPU_OK;                       // stream-ordered
+}
+
+int jfgpu_shard_pack(jfgpu_handle e, uint32_t bank, uint64_t* counts, void* stream) {
+  if(!e || !counts) return JFGPU_ERR_ARG;
+  if(!e->sh.on || bank > 1) return fail(e, JFGPU_ERR_STATE, "jfgpu_shard_setup has not been called");
+  cudaSetDevice(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  const uint32_t G = e->p.n_shards;
+  PartDev pd = shard_send_dev(e, (int)bank);
+  close_chunks_kernel<<<e->n_sm * 4, 256, 0, st>>>(pd, (uint32_t)e->n_sm); JF_LAUNCHED();
+  CUDA_OK(e, cudaMemcpyAsync(e->sh.h_counts, pd.pool_next, G * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(e, cudaStreamSynchronize(st));
+  for(uint32_t d = 0; d < G; ++d) {
+    if(e->sh.h_counts[d] > e->sh.arena_chunks) return fail(e, JFGPU_ERR_FULL, "route bucket capacity exceeded (an arena of the send pool overflowed)");
+    counts[d] = e->sh.h_counts[d];
+  }
+  CUDA_OK(e, cudaMemsetAsync(pd.pool_next, 0, ((size_t)G + 2) * 4, st));    // (the chunks stay where they are until the caller has sent them)
+  return JFGPU_OK;
+}
+
+int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
+  if(!e || !counts) return JFGPU_ERR_ARG;
+  if(!e->sh.on) return fail(e, JFGPU_ERR_STATE, "jfgpu_shard_setup has not been called");
+  cudaSetDevice(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->cs;
+  const uint32_t G = e->p.n_shards;
+  PartState& ps = e->part;
+  int rc = part_alloc(e);
+  if(rc) return rc;
+  uint64_t total = 0;
+  for(uint32_t s = 0; s < G; ++s) { if(counts[s] > e->sh.seg_chunks) return fail(e, JFGPU_ERR_ARG, "more chunks than a receive segment holds"); total += counts[s]; }
+  if(total == 0) return JFGPU_OK;
+  // room in the CTAs' arenas of the local pool (as in run_batch): drain first when the bound says they could fill up
+  const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
+  const uint64_t per_cta = (total + e->n_sm - 1) / e->n_sm + 2;
+  const uint64_t need = per_cta * (CHUNK_BYTES / 4) / usable + 2;
+  if(ps.bound_chunks + need > ps.arena_chunks) { rc = part_drain(e, st); if(rc) return rc; }
+  if(ps.bound_chunks + need > ps.arena_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one exchange round");
+  ps.bound_chunks += need;
+  ps.pending = true;
+  RestageArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.T = table_dev(e, e->tab);
+  ra.recv_pool = e->sh.recv_pool; ra.recv_dir = e->sh.recv_dir; ra.n_src = G; ra.seg_chunks = (uint32_t)e->sh.seg_chunks;
+  for(uint32_t s = 0; s < G; ++s) ra.count[s] = (uint32_t)counts[s];
+  ra.first_region = e->p.shard_index * e->sh.own_regions; ra.split_lg = e->sh.split_lg; ra.sbits = e->sh.sbits;
+  ra.inv_lut = e->tab.inv_lut.as<uint64_t>(); ra.nbytes = e->nbytes;
+  PartDev pd = part_dev(e);
+  const size_t smem = (size_t)RING_P * 8 + (size_t)RING_P * RING * 4;
+  cudaFuncSetAttribute(restage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = (int)std::min<uint64_t>((total + 1) / 2, (uint64_t)e->n_sm);
+  restage_kernel<1><<<grid, 1024, smem, st>>>(ra, pd); JF_LAUNCHED();
+  CUDA_OK(e, cudaGetLastError());
+  return JFGPU_OK;
+}
+
 int jfgpu_insert_keys(jfgpu_handle e, const void* dev_keys, uint64_t n, void* stream) {
   if(!e) return JFGPU_ERR_ARG;
   if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
@@ -1364,6 +1542,11 @@ int jfgpu_clear(jfgpu_handle e) {
     CUDA_OK(e, cudaMemsetAsync(e->part.cta_fill.p, 0, e->part.cta_fill.bytes, e->cs));
     e->part.bound_chunks = e->part.P;
     e->part.pending = false;
+  }
+  if(e->sh.on) {
+    for(int i = 0; i < 2; ++i) CUDA_OK(e, cudaMemsetAsync(e->sh.pool_next[i].p, 0, e->sh.pool_next[i].bytes, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->sh.cta_chunk.p, 0xFF, e->sh.cta_chunk.bytes, e->cs));
+    CUDA_OK(e, cudaMemsetAsync(e->sh.cta_fill.p, 0, e->sh.cta_fill.bytes, e->cs));
   }
   e->bytes_fed = 0; e->count_ms = 0; e->kernel_ms = 0; e->kernel_launches = 0; e->drain_ms = 0; e->win_ms[0] = e->win_ms[1] = e->win_ms[2] = 0;
   e->eff_val_len = e->p.counter_len;

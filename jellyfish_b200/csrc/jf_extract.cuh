@@ -99,12 +99,12 @@ __device__ __noinline__ void spill_record(const TableDev T, uint64_t* spill_keys
 }
 
 // FAST = the common geometry of the region-by-region path, everything in 32-bit arithmetic: one key word, the
-// 11-bit-table hash with at most two parity rows (tables of up to 2^34 slots), 4-byte records, a single shard, at most
-// RING_P regions.  Its records do not go to the chunks one 4-byte store at a time (the GPU retires ~98 G scattered stores
+// 11-bit-table hash with at most six parity rows (tables of up to 2^38 slots), 4-byte records, at most RING_P regions
+// (the regions of this GPU's table, or -- sharded counting -- of the GLOBAL table, chunks then grouped by owning shard).  Its records do not go to the chunks one 4-byte store at a time (the GPU retires ~98 G scattered stores
 // per second whatever their width, scripts/micro/scatter_store.cu -- that alone would cap K1 at 98 G k-mers/s): every region
 // has a ring of RING records in shared memory, and after every SG k-mers per thread a pass over the regions writes the
 // complete groups of 8 records with two 16-byte stores (one 32-byte sector).
-constexpr uint32_t RING = 32;                     // records per region ring (power of two)
+constexpr uint32_t RING = 32;                     // records per region ring with RING_P regions (PartDev::ring_len in general)
 constexpr uint32_t RING_P = 1024;                 // regions at most on the FAST path (shared memory: RING_P * RING * 4 bytes)
 template<int KW, int SB, int MODE, int NTH, bool FAST>
 __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(const CountArgs a, const PartDev pd) {
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
     for(uint32_t p = tid; p < pd.P; p += NTH) {
       uint32_t c = my_chunk[p], f = my_fill[p];
       if(c == NO_CHUNK) {
-        c = alloc_chunk(pd, blockIdx.x); f = 0;
+        c = alloc_chunk(pd, pd.by_owner ? (p >> pd.owner_shift) : blockIdx.x); f = 0;
         if(c == NO_CHUNK) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); f = pd.chunk_recs; }
       }
       st_chunk[p] = c; st_cnt[p] = FAST ? (f | (f << 16)) : f;
@@ -148,27 +148,28 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   }
   // FAST: one pass over the regions -- write the complete groups of 8 records of every ring to its chunk, close chunks that are
   // nearly full.  Between two barriers; `finish` also writes the incomplete group (end of the launch).
+  const uint32_t rlen = pd.ring_len;
   auto flush_rings = [&](const bool finish) {
     for(uint32_t p = tid; p < pd.P; p += NTH) {
       const uint32_t v = st_cnt[p];
       uint32_t cnt = v & 0xFFFFu, fl = v >> 16;
-      const uint32_t lim = min(fl + RING, pd.chunk_recs);
+      const uint32_t lim = min(fl + rlen, pd.chunk_recs);
       if(cnt > lim) cnt = lim;                    // the slots beyond went to the spill list: hand them out again
       const uint32_t c = st_chunk[p];
       if(c == NO_CHUNK) continue;
       uint32_t* dst = reinterpret_cast<uint32_t*>(pd.pool + (size_t)c * CHUNK_BYTES);
-      const uint32_t* rg = ring + p * RING;
-      while((fl & 7u) && fl < cnt) { dst[fl] = rg[fl & (RING - 1)]; ++fl; }          // (only after a launch that ended inside a group)
+      const uint32_t* rg = ring + p * rlen;
+      while((fl & 7u) && fl < cnt) { dst[fl] = rg[fl & (rlen - 1)]; ++fl; }          // (only after a launch that ended inside a group)
       while(cnt - fl >= 8u) {
-        const uint4 x0 = *reinterpret_cast<const uint4*>(rg + (fl & (RING - 1))), x1 = *reinterpret_cast<const uint4*>(rg + (fl & (RING - 1)) + 4);
+        const uint4 x0 = *reinterpret_cast<const uint4*>(rg + (fl & (rlen - 1))), x1 = *reinterpret_cast<const uint4*>(rg + (fl & (rlen - 1)) + 4);
         *reinterpret_cast<uint4*>(dst + fl) = x0; *reinterpret_cast<uint4*>(dst + fl + 4) = x1;
         fl += 8;
       }
-      const bool close = cnt + RING > pd.chunk_recs;
-      if(close || finish) for(; fl < cnt; ++fl) dst[fl] = rg[fl & (RING - 1)];
+      const bool close = cnt + min(rlen, pd.margin) > pd.chunk_recs;
+      if(close || finish) for(; fl < cnt; ++fl) dst[fl] = rg[fl & (rlen - 1)];
       if(close) {
         pd.dir[c] = make_uint2(p, cnt);
-        const uint32_t nc = alloc_chunk(pd, blockIdx.x);
+        const uint32_t nc = alloc_chunk(pd, pd.by_owner ? (p >> pd.owner_shift) : blockIdx.x);
         st_chunk[p] = nc;
         if(nc == NO_CHUNK) { atomicAdd(&a.T.stats[STAT_POOL_FULL], 1ull); cnt = fl = pd.chunk_recs; }
         else cnt = fl = 0;
@@ -199,7 +200,6 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
   // constants of the 32-bit tail (FAST)
   const uint32_t f_rgb = pd.region_bits, f_hb = a.T.fbits - a.T.rbits, f_lsz = a.T.lsize;
   const uint32_t f_relmask = f_rgb >= 32 ? 0xFFFFFFFFu : ((1u << f_rgb) - 1u);
-  const uint32_t f_p0lo = (uint32_t)a.prow[0], f_p0hi = (uint32_t)(a.prow[0] >> 32), f_p1lo = (uint32_t)a.prow[1], f_p1hi = (uint32_t)(a.prow[1] >> 32);
   // constants of the k-mer extraction
   const uint32_t kbits = 2 * k;
   const uint64_t kmask_lo = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1ull);
@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
           auto ring_append = [&](const uint32_t p, const uint32_t rec, const int j) {
             const uint32_t v = atomicAdd(&st_cnt[p], 1u);
             const uint32_t slot = v & 0xFFFFu, fl = v >> 16;
-            if(slot - fl < RING && slot < pd.chunk_recs) ring[p * RING + (slot & (RING - 1))] = rec;
+            if(slot - fl < rlen && slot < pd.chunk_recs) ring[p * rlen + (slot & (rlen - 1))] = rec;
+            else if(pd.by_owner) atomicAdd(&a.T.stats[STAT_ROUTE_DROPPED], 1ull);   // sharded send side: another shard's k-mer cannot be spilled here
             else {
               uint64_t key[KW];
               kmer_at(j, key);
@@ -568,7 +569,10 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
                 const uint32_t klo = (uint32_t)key[0], khi = (uint32_t)(key[0] >> 32);
                 const uint32_t h32 = lut32[klo & 2047u] ^ lut32[2048 + ((klo >> 11) & 2047u)] ^
                                      lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + ((khi >> 1) & 2047u)];
-                const uint32_t ext = (__popc((klo & f_p0lo) ^ (khi & f_p0hi)) & 1u) | ((__popc((klo & f_p1lo) ^ (khi & f_p1hi)) & 1u) << 1);
+                uint32_t ext = 0;                 // position bits 32.. : one parity row each (two for a table of 2^34 slots)
+#pragma unroll
+                for(int r = 0; r < 6; ++r)
+                  if(r < (int)a.n_prow) ext |= (__popc((klo & (uint32_t)a.prow[r]) ^ (khi & (uint32_t)(a.prow[r] >> 32))) & 1u) << r;
                 P[jj] = (h32 >> f_rgb) | (ext << (32 - f_rgb));                       // region
                 R[jj] = ((h32 & f_relmask) << f_hb) | (uint32_t)(key[0] >> f_lsz);    // (position in the region, explicit key bits)
               }

@@ -325,6 +325,10 @@ struct PartDev {
   uint32_t  margin;         // a chunk is closed once fewer than `margin` free records remain
   uint32_t  arena_chunks;   // the pool is cut into one arena of this many chunks per CTA of the staging kernels: a CTA's open
                             // chunks then lie within a few MB of each other (its own TLB reach) whatever the other CTAs do
+  uint32_t  ring_len;       // records per region ring of the staging kernels (power of two, >= 32): the 128 KB of ring memory
+                            // are shared out among the regions, so tables with few regions get long rings
+  uint32_t  by_owner;       // sharded counting, send side: regions are those of the GLOBAL table and the arenas belong to the owning
+  uint32_t  owner_shift;    // shards (arena = region >> owner_shift), so that a shard's chunks are contiguous for the exchange
   uint8_t*  pool;
   unsigned int* pool_next;  // allocation cursor of every arena
   unsigned int* n_units;    // chunks listed in `order` (written by chunk_scan_kernel)

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(WIN_ST_NTH, 2) win_scatter_kernel(PartDev pd, 
   for(uint32_t i = b; i < min(b + per, wpr); ++i) {
     const uint32_t c = cnt[i];
     lbase[i] = run; lcur[i] = run;
-    gbase[i] = c ? atomicAdd(&wd.wcursor[(r << wd.wpr_lg) + i], c) : 0u;
+    gbase[i] = (c ? atomicAdd(&wd.wcursor[(r << wd.wpr_lg) + i], c) : 0u) - run;      // (output position = this + index in the staging buffer)
     run += c;
   }
   __syncthreads();
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(WIN_ST_NTH, 2) win_scatter_kernel(PartDev pd, 
   __syncthreads();
   for(uint32_t i = tid; i < total; i += WIN_ST_NTH) {
     const uint32_t v = stage[i], w = ((v >> hb) >> WIN_LG) & wmask;
-    const uint64_t dst = (uint64_t)gbase[w] + (i - lbase[w]);
+    const uint32_t dst = gbase[w] + i;
     if(dst < wd.wrec_cap) wd.wrec[dst] = v;
   }
 }
@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(WIN_ST_NTH, 2) win_scatter_kernel(PartDev pd, 
 constexpr uint32_t WIN2_NTH = 1024;
 constexpr uint32_t WIN2_CONS = WIN2_NTH - 32;      // consumer threads
 constexpr uint32_t WIN2_RB  = 10240;               // records per batch (a window of iid input holds ~0.6 * WIN_SLOTS)
+constexpr uint32_t WIN2_BLK = 256;                 // records a consumer warp claims at a time
 constexpr uint32_t WIN2_NONE = 0xFFFFFFFFu;
 constexpr size_t   WIN2_SMEM = (size_t)2 * WIN_SLOTS * 4 + (size_t)2 * WIN2_RB * 4;
 
@@ -281,29 +282,35 @@ __global__ void __launch_bounds__(WIN2_NTH, 1) win_insert2_kernel(TableDev T, Pa
       const uint32_t nb = min(WIN2_RB, inf.n - off);
       if(off) { mbar_wait(&full[s], fphase[s]); fphase[s] ^= 1u; }
       // Every lane keeps one record in flight and performs ONE probe per trip of the loop; the lanes whose record is settled
-      // take the next unclaimed records of the batch together (one shared-memory atomic per warp and trip), so a warp stays
-      // full until the batch is exhausted whatever the lengths of the probe sequences.
+      // take the next records of the warp's current block (WIN2_BLK records, claimed with one shared-memory atomic per block;
+      // inside a block the indices come from a warp-uniform register counter and a ballot), so a warp stays full until the
+      // batch is exhausted whatever the lengths of the probe sequences.
       bool have = false, want = true;
       uint32_t rec = 0, local = 0, kf = 0, at = 0, p = 0;
+      uint32_t blk_next = 0, blk_end = 0;          // (warp-uniform)
+      bool more = true;                            // the batch may still have unclaimed blocks (warp-uniform)
       for(;;) {
         const uint32_t need = __ballot_sync(0xffffffffu, want);
-        if(need) {
-          uint32_t base = 0;
-          const uint32_t leader = __ffs(need) - 1;
-          if(lane == leader) base = atomicAdd(&cursor[s], (uint32_t)__popc(need));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if(want) {
-            const uint32_t i = base + __popc(need & lt_mask);
-            have = i < nb;
-            want = false;
-            if(have) {
+        if(need && more) {
+          if(blk_next >= blk_end) {                // claim the next block
+            uint32_t base = 0;
+            if(lane == 0) base = atomicAdd(&cursor[s], WIN2_BLK);
+            blk_next = __shfl_sync(0xffffffffu, base, 0);
+            blk_end = min(blk_next + WIN2_BLK, nb);
+            more = blk_next < nb;
+          }
+          if(want && more) {
+            const uint32_t i = blk_next + __popc(need & lt_mask);
+            if(i < blk_end) {
               rec = recs[i];
               local = (rec >> hb) & (WIN_SLOTS - 1); kf = ((rec & hmask) << rb) | 1u;
               at = local; p = 0;
-            }
+              have = true; want = false;
+            }                                      // (else: asks again on the next trip, from the next block)
           }
+          blk_next = min(blk_next + (uint32_t)__popc(need), blk_end);
         }
-        if(!__any_sync(0xffffffffu, have)) break;
+        if(!__any_sync(0xffffffffu, have)) { if(!more) break; else continue; }
         if(have) {
           if(at < WIN_SLOTS) {
             const uint32_t o = atomicCAS(&win[at], 0u, kf | one);

@@ -8,8 +8,9 @@ ranks draw the same hash matrix (the reference's deterministic random stream), a
 the positions whose top log2(world) bits equal r, so the rank-ordered concatenation of the
 shard dumps is byte-identical to the single-GPU dump.
 
-The exchange logic (bucket capacities, count exchange, uneven all-to-all, ordering of the shard
-files) is plain torch.distributed code and is exercised on CPU with the gloo backend in
+Two forms of the exchange: 4-byte region RECORDS (RecordExchange, the default where the table geometry allows it: k <= 21,
+32-bit slots) and packed KEYS (any geometry).  The exchange logic (bucket capacities, count exchange, uneven all-to-all,
+ordering of the shard files) is plain torch.distributed code and is exercised on CPU with the gloo backend in
 tests/test_distributed_cpu.py through the `RouteBackend` seam below.
 """
 import os
@@ -90,19 +91,123 @@ def exchange_and_insert(backend, world, send, counts, capacity, recv, before_pay
     return total
 
 
+CHUNK = 8192          # bytes of a record chunk (jf_kernels.cuh CHUNK_BYTES)
+
+
+class RecordExchange(object):
+    """The record form of the exchange (include/jfgpu.h, jfgpu_shard_*): every rank's K1 writes 4-byte records of the GLOBAL
+    table's regions into a send pool whose chunk arenas belong to the owning shards; the chunks cross NVLink as they are
+    (one NCCL all-to-all per round, list form: no packing copy), the owner re-files them under its own regions
+    (restage_kernel) and drains them like a single GPU.  Two send banks: the extraction of round r+1 (stream A) runs beside
+    the exchange and the restaging of round r (stream B)."""
+
+    def __init__(self, hc, world, rank, dev, send_gb=None):
+        self.hc, self.world, self.rank, self.dev = hc, world, rank, dev
+        self.ok = False
+        if not hc.shard_setup(0, 0, 0, 0, 0, 0):       # geometry probe: nothing is allocated for tables the record form does not cover
+            return
+        free, _ = torch.cuda.mem_get_info(dev)
+        # two send banks + one receive pool = 3 x world x arena; a quarter of the free memory, at most 36 GB, for the three
+        budget = min(free // 4, 36 << 30) if send_gb is None else int(send_gb * (1 << 30))
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        floor = 2 * n_sm * max(1, 1024 // world) + 64
+        self.arena = max(floor, budget // (3 * world * (CHUNK + 8)))
+        try:
+            self.send = torch.empty(2 * world * self.arena * CHUNK, dtype=torch.uint8, device=dev)
+            self.send_dir = torch.empty(2 * world * self.arena * 8, dtype=torch.uint8, device=dev)
+            self.recv = torch.empty(world * self.arena * CHUNK, dtype=torch.uint8, device=dev)
+            self.recv_dir = torch.empty(world * self.arena * 8, dtype=torch.uint8, device=dev)
+        except RuntimeError:
+            return
+        if not hc.shard_setup(self.send.data_ptr(), self.send_dir.data_ptr(), self.arena, self.recv.data_ptr(), self.recv_dir.data_ptr(), self.arena):
+            self.send = self.send_dir = self.recv = self.recv_dir = None
+            return
+        self.round_bytes = hc.shard_round_bytes()
+        if self.round_bytes < (1 << 20):
+            return
+        self.sa = torch.cuda.Stream(device=dev)       # extraction
+        self.sb = torch.cuda.Stream(device=dev)       # exchange + restaging
+        self.sent = [torch.cuda.Event(), torch.cuda.Event()]     # bank b has been sent (may be overwritten)
+        self.ok = True
+
+    def _views(self, pool, bank, counts, unit):
+        w, a = self.world, self.arena
+        return [pool[((bank * w + d) * a) * unit:((bank * w + d) * a + counts[d]) * unit] for d in range(w)]
+
+    def add_device_text(self, ptr, n, begin, end):
+        self._rounds(n, begin, end, lambda off, ln, bank: ptr + off)
+
+    def add_host_text(self, hptr, n, begin, end):
+        """Pinned host text: every round's slice is copied to a device staging buffer (one per bank) on the extraction stream."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        if getattr(self, "_stage", None) is None:
+            self._stage = [torch.empty(self.round_bytes + 256, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+
+        def fetch(off, ln, bank):
+            dst = self._stage[bank].data_ptr()
+            if ln and lib.jfgpu_memcpy_h2d(C.c_void_p(dst), C.c_void_p(hptr + off), ln, C.c_void_p(self.sa.cuda_stream)):
+                raise RuntimeError("host to device copy failed")
+            return dst
+        self._rounds(n, begin, end, fetch)
+
+    def _rounds(self, n, begin, end, fetch):
+        w = self.world
+        rounds = (n + self.round_bytes - 1) // self.round_bytes if n else 0
+        t = torch.tensor([rounds], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rounds_all = max(int(t.item()), 1)        # every rank takes part in every exchange
+        for ev in self.sent:
+            ev.record(self.sb)
+        for r in range(rounds_all):
+            bank = r & 1
+            off = r * self.round_bytes
+            ln = max(0, min(self.round_bytes, n - off))
+            with torch.cuda.stream(self.sa):
+                self.sa.wait_event(self.sent[bank])
+                if ln or (r == 0 and begin) or (r == rounds_all - 1 and end):
+                    src = fetch(off, ln, bank)
+                    self.hc.shard_extract(src, ln, bank, begin and r == 0, end and off + ln >= n, stream=self.sa.cuda_stream)
+                counts = self.hc.shard_pack(bank, stream=self.sa.cuda_stream)       # synchronises stream A
+            with torch.cuda.stream(self.sb):
+                sc = torch.tensor(counts, dtype=torch.int64, device=self.dev)
+                rc = torch.empty_like(sc)
+                dist.all_to_all_single(rc, sc)
+                rcl = rc.tolist()
+                if max(rcl) > self.arena:
+                    raise RuntimeError("route bucket capacity exceeded (%d chunks > %d)" % (max(rcl), self.arena))
+                outs = [self.recv[(s * self.arena) * CHUNK:(s * self.arena + rcl[s]) * CHUNK] for s in range(w)]
+                dist.all_to_all(outs, self._views(self.send, bank, counts, CHUNK))
+                outs_d = [self.recv_dir[(s * self.arena) * 8:(s * self.arena + rcl[s]) * 8] for s in range(w)]
+                dist.all_to_all(outs_d, self._views(self.send_dir, bank, counts, 8))
+                self.sent[bank].record(self.sb)
+                self.hc.shard_unpack(rcl, stream=self.sb.cuda_stream)
+        self.sa.synchronize()
+        self.sb.synchronize()
+
+
 class ShardedCounter(object):
     """hash_counter over `world` GPUs.  `size` is the GLOBAL table size (jellyfish count -s)."""
 
     def __init__(self, size, val_len=7, k=None, canonical=False, rank=0, world=1, device=0, reprobes=126,
-                 batch_bytes=256 << 20, slack=1.25):
+                 batch_bytes=256 << 20, slack=1.25, exchange="auto", send_gb=None, **engine_kw):
         from .engine import HashCounter
         self.rank, self.world = rank, world
         self.hc = HashCounter(size, val_len, k=k, canonical=canonical, reprobes=reprobes, device=device,
-                              shard_index=rank, n_shards=world, allow_regrow=(world == 1), max_batch_bytes=batch_bytes)
+                              shard_index=rank, n_shards=world, allow_regrow=(world == 1), max_batch_bytes=batch_bytes, **engine_kw)
         self.backend = EngineBackend(self.hc)
         self.batch_bytes = batch_bytes
         self.dev = torch.device("cuda", device)
-        if world > 1:
+        self.records = None
+        if world > 1 and exchange in ("auto", "records"):
+            rx = RecordExchange(self.hc, world, rank, self.dev, send_gb=send_gb)
+            if rx.ok:
+                self.records = rx
+            elif exchange == "records":
+                raise RuntimeError("the record exchange does not cover this table geometry")
+            del rx
+        if world > 1 and self.records is None:
             kw = self.hc.key_words
             # a batch of B bytes yields at most B k-mers, spread evenly over the owners by the hash
             self.capacity = int(batch_bytes / world * slack) + 65536
@@ -120,6 +225,9 @@ class ShardedCounter(object):
             self.hc.add_device_text(ptr, n, begin=begin, end=end)
             return
         torch.cuda.current_stream(self.dev).synchronize()     # the caller's text is complete
+        if self.records is not None:
+            self.records.add_device_text(ptr, n, begin, end)
+            return
         with torch.cuda.stream(self.stream):
             self._add_device_text(ptr, n, begin, end)
         self.stream.synchronize()
@@ -169,6 +277,9 @@ class ShardedCounter(object):
         if self.world == 1:
             import ctypes as C
             self.hc.add_text((C.c_void_p(hptr), n), begin=begin, end=end)
+            return
+        if self.records is not None:
+            self.records.add_host_text(hptr, n, begin, end)
             return
         with torch.cuda.stream(self.stream):
             self._add_host_text(hptr, n, begin, end)

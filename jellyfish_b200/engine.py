@@ -79,6 +79,7 @@ class HashCounter(object):
         self.k = k
         self.canonical = bool(canonical)
         self.key_words = 2 if k > 32 else 1
+        self.n_shards = n_shards
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
@@ -155,6 +156,35 @@ class HashCounter(object):
 
     def insert_keys(self, keys_ptr, n, stream=None):
         self._check(self._lib.jfgpu_insert_keys(self._h, C.c_void_p(keys_ptr), n, C.c_void_p(stream or 0)))
+
+    # -- sharded counting, record exchange (include/jfgpu.h: jfgpu_shard_*) ----------------------------
+    def shard_setup(self, send_pool, send_dir, send_arena_chunks, recv_pool, recv_dir, recv_seg_chunks):
+        """Register the exchange buffers (device pointers).  False when the table geometry is not covered by the
+        record exchange (the caller then uses extract_route / insert_keys)."""
+        b = L.ShardBuffers(send_pool, send_dir, send_arena_chunks, recv_pool, recv_dir, recv_seg_chunks)
+        rc = self._lib.jfgpu_shard_setup(self._h, C.byref(b))
+        if rc == L.ERR_ARG:
+            return False
+        self._check(rc)
+        return True
+
+    def shard_round_bytes(self):
+        return self._lib.jfgpu_shard_round_bytes(self._h)
+
+    def shard_extract(self, dev_ptr, n, bank, begin=True, end=True, stream=None):
+        flags = (L.FILE_BEGIN if begin else 0) | (L.FILE_END if end else 0)
+        self._check(self._lib.jfgpu_shard_extract(self._h, C.c_void_p(dev_ptr), n, flags, bank, C.c_void_p(stream or 0)))
+
+    def shard_pack(self, bank, stream=None):
+        """Close the round: chunks per destination shard (synchronises the stream)."""
+        n = self.n_shards
+        counts = (C.c_uint64 * n)()
+        self._check(self._lib.jfgpu_shard_pack(self._h, bank, counts, C.c_void_p(stream or 0)))
+        return list(counts)
+
+    def shard_unpack(self, counts, stream=None):
+        arr = (C.c_uint64 * len(counts))(*counts)
+        self._check(self._lib.jfgpu_shard_unpack(self._h, arr, C.c_void_p(stream or 0)))
 
     OP_COUNT, OP_PRIME, OP_UPDATE = 0, 1, 2
 

@@ -13,9 +13,10 @@ cfg = json.loads(sys.argv[1])
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
+os.environ.setdefault("NCCL_MAX_CTAS", "16")      # K1 leaves 16 SMs to the exchange that runs beside it
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sc = ShardedCounter(cfg["size"], 7, k=cfg["k"], canonical=cfg["canonical"], rank=rank, world=world, device=local,
-                    batch_bytes=cfg.get("batch_bytes", 1 << 20))
+                    batch_bytes=cfg.get("batch_bytes", 1 << 20), **cfg.get("engine", {}))
 files = cfg["files"][rank::world]
 rounds = torch.tensor([len(files)], device="cuda")
 dist.all_reduce(rounds, op=dist.ReduceOp.MAX)
@@ -33,5 +34,5 @@ sc.dump_shard(cfg["out"])
 tot = torch.tensor([st["kmers"], st["inserted"]], dtype=torch.int64, device="cuda")
 dist.all_reduce(tot)
 if rank == 0:
-    print("TOTAL", tot.tolist())
+    print("TOTAL", tot.tolist(), "exchange:", "records" if sc.records is not None else "keys")
 dist.destroy_process_group()

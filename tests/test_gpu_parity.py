@@ -489,3 +489,85 @@ def test_baseline_config0_100mbp_body_md5(built, workdir):
     assert h["matrix1"]["columns"][:3] == [64834949, 57999349, 22595292] and h["matrix1"]["columns"][41] == 69326724
     assert len(b) == 99997658 * 10
     assert jfutil.md5(b) == "63058a336e1d9431eb6618d4a4f4deed"
+
+
+@pytest.mark.parametrize("name,world", [("multi_files", 2), ("multi_files", 4), ("k15C", 2), ("fq_dos", 2), ("c3", 2), ("x17_4M", 8)])
+def test_record_exchange_on_one_gpu(name, world, built, workdir, inputs):
+    """The record form of the multi-GPU data path without NCCL: one engine per shard on the same device.  K1 files 4-byte
+    records of the GLOBAL regions by owning shard (jfgpu_shard_extract / _pack), the chunks are copied into the owners'
+    receive pools the way the all-to-all would, the owners re-file them under their own regions (jfgpu_shard_unpack) and
+    drain them; the concatenated shard dumps must be the reference's database."""
+    import torch
+    from jellyfish_b200 import HashCounter
+    from jellyfish_b200.distributed import CHUNK, concat_shards
+    # (x17_4M: no golden of that size -- eight shards need a table of 4M slots to be filled region by region; the yardstick
+    # is the single-GPU engine, itself held to the goldens above)
+    args, ins = CASES[name] if name in CASES else (["-m", "17", "-s", "4M", "-C"], ["plain1m.fa"])
+    k = int(args[args.index("-m") + 1])
+    v = args[args.index("-s") + 1]
+    size = int(v[:-1]) * {"k": 10**3, "M": 10**6, "G": 10**9}[v[-1]] if v[-1] in "kMG" else int(v)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    arena = 2 * n_sm * max(1, 1024 // world) + 64
+    shards, bufs = [], []
+    for r in range(world):
+        hc = HashCounter(size, 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world, allow_regrow=False, part_min_mb=1, pool_bytes=256 << 20)
+        send = torch.empty(2 * world * arena * CHUNK, dtype=torch.uint8, device="cuda")
+        send_dir = torch.empty(2 * world * arena * 8, dtype=torch.uint8, device="cuda")
+        recv = torch.empty(world * arena * CHUNK, dtype=torch.uint8, device="cuda")
+        recv_dir = torch.empty(world * arena * 8, dtype=torch.uint8, device="cuda")
+        assert hc.shard_setup(send.data_ptr(), send_dir.data_ptr(), arena, recv.data_ptr(), recv_dir.data_ptr(), arena), "geometry not covered"
+        assert hc.shard_round_bytes() >= 1 << 20
+        shards.append(hc)
+        bufs.append((send, send_dir, recv, recv_dir))
+    n_round = 0
+    for i, f in enumerate(ins):
+        data = open(inputs[f], "rb").read()
+        buf = torch.zeros(len(data) + 256, dtype=torch.uint8, device="cuda")
+        if data:
+            buf[:len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        src = i % world
+        router = shards[src]
+        off = 0
+        while True:
+            ln = min(170000, len(data) - off)
+            bank = n_round & 1
+            n_round += 1
+            router.shard_extract(buf.data_ptr() + off, ln, bank, begin=off == 0, end=off + ln >= len(data))
+            counts = router.shard_pack(bank)
+            assert max(counts) <= arena
+            send, send_dir = bufs[src][0], bufs[src][1]
+            for d in range(world):
+                c = counts[d]
+                recv, recv_dir = bufs[d][2], bufs[d][3]
+                a0 = (bank * world + d) * arena
+                recv[src * arena * CHUNK:(src * arena + c) * CHUNK] = send[a0 * CHUNK:(a0 + c) * CHUNK]
+                recv_dir[src * arena * 8:(src * arena + c) * 8] = send_dir[a0 * 8:(a0 + c) * 8]
+                torch.cuda.synchronize()
+                got = [0] * world
+                got[src] = c
+                shards[d].shard_unpack(got)
+                torch.cuda.synchronize()
+            off += ln
+            if off >= len(data):
+                break
+    out = os.path.join(workdir, "recx_%s_%d" % (name, world))
+    n_kmers = n_ins = 0
+    for r, hc in enumerate(shards):
+        st = hc.done()
+        n_kmers += st["kmers"]
+        n_ins += st["inserted"]
+        hc.dump("%s.%d" % (out, r))
+        hc.close()
+    assert n_ins == n_kmers > 0
+    h, b = jfutil.split_db(concat_shards(out, world, out + ".jf"))
+    if name in GOLDEN:
+        g = GOLDEN[name]
+        assert jfutil.semantic(h) == g["header"]
+        assert jfutil.md5(b) == g["body_md5"]
+    else:
+        with HashCounter(size, 7, k=k, canonical="-C" in args, allow_regrow=False) as one:
+            one.add_files([inputs[f] for f in ins])
+            one.done()
+            assert jfutil.md5(one.dump_records()) == jfutil.md5(b) and len(b) > 0
+            hdr = one.header()
+            assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == jfutil.semantic(h)
