@@ -283,7 +283,8 @@ def main():
     nbytes = lib.jfgpu_synth_fasta_bytes(n_bases)
     text = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
     got = C.c_uint64(0)
-    rc = lib.jfgpu_synth_fasta_device(local_rank, C.c_void_p(text.data_ptr()), nbytes + 256, n_bases, 1000003 * (rank + 1), C.byref(got), None)
+    rc = lib.jfgpu_synth_fasta_device(local_rank, C.c_void_p(text.data_ptr()), nbytes + 256, n_bases, (0x9E3779B97F4A7C15 * (rank + 1)) & ((1 << 64) - 1), C.byref(got), None)      # (the seed is an OFFSET into one stream:
+    # ranks far apart, or they would count nearly the same k-mers and halve the load of the shared table)
     assert rc == 0, "synthetic FASTA generation failed"
     torch.cuda.synchronize()
     n_text = got.value
@@ -336,6 +337,7 @@ def main():
             acc[key] += st[key]
     barrier()
     wall = time.perf_counter() - t0
+    xtrace = counter.records.trace if counter is not None and counter.records is not None else None     # (stages of the last step)
     clocks = sampler.stop()
     launches = lib.jfgpu_kernel_launches() - launches0
     tot = torch.tensor([st["kmers"], st["inserted"], st["distinct"]], dtype=torch.int64, device=dev)
@@ -483,6 +485,7 @@ def main():
             "init_s": init_s, "writing": writing,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "distinct": distinct_total, "load_factor": distinct_total / float(info["size"]), "parity_n": parity_n,
+            "exchange": dict(xtrace, form="records") if xtrace else ({"form": "keys"} if counter is not None else None),
         }
         print(json.dumps(line))
     if world > 1:

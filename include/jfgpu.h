@@ -59,7 +59,7 @@ typedef struct {
   uint32_t max_reprobe;    /* -p : reprobe limit before clipping (default 126)        */
   uint32_t canonical;      /* -C                                                      */
   uint32_t allow_regrow;   /* 1: double the table when full (hash_counter.hpp:200-238);
-                              0: --disk behaviour is not implemented -> JFGPU_ERR_FULL */
+                              0: --disk: a full table goes to the spill hook (jfgpu_set_spill), JFGPU_ERR_FULL without one */
   int32_t  device;         /* CUDA device ordinal                                     */
   uint32_t shard_index;    /* this engine owns the slots whose top log2(n_shards)     */
   uint32_t n_shards;       /*   position bits equal shard_index (1 = whole table)     */
@@ -82,7 +82,10 @@ typedef struct {
                               (sub_commands/bc_main.cc:84-161): bf_size = expected number of k-mers (-s), bf_fp =
                               false positive rate (-f); `size`, `counter_len`, `max_reprobe` are ignored.  Feed text as
                               usual, then jfgpu_bloom_info_get / jfgpu_bloom_dump                                      */
-  uint32_t reserved32;
+  uint32_t min_qual;       /* -Q / --min-qual-char (the character) or --quality-start + --min-quality: bases whose quality character
+                              is below it do not count (count_main.cc:234-256,326-329; mer_qual_iterator.hpp:64-92); 0 = off.
+                              Text then has whole_sequence_parser semantics (a '\r' is an ordinary, window-resetting character);
+                              FASTQ must be 4 lines per record, and a feed must end on a record boundary unless it ends the file */
   uint64_t reserved[2];
 } jfgpu_params;
 
@@ -193,6 +196,14 @@ int  jfgpu_shard_unpack(jfgpu_handle h, const uint64_t* chunks_per_src /* [n_sha
  *    of `count --if`), JFGPU_OP_UPDATE adds only to keys already present (update_add, the second pass).
  *    Applies to the text fed after the call; drains pending work first. */
 int  jfgpu_set_op(jfgpu_handle h, uint32_t op);
+
+/* -- --disk (hash_counter::handle_full_ary without size doubling, hash_counter.hpp:187-192; count_main.cc:346-371): when the
+ *    table is full and may not or cannot be doubled (allow_regrow = 0, or no device memory for twice the size), the engine
+ *    calls `fn`, which writes the resident table out -- jfgpu_dump from inside the hook dumps the table as it stands --, then
+ *    zeroes the table and goes on counting with the same geometry and matrix.  The caller merges the intermediate files
+ *    (jellyfish merge / merge_files.cc:105-176).  Without a hook the same situations return JFGPU_ERR_FULL ("Hash full"). */
+typedef int (*jfgpu_spill_fn)(void* ctx, jfgpu_handle h);
+int  jfgpu_set_spill(jfgpu_handle h, jfgpu_spill_fn fn, void* ctx);
 
 /* -- zero the table and the statistics, keep geometry and hash matrix: what the dumper's
  *    zero_blocks leaves behind (sorted_dumper.hpp:67-68,98-99) so the counter can be reused. */

@@ -18,7 +18,7 @@ SYMBOLS = [
     "jfgpu_reference_matrix", "jfgpu_synth_fasta_bytes", "jfgpu_synth_fasta_device",
     "jfgpu_host_alloc", "jfgpu_host_free", "jfgpu_memcpy_h2d", "jfgpu_kernel_launches", "jfgpu_version",
     "jfgpu_bloom_info_get", "jfgpu_bloom_load", "jfgpu_bloom_dump",
-    "jfgpu_shard_setup", "jfgpu_shard_round_bytes", "jfgpu_shard_extract", "jfgpu_shard_pack", "jfgpu_shard_unpack",
+    "jfgpu_set_spill", "jfgpu_shard_setup", "jfgpu_shard_round_bytes", "jfgpu_shard_extract", "jfgpu_shard_pack", "jfgpu_shard_unpack",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_FULL, ERR_FORMAT, ERR_STATE, ERR_NOMEM, ERR_SINK = range(8)
@@ -33,7 +33,7 @@ class Params(C.Structure):
         ("n_shards", C.c_uint32), ("matrix_skip", C.c_uint32), ("bf_size", C.c_uint64),
         ("bf_fp", C.c_double), ("max_batch_bytes", C.c_uint64), ("pool_bytes", C.c_uint64),
         ("no_partition", C.c_uint32), ("part_min_mb", C.c_uint32), ("k2_mode", C.c_uint32), ("region_mb", C.c_uint32),
-        ("bloom_counter", C.c_uint32), ("reserved32", C.c_uint32), ("reserved", C.c_uint64 * 2),
+        ("bloom_counter", C.c_uint32), ("min_qual", C.c_uint32), ("reserved", C.c_uint64 * 2),
     ]
 
 
@@ -71,6 +71,7 @@ class BloomInfo(C.Structure):
 
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+SPILL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 _lib = None
 
@@ -137,6 +138,8 @@ def load():
     lib.jfgpu_bloom_load.restype = C.c_int
     lib.jfgpu_bloom_dump.argtypes = [H, SINK_FN, C.c_void_p]
     lib.jfgpu_bloom_dump.restype = C.c_int
+    lib.jfgpu_set_spill.argtypes = [H, SPILL_FN, C.c_void_p]
+    lib.jfgpu_set_spill.restype = C.c_int
     lib.jfgpu_shard_setup.argtypes = [H, C.POINTER(ShardBuffers)]
     lib.jfgpu_shard_setup.restype = C.c_int
     lib.jfgpu_shard_round_bytes.argtypes = [H]

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <limits>
 #include <map>
@@ -158,6 +159,8 @@ struct count_args {
   bool canonical = false, text = false, disk = false, no_merge = false, no_unlink = false, no_write = false;
   bool bc_given = false, bf_size_given = false, if_given = false, generator_given = false, sam_given = false;
   bool qual_given = false, timing_given = false, lower_given = false, upper_given = false;
+  bool min_qual_char_given = false, min_quality_given = false;
+  std::string min_qual_char; int quality_start = 64, min_quality = 0; uint32_t min_qual = 0;
   uint64_t bf_size = 0, lower = 0, upper = 0;
   double bf_fp = 0.01;
   const char* timing = "";
@@ -350,6 +353,9 @@ int bc_main(int argc, char* argv[]) {
   return 0;
 }
 
+// k-way SUM merge of binary/sorted files into `output` under header `oh` (defined with merge_main below)
+void merge_sum(const std::vector<std::string>& inputs, const char* output, jfb::file_header& oh, uint64_t lower, uint64_t upper);
+
 int count_main(int argc, char* argv[]) {
   using clk = std::chrono::system_clock;
   auto start_time = clk::now();
@@ -392,7 +398,9 @@ int count_main(int argc, char* argv[]) {
     case O_BFSIZE: a.bf_size = parse_u64(optarg, true, "--bf-size"); a.bf_size_given = true; break;
     case O_BFFP: a.bf_fp = atof(optarg); break;
     case O_IF: a.if_given = true; a.if_files.push_back(optarg); break;
-    case 'Q': case O_QSTART: case O_MINQ: a.qual_given = true; break;
+    case 'Q': a.min_qual_char = optarg; a.min_qual_char_given = true; break;
+    case O_QSTART: a.quality_start = atoi(optarg); break;
+    case O_MINQ: a.min_quality = atoi(optarg); a.min_quality_given = true; break;
     case 'p': a.reprobes = (uint32_t)parse_u64(optarg, false, "-p"); break;
     case O_TEXT: a.text = true; break;
     case O_DISK: a.disk = true; break;
@@ -413,8 +421,21 @@ int count_main(int argc, char* argv[]) {
   if(a.bc_given && a.bf_size_given) usage_error("Switches [--bf-size] and [--bc] conflict");
   if(a.sam_given) usage_error("SAM/BAM/CRAM not supported (missing htslib).");
   if(a.generator_given) usage_error("generators (-g) are not supported by jellyfish-b200");
-  if(a.qual_given) usage_error("quality filtering (-Q/--min-quality) is not implemented yet in jellyfish-b200");
-  if(a.disk) usage_error("--disk is not implemented in jellyfish-b200 (the table is doubled on the device instead)");
+  // count_main.cc:234-256
+  if(a.min_qual_char_given) {
+    if(a.min_qual_char.size() != 1) usage_error("[-Q, --min-qual-char] must be one character.");
+    const char c = a.min_qual_char[0];
+    if(c < '!' || c > '~') usage_error(std::string("Quality character '") + c + "' is outside of the range [!, ~]");
+    a.min_qual = (uint32_t)(unsigned char)c;
+  }
+  if(a.min_quality_given) {
+    if(a.quality_start < '!' || a.quality_start > '~') usage_error("Quality start " + std::to_string(a.quality_start) + " is outside the range [33, 126]");
+    const int mq = a.quality_start + a.min_quality;
+    if(mq < '!' || mq > '~') usage_error("Min quality " + std::to_string(a.min_quality) + " is outside the range [0, " + std::to_string((int)'~' - a.quality_start) + "]");
+    a.min_qual = (uint32_t)mq;
+  }
+  a.qual_given = a.min_qual != 0;
+  if(a.disk && a.text) usage_error("--disk with --text is not supported by jellyfish-b200 (intermediate files are binary)");
   if(a.mer_len < 1 || a.mer_len > 64) usage_error("jellyfish-b200 supports mer lengths 1..64");
 
   header.canonical(a.canonical);
@@ -422,10 +443,55 @@ int count_main(int argc, char* argv[]) {
   memset(&p, 0, sizeof(p));
   p.struct_size = sizeof(p);
   p.k = a.mer_len; p.size = a.size; p.counter_len = a.counter_len; p.max_reprobe = a.reprobes;
-  p.canonical = a.canonical; p.allow_regrow = 1; p.device = a.device; p.shard_index = 0; p.n_shards = 1;
+  p.canonical = a.canonical; p.allow_regrow = a.disk ? 0 : 1; p.device = a.device;      // --disk: no size doubling (count_main.cc:277) p.shard_index = 0; p.n_shards = 1;
   if(a.bf_size_given) { p.bf_size = a.bf_size; p.bf_fp = a.bf_fp; }       // count_main.cc:317-321
+  p.min_qual = a.min_qual;                                                 // count_main.cc:326-329
   jfgpu_handle h = nullptr;
   if(jfgpu_create(&p, &h) != JFGPU_OK) die(std::string("Failed to create the device hash: ") + jfgpu_last_error(nullptr));
+  // header + sorted records of the resident table into `path`; `final`: the one output file (-L/-U apply), else an
+  // intermediate file of --disk (everything, merged later)
+  auto write_table = [&](const char* path, bool final) {
+    jfgpu_table_info ti;
+    jfgpu_table_info_get(h, &ti);
+    header.size(ti.size);
+    header.key_len(ti.key_len);
+    header.val_len(ti.val_len);
+    if(ti.matrix_identity) header.matrix(ti.matrix_r == ti.matrix_c ? jfb::gf2_matrix::identity(ti.matrix_c)
+                                                                      : jfb::gf2_matrix::low_identity(ti.matrix_r, ti.matrix_c));
+    else header.matrix(jfb::gf2_matrix(ti.matrix_r, ti.matrix_c, ti.matrix_columns));
+    header.max_reprobe(ti.max_reprobe);
+    header.set_reprobes(ti.reprobes);
+    if(a.text) header.format("text/sorted");
+    else { header.format("binary/sorted"); header.counter_len(a.out_counter_len); }
+    std::ofstream out(path, std::ios::binary);
+    if(!out.good()) die(std::string("Can't open output file '") + path + "'");
+    header.write(out);
+    out.close();
+    FILE* f = fopen(path, "ab");
+    if(!f) die(std::string("Can't open output file '") + path + "'");
+    std::vector<char> iobuf((size_t)8 << 20);
+    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+    const unsigned key_bytes = (2 * a.mer_len + 7) / 8;
+    sink_ctx sc = { f, true, a.text, a.mer_len, key_bytes, key_bytes + 8 };
+    const uint64_t lo = final && a.lower_given ? a.lower : 0, hi = final && a.upper_given ? a.upper : std::numeric_limits<uint64_t>::max();
+    int rc = jfgpu_dump(h, lo, hi, a.text ? 8 : a.out_counter_len, file_sink, &sc, nullptr);
+    fclose(f);
+    if(rc != JFGPU_OK) die(std::string("Error while dumping: ") + jfgpu_last_error(h));
+  };
+  // --disk (hash_counter.hpp:187-192, dumper.hpp:45-60): a full table is written to <output>0, <output>1, ... and zeroed
+  struct spill_state { std::vector<std::string> files; std::function<void(const char*)> write; const char* prefix; } spill;
+  spill.prefix = a.output;
+  spill.write = [&](const char* path) { write_table(path, false); };
+  if(a.disk) {
+    auto hook = [](void* ctx, jfgpu_handle) -> int {
+      spill_state* sp = (spill_state*)ctx;
+      const std::string name = std::string(sp->prefix) + std::to_string(sp->files.size());
+      sp->files.push_back(name);
+      sp->write(name.c_str());
+      return 0;
+    };
+    if(jfgpu_set_spill(h, hook, &spill) != JFGPU_OK) die(jfgpu_last_error(h));
+  }
   auto after_init_time = clk::now();
 
   // count_main.cc:288-295: with --if the keys of those files are primed first, then only they are counted
@@ -442,32 +508,18 @@ int count_main(int argc, char* argv[]) {
 
   // ---- dump (binary_dumper::_dump -> sorted_dumper::_dump, binary_dumper.hpp:62-69) ------------
   if(!a.no_write) {
-    jfgpu_table_info ti;
-    jfgpu_table_info_get(h, &ti);
-    header.size(ti.size);
-    header.key_len(ti.key_len);
-    header.val_len(ti.val_len);
-    if(ti.matrix_identity) header.matrix(ti.matrix_r == ti.matrix_c ? jfb::gf2_matrix::identity(ti.matrix_c)
-                                                                      : jfb::gf2_matrix::low_identity(ti.matrix_r, ti.matrix_c));
-    else header.matrix(jfb::gf2_matrix(ti.matrix_r, ti.matrix_c, ti.matrix_columns));
-    header.max_reprobe(ti.max_reprobe);
-    header.set_reprobes(ti.reprobes);
-    if(a.text) header.format("text/sorted");
-    else { header.format("binary/sorted"); header.counter_len(a.out_counter_len); }
-    std::ofstream out(a.output, std::ios::binary);
-    if(!out.good()) die(std::string("Can't open output file '") + a.output + "'");
-    header.write(out);
-    out.close();
-    FILE* f = fopen(a.output, "ab");
-    if(!f) die(std::string("Can't open output file '") + a.output + "'");
-    std::vector<char> iobuf((size_t)8 << 20);
-    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
-    const unsigned key_bytes = (2 * a.mer_len + 7) / 8;
-    sink_ctx sc = { f, true, a.text, a.mer_len, key_bytes, key_bytes + 8 };
-    const uint64_t lo = a.lower_given ? a.lower : 0, hi = a.upper_given ? a.upper : std::numeric_limits<uint64_t>::max();
-    int rc = jfgpu_dump(h, lo, hi, a.text ? 8 : a.out_counter_len, file_sink, &sc, nullptr);
-    fclose(f);
-    if(rc != JFGPU_OK) die(std::string("Error while dumping: ") + jfgpu_last_error(h));
+    if(spill.files.empty()) write_table(a.output, true);
+    else {
+      // intermediate files exist (--disk): the rest of the table becomes one more, then a round of merging (count_main.cc:356-371)
+      const std::string last = std::string(a.output) + std::to_string(spill.files.size());
+      spill.files.push_back(last);
+      write_table(last.c_str(), false);
+      if(!a.no_merge) {
+        const uint64_t lo = a.lower_given ? a.lower : 0, hi = a.upper_given ? a.upper : std::numeric_limits<uint64_t>::max();
+        merge_sum(spill.files, a.output, header, lo, hi);
+        if(!a.no_unlink) for(const std::string& f : spill.files) unlink(f.c_str());
+      }
+    }
   }
   auto after_dump_time = clk::now();
   if(a.timing_given) {
@@ -720,11 +772,34 @@ int merge_main(int argc, char* argv[]) {
   jfb::file_header oh;
   oh.fill_standard();
   oh.set_cmdline(argc, argv);
+  std::vector<std::string> inputs;
+  for(int i = 0; i < n; ++i) inputs.push_back(argv[optind + i]);
+  dbs.clear();
+  merge_sum(inputs, output, oh, lower, upper);
+  return 0;
+}
+
+void merge_sum(const std::vector<std::string>& inputs, const char* output, jfb::file_header& oh, uint64_t lower, uint64_t upper) {
+  const int n = (int)inputs.size();
+  std::vector<db_reader> dbs(n);
+  for(int i = 0; i < n; ++i) {
+    dbs[i].open(inputs[i].c_str());
+    if(dbs[i].header.format() != "binary/sorted") die(std::string("Can only merge binary/sorted files: '") + inputs[i] + "'");
+    if(i) {
+      const jfb::file_header &a = dbs[0].header, &b = dbs[i].header;
+      if(a.key_len() != b.key_len()) die("Can't merge hashes of different key lengths");
+      if(a.size() != b.size()) die("Can't merge hash with different size");
+      if(a.matrix(1) != b.matrix(1)) die("Can't merge hash with different hash function");
+      if(a.max_reprobe_offset() != b.max_reprobe_offset()) die("Can't merge hashes with different reprobing strategies");
+    }
+  }
   const jfb::file_header& h0 = dbs[0].header;
-  // exactly the keys merge_files() sets (merge_files.cc:125-138,160-165): no val_len, no canonical
+  // exactly the keys merge_files() sets (merge_files.cc:125-138,160-165) on top of what the caller's header holds
   oh.size(h0.size()); oh.key_len(h0.key_len()); oh.matrix(h0.matrix(1));
   oh.max_reprobe(h0.max_reprobe()); { std::vector<uint64_t> r = h0.reprobes(); oh.set_reprobes(r.data()); }
-  oh.format("binary/sorted"); oh.counter_len(h0.counter_len());
+  unsigned ocl_min = h0.counter_len();
+  for(int i = 1; i < n; ++i) ocl_min = std::min<unsigned>(ocl_min, dbs[i].header.counter_len());
+  oh.format("binary/sorted"); oh.counter_len(ocl_min);
   std::ofstream out(output, std::ios::binary);
   if(!out.good()) die(std::string("Can't open out file '") + output + "'");
   oh.write(out);
@@ -740,7 +815,7 @@ int merge_main(int argc, char* argv[]) {
     if(cur[i] < dbs[i].n_records) { item it; dbs[i].key_at(cur[i], it.key); it.pos = dbs[i].pos_of(it.key); it.src = i; heap.push(it); }
   };
   for(int i = 0; i < n; ++i) push(i);
-  const unsigned key_bytes = dbs[0].key_bytes, ocl = dbs[0].counter_len;
+  const unsigned key_bytes = dbs[0].key_bytes, ocl = ocl_min;
   const uint64_t maxv = ocl >= 8 ? ~(uint64_t)0 : (((uint64_t)1 << (8 * ocl)) - 1);
   while(!heap.empty()) {
     item top = heap.top();
@@ -757,7 +832,6 @@ int merge_main(int argc, char* argv[]) {
     }
   }
   out.close();
-  return 0;
 }
 
 }  // namespace

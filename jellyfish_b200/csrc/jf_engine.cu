@@ -129,6 +129,12 @@ struct jfgpu_engine {
   // per-batch scratch
   DevBuf nlA, nlB, cntA, cntB, tstate; uint64_t scratch_tiles = 0;
   int format = 0;                 // 0 = FASTA, 1 = FASTQ: format of the file being fed
+  // -Q on FASTQ: a batch must end on a record boundary (the qualities of a read are looked up two lines further down);
+  // lines seen so far in the file (mod 4) and the incomplete last record of the previous feed
+  uint32_t q_lines = 0; std::string q_tail;
+  // --disk: what hash_counter::handle_full_ary does when the table cannot double (hash_counter.hpp:187-192): the caller's
+  // hook dumps the resident table (jfgpu_dump from inside the hook), the engine zeroes it and goes on counting
+  jfgpu_spill_fn spill_fn = nullptr; void* spill_ctx = nullptr; bool in_spill = false; uint64_t spills = 0;
   uint32_t op = 0;                // JFGPU_OP_*
   // bookkeeping
   bool in_file = false;
@@ -234,6 +240,7 @@ int table_setup(jfgpu_engine* e, Table& t, unsigned lsize, const jfb::gf2_matrix
   // fast hash tables: 2k <= 44 -> four 11-bit chunks; entries = low 32 bits of the partial products,
   // position bits 32.. come from parity rows
   t.hash_fast = false; t.n_prow = 0;
+  for(unsigned i = 0; i < 8; ++i) t.prow[i] = 0;            // (unused rows must be zero: K1 evaluates a fixed number of them)
   std::vector<uint32_t> l11;
   if(e->kw == 1 && kbits <= 44 && lsize <= 40) {
     l11.assign(4 * 2048, 0);
@@ -407,6 +414,7 @@ void part_release(jfgpu_engine* e) {
 }
 
 int regrow(jfgpu_engine* e);
+int spill_table(jfgpu_engine* e, uint64_t n_failed);
 int read_stats(jfgpu_engine* e);
 int bloom_draw(jfgpu_engine* e);
 BloomDev bloom_dev(const jfgpu_engine* e);
@@ -554,7 +562,7 @@ int part_drain(jfgpu_engine* e, cudaStream_t st) {
   // geometry the records were written with (a regrow in the middle changes e->tab)
   const TableDev T0 = table_dev(e, e->tab);
   const unsigned sb0 = e->tab.slot_bits;
-  const bool careful = e->p.allow_regrow != 0;
+  const bool careful = e->p.allow_regrow != 0 || e->spill_fn != nullptr;
   unsigned int n_units = 0;
   if(careful) {
     CUDA_OK(e, cudaMemcpyAsync(&n_units, pd.n_units, 4, cudaMemcpyDeviceToHost, st));
@@ -674,9 +682,12 @@ size_t part_cap_len(const jfgpu_engine* e, size_t len) {
   return len > cap ? (size_t)std::max<uint64_t>(cap & ~(uint64_t)15, 16) : len;
 }
 
+// the quality threshold in force: the PRIME pass of --if reads its files without it (count_main.cc:289-295 uses mer_counter there)
+static uint32_t eff_min_qual(const jfgpu_engine* e) { return e->op == JFGPU_OP_PRIME ? 0u : e->p.min_qual; }
+
 // One batch of device-resident text through K0a, K0b, K1 on `stream`.
 int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, cudaStream_t stream,
-              int mode, uint64_t* route_keys, unsigned long long* route_counts, uint64_t route_cap) {
+              int mode, uint64_t* route_keys, unsigned long long* route_counts, uint64_t route_cap, uint64_t n_back = 0) {
   if(n == 0) return JFGPU_OK;
   PartState& ps = e->part;
   const bool bc_build = e->bloom.mode == BLOOM_COUNT;
@@ -696,7 +707,7 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     if(ps.bound_chunks + need > ps.arena_chunks) {
       rc = part_drain(e, stream);
       if(rc) return rc;
-      if(!e->part.P) return run_batch(e, dev, n, n_look, stream, mode, route_keys, route_counts, route_cap);
+      if(!e->part.P) return run_batch(e, dev, n, n_look, stream, mode, route_keys, route_counts, route_cap, n_back);
     }
     if(ps.bound_chunks + need > ps.arena_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one batch");
     ps.bound_chunks += need;
@@ -714,7 +725,7 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
     tile_state_fastq_kernel<<<1, 1024, 0, stream>>>(n_tiles, e->cntA.as<uint32_t>(), e->cntB.as<uint32_t>(), e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
   else
     tile_state_kernel<<<1, 1024, 0, stream>>>(dev, n_tiles, tile, e->nlA.as<long long>(), e->nlB.as<long long>(),
-                                              e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>());
+                                              e->carry[e->carry_cur].as<Carry>(), e->tstate.as<uint8_t>(), eff_min_qual(e));
   JF_LAUNCHED();
   CountArgs a;
   memset(&a, 0, sizeof(a));
@@ -726,6 +737,7 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   a.hash_fast = e->tab.hash_fast ? 1 : 0; a.n_prow = e->tab.n_prow;
   a.lut_bytes = e->tab.hash_fast ? 4 * 2048 * 4 : e->nbytes * 256 * 8;
   for(unsigned i = 0; i < 8; ++i) a.prow[i] = e->tab.prow[i];
+  a.min_qual = eff_min_qual(e); a.n_back = n_back;
   a.k = e->k; a.canonical = e->p.canonical; a.nbytes = e->nbytes; a.mode = (uint32_t)(shard_send ? 2 : mode); a.format = (uint32_t)e->format;
   a.T = table_dev(e, e->tab);
   a.bloom = bloom_dev(e);
@@ -753,7 +765,8 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
   rc = dispatch(e, e->kw, e->tab.slot_bits, [&](auto KW, auto SB) -> int {
     constexpr int kw = decltype(KW)::value, sb = decltype(SB)::value;
     if(shard_send) {
-      if(kw == 1) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, 0, 0, true), true);
+      if(kw == 1 && e->tab.n_prow <= 2) return launch(extract_kernel<1, sb, 2, 1024, true, 2>, 1024, count_smem_bytes<1024>(a.lut_bytes, 0, 0, true), true);
+      if(kw == 1) return launch(extract_kernel<1, sb, 2, 1024, true, 6>, 1024, count_smem_bytes<1024>(a.lut_bytes, 0, 0, true), true);
       return fail(e, JFGPU_ERR_STATE, "internal: record exchange with a two-word key");
     }
     if(part) {
@@ -762,7 +775,8 @@ int run_batch(jfgpu_engine* e, const uint8_t* dev, uint64_t n, uint64_t n_look, 
       const bool fast = kw == 1 && e->tab.hash_fast && e->tab.n_prow <= 6 && ps.rec_bytes == 4 && e->shard_bits == 0 &&
                         ps.region_bits >= 2 && ps.region_bits < 32 && e->tab.lsize <= 38 && e->tab.lsize >= ps.region_bits &&
                         ps.P <= RING_P && !a.bloom.mode;
-      if(kw == 1 && fast) return launch(extract_kernel<1, sb, 2, 1024, true>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, 0, true), true);
+      if(kw == 1 && fast && e->tab.n_prow <= 2) return launch(extract_kernel<1, sb, 2, 1024, true, 2>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, 0, true), true);
+      if(kw == 1 && fast) return launch(extract_kernel<1, sb, 2, 1024, true, 6>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, 0, true), true);
       return launch(extract_kernel<kw, sb, 2, 1024, false>, 1024, count_smem_bytes<1024>(a.lut_bytes, ps.stage_bytes, bloom_smem), true);
     }
     if(mode == 1) return launch(extract_kernel<kw, sb, 1, 512, false>, 512, count_smem_bytes<512>(a.lut_bytes, 0, bloom_smem), false);
@@ -968,6 +982,41 @@ int rebuild_table_impl(jfgpu_engine* e, unsigned nl, const jfb::gf2_matrix& M, i
   return JFGPU_OK;
 }
 
+// hash_counter::handle_full_ary without doubling (hash_counter.hpp:187-192): the caller's hook writes the resident table out,
+// the table is zeroed, the keys that found no slot go into the empty table, counting continues with the same geometry.
+int spill_table(jfgpu_engine* e, uint64_t n_failed) {
+  e->in_spill = true;
+  const int hrc = e->spill_fn(e->spill_ctx, e);
+  e->in_spill = false;
+  if(hrc) return fail(e, JFGPU_ERR_SINK, "the spill hook failed (--disk: writing an intermediate file)");
+  CUDA_OK(e, cudaMemsetAsync(e->tab.slots.p, 0, e->tab.bytes(), e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_keys.p, 0, e->tab.ovf_size * 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_vals.p, 0, e->tab.ovf_size * 8, e->cs));
+  unsigned long long* st = e->stats.as<unsigned long long>();
+  unsigned long long inserted_before = 0;
+  CUDA_OK(e, cudaMemcpyAsync(&inserted_before, st + STAT_INSERTED, 8, cudaMemcpyDeviceToHost, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(st + STAT_DISTINCT, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(st + STAT_REPROBES, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(st + STAT_OVERFLOWED, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(st + STAT_FAILED, 0, 8, e->cs));
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  const int old_fail = e->fail_cur;
+  e->fail_cur ^= 1;                                   // (failures of the re-insertion -- there should be none -- are kept apart)
+  if(!e->fail_keys[e->fail_cur].p) {
+    CUDA_OK(e, e->fail_keys[e->fail_cur].alloc(e->fail_cap * 8 * e->kw));
+    CUDA_OK(e, e->fail_counts[e->fail_cur].alloc(e->fail_cap * 8));
+  }
+  const uint32_t op = e->op; e->op = 0;
+  int rc = insert_keys_into(e, e->tab, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
+  e->op = op;
+  if(rc) return rc;
+  // the failed keys were counted as occurrences when they failed? no: they are counted now, once
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));
+  (void)inserted_before;
+  e->spills++;
+  return JFGPU_OK;
+}
+
 // hash_counter::double_size (hash_counter.hpp:200-238): allocate a table twice as large with a
 // freshly drawn matrix, re-insert every (key, count) of the old one, then the keys that failed.
 int regrow(jfgpu_engine* e) {
@@ -978,9 +1027,11 @@ int regrow(jfgpu_engine* e) {
     const uint64_t n_failed = e->h_stats[STAT_FAILED];
     if(n_failed == 0) return JFGPU_OK;
     if(e->h_stats[STAT_FAIL_DROPPED]) return fail(e, JFGPU_ERR_FULL, "Hash full (too many keys failed before the table could be doubled)");
-    if(!e->p.allow_regrow || e->shard_bits) return fail(e, JFGPU_ERR_FULL, "Hash full");
     const unsigned kbits = 2 * e->k;
-    if(kbits < 64 && e->tab.size >= ((uint64_t)1 << kbits)) return fail(e, JFGPU_ERR_FULL, "Hash full");
+    if(!e->p.allow_regrow || e->shard_bits || (kbits < 64 && e->tab.size >= ((uint64_t)1 << kbits))) {
+      if(e->spill_fn && !e->shard_bits) { rc = spill_table(e, n_failed); if(rc) return rc; continue; }
+      return fail(e, JFGPU_ERR_FULL, "Hash full");
+    }
     const unsigned nl = e->tab.lsize + 1;
     jfb::gf2_matrix M = draw_matrix(e, (uint64_t)1 << nl, nl);
     // switch the failure list so that failures of the re-insertion are kept apart
@@ -992,6 +1043,14 @@ int regrow(jfgpu_engine* e) {
     }
     CUDA_OK(e, cudaMemsetAsync(e->stats.as<unsigned long long>() + STAT_FAILED, 0, 8, e->cs));
     rc = rebuild_table(e, nl, M, old_fail, n_failed);
+    if(rc == JFGPU_ERR_FULL && e->spill_fn) {          // no memory for the doubled table: dump and zero this one instead
+      e->fail_cur = old_fail;
+      CUDA_OK(e, cudaMemcpyAsync(e->stats.as<unsigned long long>() + STAT_FAILED, &n_failed, 8, cudaMemcpyHostToDevice, e->cs));
+      CUDA_OK(e, cudaStreamSynchronize(e->cs));
+      rc = spill_table(e, n_failed);
+      if(rc) return rc;
+      continue;
+    }
     if(rc) return rc;
     e->regrows++;
   }
@@ -1153,7 +1212,7 @@ int jfgpu_create(const jfgpu_params* params, jfgpu_handle* out) {
 
   // side structures
   e->batch_bytes = params->max_batch_bytes ? (size_t)((params->max_batch_bytes + 15) & ~(uint64_t)15) : ((size_t)64 << 20);
-  e->fail_cap = params->allow_regrow ? 2 * (uint64_t)e->batch_bytes : ((uint64_t)1 << 16);
+  e->fail_cap = 2 * (uint64_t)e->batch_bytes;      // (two groups of failed keys: the failure counter is read one group late)
   bool ok = e->stats.alloc(STAT_N * 8) == cudaSuccess && e->carry[0].alloc(sizeof(Carry)) == cudaSuccess &&
             e->carry[1].alloc(sizeof(Carry)) == cudaSuccess &&
             e->fail_keys[0].alloc(e->fail_cap * 8 * e->kw) == cudaSuccess && e->fail_counts[0].alloc(e->fail_cap * 8) == cudaSuccess &&
@@ -1247,10 +1306,10 @@ int jfgpu_feed_device(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t 
   for(size_t off = 0; off < n; ) {
     size_t len = std::min(e->part.P ? std::max<size_t>(e->batch_bytes, (size_t)512 << 20) : e->batch_bytes, n - off);
     len = part_cap_len(e, len);
-    rc = run_batch(e, p + off, len, n - off, st, 0, nullptr, nullptr, 0);
+    rc = run_batch(e, p + off, len, n - off, st, 0, nullptr, nullptr, 0, off);
     if(rc) return rc;
     off += len;
-    if(e->p.allow_regrow && !e->part.P && e->tab.slots.p) {          // the failure list only holds two batches
+    if((e->p.allow_regrow || e->spill_fn) && !e->part.P && e->tab.slots.p) {          // the failure list only holds two batches
       if(st != e->cs) CUDA_OK(e, cudaStreamSynchronize(st));
       rc = check_after_batches(e);
       if(rc) return rc;
@@ -1264,11 +1323,41 @@ int jfgpu_feed_device(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_t 
   return end_feed(e, flags, st);
 }
 
+// length of the longest prefix of [p, p+len) that ends right behind the newline closing a 4-line record, given the number
+// of lines (mod 4) in front of p; 0 when there is none.  *lines_out = lines (mod 4) at that point.
+static size_t fastq_record_prefix(const char* p, size_t len, uint32_t lines_mod4, uint32_t* lines_out) {
+  size_t best = 0; uint32_t lines = lines_mod4, best_lines = lines_mod4;
+  const char* q = p; const char* end = p + len;
+  while(q < end) {
+    const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
+    if(!nl) break;
+    lines = (lines + 1) & 3u;
+    q = nl + 1;
+    if(lines == 0) { best = (size_t)(q - p); best_lines = 0; }
+  }
+  *lines_out = best_lines;
+  return best;
+}
+
 int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
   if(!e) return JFGPU_ERR_ARG;
   cudaSetDevice(e->device);
-  int rc = begin_feed(e, flags, n ? (unsigned char)bytes[0] : -1, e->cs);
+  int rc = begin_feed(e, flags, n ? (unsigned char)bytes[0] : (e->q_tail.empty() ? -1 : (unsigned char)e->q_tail[0]), e->cs);
   if(rc) return rc;
+  if(flags & JFGPU_FILE_BEGIN) { e->q_lines = 0; e->q_tail.clear(); }
+  const bool qfastq = eff_min_qual(e) != 0 && e->format == 1;
+  std::string joined;                         // (-Q on FASTQ: the incomplete record of the previous feed comes first)
+  if(qfastq && !e->q_tail.empty()) {
+    joined.swap(e->q_tail);
+    joined.append(bytes, n);
+    bytes = joined.data(); n = joined.size();
+  }
+  if(qfastq && !(flags & JFGPU_FILE_END)) {   // keep the incomplete last record for the next feed
+    uint32_t l2 = 0;
+    const size_t whole = fastq_record_prefix(bytes, n, e->q_lines, &l2);
+    e->q_tail.assign(bytes + whole, n - whole);
+    n = whole;
+  }
   for(int i = 0; i < 2; ++i) if(!e->stage[i].p) CUDA_OK(e, e->stage[i].alloc(e->batch_bytes + 64));
   if(e->part.P) { rc = part_alloc(e); if(rc) return rc; }
   cudaEventRecord(e->ev_t0, e->cs);
@@ -1277,10 +1366,16 @@ int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
     size_t len = part_cap_len(e, std::min(e->batch_bytes, n - off));
     // never end a chunk on '\r' unless it is the end of the data: the device looks one byte ahead
     if(off + len < n) { size_t l2 = len; while(l2 > 1 && bytes[off + l2 - 1] == '\r') --l2; if(l2 > 1) len = l2; }
+    if(qfastq && off + len < n) {              // ... and, under -Q, only on a record boundary
+      uint32_t l2 = 0;
+      const size_t whole = fastq_record_prefix(bytes + off, len, e->q_lines, &l2);
+      if(whole == 0) return fail(e, JFGPU_ERR_FORMAT, "Invalid fastq file: a record is larger than the staging buffer (or has more than 4 lines)");
+      len = whole; e->q_lines = l2;
+    }
     const int s = e->stage_cur;
     // the previous batch that used this staging buffer must be done before it is overwritten
     CUDA_OK(e, cudaEventSynchronize(e->ev_done[s]));
-    if(e->p.allow_regrow && e->tab.slots.p) {
+    if((e->p.allow_regrow || e->spill_fn) && e->tab.slots.p) {
       // peek at the live failure counter without draining the compute stream
       CUDA_OK(e, cudaMemcpyAsync(e->h_stats + STAT_FAILED, e->stats.as<unsigned long long>() + STAT_FAILED, 8, cudaMemcpyDeviceToHost, e->hs));
       CUDA_OK(e, cudaStreamSynchronize(e->hs));
@@ -1295,6 +1390,7 @@ int jfgpu_feed(jfgpu_handle e, const char* bytes, size_t n, uint32_t flags) {
     e->stage_cur ^= 1;
     off += len;
   }
+  if(qfastq && !(flags & JFGPU_FILE_END)) e->q_lines = 0;       // (the feed was cut behind a complete record)
   cudaEventRecord(e->ev_t1, e->cs);
   e->bytes_fed += n;
   CUDA_OK(e, cudaStreamSynchronize(e->cs));
@@ -1323,7 +1419,7 @@ int jfgpu_extract_route(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_
   const uint8_t* p = (const uint8_t*)dev_bytes;
   for(size_t off = 0; off < n; ) {
     size_t len = std::min(e->batch_bytes, n - off);
-    rc = run_batch(e, p + off, len, n - off, st, 1, (uint64_t*)dev_keys, (unsigned long long*)dev_counts, capacity);
+    rc = run_batch(e, p + off, len, n - off, st, 1, (uint64_t*)dev_keys, (unsigned long long*)dev_counts, capacity, off);
     if(rc) return rc;
     off += len;
   }
@@ -1403,7 +1499,7 @@ int jfgpu_shard_extract(jfgpu_handle e, const void* dev_bytes, size_t n, uint32_
   const uint8_t* p = (const uint8_t*)dev_bytes;
   for(size_t off = 0; off < n; ) {
     const size_t len = std::min<size_t>((size_t)512 << 20, n - off);
-    rc = run_batch(e, p + off, len, n - off, st, 3, nullptr, nullptr, bank);
+    rc = run_batch(e, p + off, len, n - off, st, 3, nullptr, nullptr, bank, off);
     if(rc) return rc;
     off += len;
   }
@@ -1444,7 +1540,7 @@ int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
   if(total == 0) return JFGPU_OK;
   // room in the CTAs' arenas of the local pool (as in run_batch): drain first when the bound says they could fill up
   const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
-  const uint64_t per_cta = (total + e->n_sm - 1) / e->n_sm + 2;
+  const uint64_t per_cta = ((total + 1023) / 1024 + e->n_sm - 1) / e->n_sm * 1024;     // (a CTA takes batches of 1024 chunks)
   const uint64_t need = per_cta * (CHUNK_BYTES / 4) / usable + 2;
   if(ps.bound_chunks + need > ps.arena_chunks) { rc = part_drain(e, st); if(rc) return rc; }
   if(ps.bound_chunks + need > ps.arena_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one exchange round");
@@ -1460,7 +1556,7 @@ int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
   PartDev pd = part_dev(e);
   const size_t smem = (size_t)RING_P * 8 + (size_t)RING_P * RING * 4;
   cudaFuncSetAttribute(restage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = (int)std::min<uint64_t>((total + 1) / 2, (uint64_t)e->n_sm);
+  const int grid = (int)std::min<uint64_t>((total + 1023) / 1024, (uint64_t)e->n_sm);
   restage_kernel<1><<<grid, 1024, smem, st>>>(ra, pd); JF_LAUNCHED();
   CUDA_OK(e, cudaGetLastError());
   return JFGPU_OK;
@@ -1519,6 +1615,13 @@ int jfgpu_set_op(jfgpu_handle e, uint32_t op) {
   int rc = jfgpu_finish(e, nullptr);
   if(rc) return rc;
   e->op = op;
+  return JFGPU_OK;
+}
+
+int jfgpu_set_spill(jfgpu_handle e, jfgpu_spill_fn fn, void* ctx) {
+  if(!e) return JFGPU_ERR_ARG;
+  if(e->shard_bits) return fail(e, JFGPU_ERR_STATE, "spilling is not supported on a sharded table");
+  e->spill_fn = fn; e->spill_ctx = ctx;
   return JFGPU_OK;
 }
 
@@ -1613,7 +1716,7 @@ int jfgpu_dump(jfgpu_handle e, uint64_t lower, uint64_t upper, uint32_t ocl, jfg
   if(!e->tab.slots.p) return fail(e, JFGPU_ERR_STATE, "this engine holds a Bloom counter, not a hash table");
   if(ocl < 1 || ocl > 8) return fail(e, JFGPU_ERR_ARG, "out_counter_len must be in [1, 8]");
   cudaSetDevice(e->device);
-  int rc = jfgpu_finish(e, nullptr);
+  int rc = e->in_spill ? JFGPU_OK : jfgpu_finish(e, nullptr);      // (from inside the spill hook the table is dumped as it stands)
   if(rc) return rc;
   // Segment by segment, two buffers: while the host hands segment i to the sink, the device sorts and serialises segment
   // i+1 (jf_dump.cuh: no global sort, every tile of 8192 positions is ordered in shared memory) and the copy engine brings

@@ -106,7 +106,9 @@ __device__ __noinline__ void spill_record(const TableDev T, uint64_t* spill_keys
 // complete groups of 8 records with two 16-byte stores (one 32-byte sector).
 constexpr uint32_t RING = 32;                     // records per region ring with RING_P regions (PartDev::ring_len in general)
 constexpr uint32_t RING_P = 1024;                 // regions at most on the FAST path (shared memory: RING_P * RING * 4 bytes)
-template<int KW, int SB, int MODE, int NTH, bool FAST>
+// NPR (FAST only): parity rows evaluated per k-mer -- 2 covers tables of up to 2^34 slots (unused rows are zero), 6 the
+// sharded tables of up to 2^38.
+template<int KW, int SB, int MODE, int NTH, bool FAST, int NPR = 2>
 __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(const CountArgs a, const PartDev pd) {
   constexpr int WINB = NTH * 32;
   constexpr int TILEB = WINB - HALO;
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
       const uint32_t b = sm.win[tid * 32 + p];
       N |= (uint32_t)(b == '\n') << p; Gm |= (uint32_t)(b == '>') << p; Rm |= (uint32_t)(b == '\r') << p;
     }
+    if(a.min_qual) Rm = 0;                               // -Q: std::getline keeps '\r' in the sequence, where it resets the window
     const bool slow = a.format == 1 || Rm != 0;          // per-byte path: FASTQ line types, '\r' look-ahead
 
     uint32_t prevb = 'x';
@@ -322,19 +325,39 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
       // FASTQ, 4-line records (mer_overlap_sequence_parser.hpp:187-217): only sequence lines emit symbols; the
       // start of a header line emits the window reset; '@' / '+' at the line starts are verified
       uint32_t ty = st_in; bool at_start = prevb == '\n';
+      long long qoff = 0; bool have_q = false;      // -Q: quality of the sequence byte at global position g is in[g + qoff]
 #pragma unroll 1
       for(int i = vlo; i < vhi; ++i) {
         {
           const uint32_t b = sm.win[tid * 32 + i];
           uint32_t s = 8;
-          if(b == '\n') { ty = (ty + 1) & 3u; at_start = true; }
+          if(b == '\n') { ty = (ty + 1) & 3u; at_start = true; have_q = false; }
           else {
-            if(at_start && b != '\r') {
+            const bool first_of_line = at_start;
+            if(at_start && (b != '\r' || a.min_qual)) {
               at_start = false;
               if(ty == 0) { s = SYM_BREAK; if(b != '@') atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull); }
               else if(ty == 2 && b != '+') atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull);
             }
-            if(ty == 1) {
+            if(ty == 1 && a.min_qual) {
+              // whole_sequence_parser.hpp:154-193 + mer_qual_iterator.hpp:64-92, 4-line records: the quality line is the
+              // second line after this one, same column
+              const long long g = g0 + i;
+              if(!have_q) {
+                long long sl = g;                    // start of this sequence line
+                while(sl > -(long long)a.n_back && a.in[sl - 1] != '\n') --sl;
+                long long e1 = g; while(e1 < (long long)a.n_look && a.in[e1] != '\n') ++e1;
+                long long e2 = e1 + 1; while(e2 < (long long)a.n_look && a.in[e2] != '\n') ++e2;
+                qoff = e2 + 1 - sl; have_q = true;
+                if(e2 >= (long long)a.n_look) { atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull); have_q = false; }
+                else if(first_of_line) {             // once per read: as many qualities as bases
+                  long long e3 = e2 + 1; while(e3 < (long long)a.n_look && a.in[e3] != '\n') ++e3;
+                  if(e3 - (e2 + 1) != e1 - sl) atomicAdd(&a.T.stats[STAT_FORMAT_ERR], 1ull);
+                }
+              }
+              s = base_symbol(b);
+              if(have_q && (signed char)a.in[g + qoff] < (signed char)a.min_qual) s = SYM_BREAK;
+            } else if(ty == 1) {
               if(b == '\r') { if(!cr_dropped(a.in, (uint64_t)(g0 + i), a.n_look)) s = SYM_BREAK; }
               else s = base_symbol(b);
             }
@@ -420,7 +443,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
         if(lane == 0 && in_seq && idx0 < k - 1 && !sm.halo_break) {
           // pathological input (very short lines / long runs of blank lines): exact slow path
           if(a.format == 1) backfill_fastq(a.in, a.n_look, a.carry_in, h, PRE, sm.pre);
-          else backfill_symbols(a.in, a.n_look, a.carry_in, h, -2, PRE, sm.pre);
+          else backfill_symbols(a.in, a.n_look, a.carry_in, h, -2, PRE, sm.pre, a.min_qual != 0);
         }
       }
       __syncwarp();
@@ -450,7 +473,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
         }
       } else if(lane == 0) {
         if(a.format == 1) backfill_fastq(a.in, a.n_look, a.carry_in, (long long)n, PRE, cs);
-        else backfill_symbols(a.in, a.n_look, a.carry_in, (long long)n, -2, PRE, cs);
+        else backfill_symbols(a.in, a.n_look, a.carry_in, (long long)n, -2, PRE, cs, a.min_qual != 0);
       }
       if(lane == 0) a.carry_out->state = a.format == 1 ? (sm.total_state | (a.in[n - 1] == '\n' ? 4u : 0u)) : sm.total_state;
     }
@@ -571,8 +594,7 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
                                      lut32[4096 + (__funnelshift_r(klo, khi, 22) & 2047u)] ^ lut32[6144 + ((khi >> 1) & 2047u)];
                 uint32_t ext = 0;                 // position bits 32.. : one parity row each (two for a table of 2^34 slots)
 #pragma unroll
-                for(int r = 0; r < 6; ++r)
-                  if(r < (int)a.n_prow) ext |= (__popc((klo & (uint32_t)a.prow[r]) ^ (khi & (uint32_t)(a.prow[r] >> 32))) & 1u) << r;
+                for(int r = 0; r < NPR; ++r) ext |= (__popc((klo & (uint32_t)a.prow[r]) ^ (khi & (uint32_t)(a.prow[r] >> 32))) & 1u) << r;
                 P[jj] = (h32 >> f_rgb) | (ext << (32 - f_rgb));                       // region
                 R[jj] = ((h32 & f_relmask) << f_hb) | (uint32_t)(key[0] >> f_lsz);    // (position in the region, explicit key bits)
               }

@@ -72,10 +72,11 @@ __global__ void __launch_bounds__(256) nl_scan_kernel(const uint8_t* __restrict_
 }
 
 // state after the bytes [from, to) when entering them at a line start / with state s0
-__device__ __forceinline__ uint32_t line_start_state(const uint8_t* in, uint64_t from, uint64_t to, uint32_t s0) {
+// (keep_cr: -Q semantics, std::getline keeps a leading '\r': the line is then a sequence line)
+__device__ __forceinline__ uint32_t line_start_state(const uint8_t* in, uint64_t from, uint64_t to, uint32_t s0, bool keep_cr = false) {
   if(s0 != ST_L) return s0;
   uint64_t p = from;
-  while(p < to && in[p] == '\r') ++p;
+  while(!keep_cr && p < to && in[p] == '\r') ++p;
   if(p >= to) return ST_L;
   return in[p] == '>' ? ST_H : ST_S;
 }
@@ -87,7 +88,7 @@ __device__ __forceinline__ uint32_t line_start_state(const uint8_t* in, uint64_t
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) tile_state_kernel(const uint8_t* __restrict__ in, uint64_t n_tiles, uint32_t TILE,
                                                           const long long* __restrict__ nlA, const long long* __restrict__ nlB,
-                                                          const Carry* __restrict__ carry_in, uint8_t* __restrict__ tile_state) {
+                                                          const Carry* __restrict__ carry_in, uint8_t* __restrict__ tile_state, uint32_t keep_cr) {
   __shared__ long long part[1024];
   const uint64_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
   const uint64_t lo = min(n_tiles, per * threadIdx.x), hi = min(n_tiles, lo + per);
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(1024) tile_state_kernel(const uint8_t* __restr
     if(u + 1 < n_tiles) {
       const long long before = max(mu, nlA[u]);               // last newline before h_{u+1}
       const uint64_t h = (u + 1) * (uint64_t)TILE - HALO;
-      tile_state[u + 1] = (uint8_t)(before >= 0 ? line_start_state(in, (uint64_t)before + 1, h, ST_L)
-                                                : line_start_state(in, 0, h, cstate));
+      tile_state[u + 1] = (uint8_t)(before >= 0 ? line_start_state(in, (uint64_t)before + 1, h, ST_L, keep_cr != 0)
+                                                : line_start_state(in, 0, h, cstate, keep_cr != 0));
     }
     mu = max(mu, max(nlA[u], nlB[u]));
   }
@@ -192,6 +193,9 @@ struct CountArgs {
   uint32_t       n_prow;
   uint32_t       lut_bytes;     // bytes of hash tables to stage in shared memory
   uint32_t       format;        // 0 = FASTA, 1 = FASTQ (4-line records)
+  uint32_t       min_qual;      // -Q / --min-quality (0 = off): a base whose quality character is below this one resets the window;
+                                // whole_sequence_parser line semantics ('\r' is an ordinary, i.e. resetting, character)
+  uint64_t       n_back;        // bytes readable in front of `in` (the line a window starts in may begin there)
   uint64_t       prow[8];
   BloomDev       bloom;         // filter in front of the table (mode BLOOM_NONE: nothing)
 };
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(256) bloom_unpack_kernel(const uint8_t* __rest
 // missing leading entries are SYM_BREAK.  `line_nl` = position of the last '\n' before `end`
 // if known (>= -1), or -2 when unknown.
 __device__ void backfill_symbols(const uint8_t* in, uint64_t n, const Carry* cin, long long end, long long line_nl,
-                                 int need, uint8_t* out) {
+                                 int need, uint8_t* out, bool keep_cr = false) {
   for(int i = 0; i < need; ++i) out[i] = SYM_BREAK;
   int got = 0;
   long long cur_end = end;           // exclusive end of the line piece under inspection
@@ -243,7 +247,7 @@ __device__ void backfill_symbols(const uint8_t* in, uint64_t n, const Carry* cin
     long long fnc = ls;              // first non-'\r' byte of the line piece (only meaningful when s0 == L)
     uint32_t st = s0;
     if(s0 == ST_L) {
-      while(fnc < cur_end && in[fnc] == '\r') ++fnc;
+      while(!keep_cr && fnc < cur_end && in[fnc] == '\r') ++fnc;
       st = fnc >= cur_end ? ST_L : (in[fnc] == '>' ? ST_H : ST_S);
     }
     if(st == ST_H) return;           // a header precedes: window reset
@@ -252,7 +256,7 @@ __device__ void backfill_symbols(const uint8_t* in, uint64_t n, const Carry* cin
       for(long long p = cur_end - 1; p >= seq_from && got < need; --p) {
         uint32_t b = in[p];
         uint32_t sy;
-        if(b == '\r') { if(cr_dropped(in, (uint64_t)p, n)) continue; sy = SYM_BREAK; }
+        if(b == '\r') { if(!keep_cr && cr_dropped(in, (uint64_t)p, n)) continue; sy = SYM_BREAK; }
         else sy = base_symbol(b);
         if(sy == SYM_BREAK) return;
         out[need - 1 - got] = (uint8_t)sy; ++got;

@@ -79,25 +79,43 @@ __global__ void __launch_bounds__(1024, 1) restage_kernel(const RestageArgs ra, 
       st_cnt[p] = cnt | (fl << 16);
     }
   };
-  // the received chunks, flattened source after source; a trip of the loop = two chunks per CTA (512 x 16 bytes each)
+  // The received chunks, flattened source after source, in batches of NTH: every THREAD owns one chunk of the batch and a trip
+  // of the loop takes the same 16-byte piece (4 records) of all of them.  A chunk holds records of ONE global region -- `split`
+  // own regions --, so walking chunk after chunk would pour thousands of records into a handful of rings per trip; across
+  // 1024 chunks a trip's 4096 records spread over all the own regions the way K1's do.
   uint32_t total = 0;
   for(uint32_t s = 0; s < ra.n_src; ++s) total += ra.count[s];
   LocalStats ls = { 0, 0, 0, 0, 0 };
-  const uint32_t half = tid >> 9, piece = tid & 511u;
-  for(uint32_t base = blockIdx.x * 2u; base < total; base += gridDim.x * 2u) {      // (uniform over the CTA)
-    const uint32_t ci = base + half;
+  for(uint32_t base = blockIdx.x * NTH; base < total; base += gridDim.x * NTH) {      // (uniform over the CTA)
+    const uint32_t ci = base + tid;
+    uint32_t n = 0, own = 0;
+    const uint4* src = nullptr;
     if(ci < total) {
       uint32_t s = 0, rel = ci;
       while(rel >= ra.count[s]) { rel -= ra.count[s]; ++s; }
       const size_t at = (size_t)s * ra.seg_chunks + rel;
       const uint2 d = __ldg(&ra.recv_dir[at]);
-      if(piece * 4 < d.y) {
-        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(ra.recv_pool + at * CHUNK_BYTES) + piece);
+      n = d.y;
+      own = (d.x - ra.first_region) << ra.split_lg;              // first own region of that global region
+      src = reinterpret_cast<const uint4*>(ra.recv_pool + at * CHUNK_BYTES);
+    }
+    // (chunks are full but for the last of every (CTA, region) pair of the sender: most trips are needed by most threads)
+    uint32_t n_max = n;
+#pragma unroll
+    for(int o = 16; o; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+    __shared__ uint32_t s_nmax;
+    if(tid == 0) s_nmax = 0;
+    __syncthreads();
+    if((tid & 31) == 0) atomicMax(&s_nmax, n_max);
+    __syncthreads();
+    const uint32_t pieces = (s_nmax + 3) / 4;
+    for(uint32_t piece = 0; piece < pieces; ++piece) {
+      if(piece * 4 < n) {
+        const uint4 v = __ldg(src + piece);
         const uint32_t rec[4] = { v.x, v.y, v.z, v.w };
-        const uint32_t own = (d.x - ra.first_region) << ra.split_lg;            // first own region of that global region
 #pragma unroll
         for(uint32_t q = 0; q < 4; ++q) {
-          if(piece * 4 + q >= d.y) break;
+          if(piece * 4 + q >= n) break;
           const uint32_t pos = rec[q] >> hb, high = rec[q] & hmask;            // position inside the global region
           const uint32_t p = own + (pos >> fine_bits);
           const uint32_t r2 = ((pos & fine_mask) << hb) | high;
@@ -113,10 +131,10 @@ __global__ void __launch_bounds__(1024, 1) restage_kernel(const RestageArgs ra, 
           }
         }
       }
+      __syncthreads();
+      flush_rings(false);
+      __syncthreads();
     }
-    __syncthreads();
-    flush_rings(false);
-    __syncthreads();
   }
   flush_rings(true);
   __syncthreads();

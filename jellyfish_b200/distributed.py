@@ -104,6 +104,7 @@ class RecordExchange(object):
     def __init__(self, hc, world, rank, dev, send_gb=None):
         self.hc, self.world, self.rank, self.dev = hc, world, rank, dev
         self.ok = False
+        self.trace = None
         if not hc.shard_setup(0, 0, 0, 0, 0, 0):       # geometry probe: nothing is allocated for tables the record form does not cover
             return
         free, _ = torch.cuda.mem_get_info(dev)
@@ -160,17 +161,23 @@ class RecordExchange(object):
         rounds_all = max(int(t.item()), 1)        # every rank takes part in every exchange
         for ev in self.sent:
             ev.record(self.sb)
+        marks = []                                  # CUDA events around the stages of every round (self.trace)
         for r in range(rounds_all):
             bank = r & 1
             off = r * self.round_bytes
             ln = max(0, min(self.round_bytes, n - off))
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            marks.append(ev)
             with torch.cuda.stream(self.sa):
                 self.sa.wait_event(self.sent[bank])
+                ev[0].record(self.sa)
                 if ln or (r == 0 and begin) or (r == rounds_all - 1 and end):
                     src = fetch(off, ln, bank)
                     self.hc.shard_extract(src, ln, bank, begin and r == 0, end and off + ln >= n, stream=self.sa.cuda_stream)
+                ev[1].record(self.sa)
                 counts = self.hc.shard_pack(bank, stream=self.sa.cuda_stream)       # synchronises stream A
             with torch.cuda.stream(self.sb):
+                ev[2].record(self.sb)
                 sc = torch.tensor(counts, dtype=torch.int64, device=self.dev)
                 rc = torch.empty_like(sc)
                 dist.all_to_all_single(rc, sc)
@@ -182,9 +189,15 @@ class RecordExchange(object):
                 outs_d = [self.recv_dir[(s * self.arena) * 8:(s * self.arena + rcl[s]) * 8] for s in range(w)]
                 dist.all_to_all(outs_d, self._views(self.send_dir, bank, counts, 8))
                 self.sent[bank].record(self.sb)
+                ev[3].record(self.sb)
                 self.hc.shard_unpack(rcl, stream=self.sb.cuda_stream)
+                ev[4].record(self.sb)
         self.sa.synchronize()
         self.sb.synchronize()
+        t = [0.0, 0.0, 0.0]
+        for ev in marks:
+            t[0] += ev[0].elapsed_time(ev[1]); t[1] += ev[2].elapsed_time(ev[3]); t[2] += ev[3].elapsed_time(ev[4])
+        self.trace = {"rounds": rounds_all, "extract_ms": t[0], "exchange_ms": t[1], "restage_ms": t[2]}
 
 
 class ShardedCounter(object):

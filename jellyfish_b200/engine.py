@@ -59,7 +59,7 @@ class HashCounter(object):
     def __init__(self, size, val_len=7, k=None, canonical=False, reprobes=126, device=0,
                  shard_index=0, n_shards=1, allow_regrow=True, max_batch_bytes=0, matrix_skip=0,
                  pool_bytes=0, no_partition=False, part_min_mb=0, k2_mode=0, region_mb=0, bf_size=0, bf_fp=0.0,
-                 bloom_counter=False):
+                 bloom_counter=False, min_qual=0):
         if k is None:
             raise ValueError("k (mer length) is required")
         self._lib = L.load()
@@ -72,6 +72,7 @@ class HashCounter(object):
         p.pool_bytes, p.no_partition, p.part_min_mb = pool_bytes, int(bool(no_partition)), part_min_mb
         p.k2_mode, p.region_mb = k2_mode, region_mb
         p.bf_size, p.bf_fp, p.bloom_counter = bf_size, bf_fp, int(bool(bloom_counter))
+        p.min_qual = ord(min_qual) if isinstance(min_qual, str) else int(min_qual)
         rc = self._lib.jfgpu_create(C.byref(p), C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

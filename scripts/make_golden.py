@@ -14,12 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gen      # noqa: E402
 import jfutil   # noqa: E402
-from cases import BC_CASES, BF_CASES, BIG_CASES, CASES, EDGE_CASES, QUAL_CASES  # noqa: E402
+from cases import BC_CASES, BF_CASES, BIG_CASES, CASES, DISK_CASES, EDGE_CASES, QUAL_CASES  # noqa: E402
 
 os.environ["SOURCE_DATE_EPOCH"] = "0"
 with tempfile.TemporaryDirectory() as d:
   files = gen.make_all(d)
-  sets = ((BIG_CASES, "golden_big.json"),) if "--big" in sys.argv else ((CASES, "golden.json"), (QUAL_CASES, "golden_qual.json"), (BF_CASES, "golden_bf.json"), (EDGE_CASES, "golden_edge.json"))
+  sets = ((BIG_CASES, "golden_big.json"),) if "--big" in sys.argv else ((CASES, "golden.json"), (QUAL_CASES, "golden_qual.json"), (BF_CASES, "golden_bf.json"), (EDGE_CASES, "golden_edge.json"), (DISK_CASES, "golden_disk.json"))
   for cases, target in sets:
     out = {}
     for name, (args, ins) in sorted(cases.items()):

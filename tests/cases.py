@@ -147,3 +147,12 @@ EDGE_CASES = {
     "edge_k5_s2_p10":  (["-m", "5", "-s", "2", "-C", "-p", "10"], ["repeat.fa", "polya.fa"]),
     "edge_rep_c2":     (["-m", "21", "-s", "2k", "-C", "-c", "2"], ["repeat.fa", "polya.fa", "multi2.fa"]),
 }
+
+# --disk (count_main.cc:277,346-371; hash_counter.hpp:187-192): no size doubling -- a full table is written to an
+# intermediate file and zeroed, the files are merged at the end.  The merged database keeps the ORIGINAL size and matrix,
+# so its body does not depend on when the table filled up.
+DISK_CASES = {
+    "disk_k40":    (["-m", "40", "-s", "50k", "--disk", "-C"], ["plain.fa"]),
+    "disk_k21_LU": (["-m", "21", "-s", "100k", "--disk", "-C", "-L", "2"], ["plain.fa", "multi.fa", "plain.fa"]),
+    "disk_k17_c3": (["-m", "17", "-s", "30k", "--disk", "-c", "3", "--out-counter-len", "2"], ["multi.fa", "multi2.fa"]),
+}

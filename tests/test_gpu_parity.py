@@ -510,7 +510,8 @@ def test_record_exchange_on_one_gpu(name, world, built, workdir, inputs):
     arena = 2 * n_sm * max(1, 1024 // world) + 64
     shards, bufs = [], []
     for r in range(world):
-        hc = HashCounter(size, 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world, allow_regrow=False, part_min_mb=1, pool_bytes=256 << 20)
+        hc = HashCounter(size, int(args[args.index("-c") + 1]) if "-c" in args else 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world,
+                         allow_regrow=False, part_min_mb=1, pool_bytes=256 << 20)
         send = torch.empty(2 * world * arena * CHUNK, dtype=torch.uint8, device="cuda")
         send_dir = torch.empty(2 * world * arena * 8, dtype=torch.uint8, device="cuda")
         recv = torch.empty(world * arena * CHUNK, dtype=torch.uint8, device="cuda")
@@ -571,3 +572,128 @@ def test_record_exchange_on_one_gpu(name, world, built, workdir, inputs):
             assert jfutil.md5(one.dump_records()) == jfutil.md5(b) and len(b) > 0
             hdr = one.header()
             assert {x: hdr[x] for x in jfutil.SEMANTIC_KEYS} == jfutil.semantic(h)
+
+
+GOLDEN_QUAL = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_qual.json")))
+QUAL_MULTILINE = ("q_ml", "q_mixed")       # inputs with FASTQ records wrapped over several lines
+
+
+@pytest.mark.parametrize("name", sorted(n for n in __import__("cases").QUAL_CASES))
+def test_quality_filter_matches_reference_golden(name, built, workdir, inputs):
+    """-Q / --min-quality on the device (count_main.cc:234-256,326-329; whole_sequence_parser.hpp:137-193;
+    mer_qual_iterator.hpp:64-92): 4-line FASTQ records and FASTA, byte for byte against the reference's goldens.
+    FASTQ records wrapped over several lines are rejected loudly."""
+    import subprocess
+    from cases import QUAL_CASES
+    args, ins = QUAL_CASES[name]
+    if name in QUAL_MULTILINE:
+        r = subprocess.run([jfutil.OUR_JF, "count"] + jfutil.subst(list(args), inputs) + ["-o", os.path.join(workdir, "q.jf")] + [inputs[i] for i in ins],
+                           stderr=subprocess.PIPE)
+        assert r.returncode != 0 and b"Invalid fastq" in r.stderr
+        return
+    h, b = _count_cli(workdir, inputs, name, args, ins)
+    g = GOLDEN_QUAL[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"]
+    assert jfutil.md5(b) == g["body_md5"]
+
+
+def test_quality_filter_python_api_split_feeds(built, inputs):
+    """The same through the ctypes mirror with the file fed in arbitrary pieces: the engine keeps the incomplete last read of a
+    feed for the next one."""
+    from jellyfish_b200 import HashCounter
+    from cases import QUAL_CASES
+    args, ins = QUAL_CASES["q_fq"]
+    data = open(inputs[ins[0]], "rb").read()
+    g = GOLDEN_QUAL["q_fq"]
+    rng = random.Random(11)
+    with HashCounter(1000000, 7, k=21, canonical=True, min_qual="5", max_batch_bytes=70000) as hc:
+        off, first = 0, True
+        while off < len(data):
+            n = rng.choice([1, 7, 300, 5000, 44444, 200000])
+            hc.add_text(data[off:off + n], begin=first, end=off + n >= len(data))
+            first = False
+            off += n
+        hc.done()
+        assert jfutil.md5(hc.dump_records()) == g["body_md5"]
+
+
+def test_shard_records_of_a_2_to_37_slot_table_match_the_host_hash(built, inputs):
+    """The send side of the record exchange at the bench's 8-GPU geometry (global table 2^37 slots, five position bits
+    beyond the 32 the table-driven hash produces: parity rows): every record K1 files -- (global region, position in the
+    region, explicit key bits) -- against the position computed on the host from the hash matrix the header would carry."""
+    import numpy as np
+    import torch
+    from jellyfish_b200 import HashCounter, canonical_int, mer_to_int
+    from jellyfish_b200.distributed import CHUNK
+    world, k = 8, 21
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    arena = 2 * n_sm * (1024 // world) + 64
+    with HashCounter(1 << 37, 7, k=k, canonical=True, shard_index=3, n_shards=world, allow_regrow=False) as hc:
+        info = hc.info()
+        assert info["lsize"] == 37 and info["matrix_r"] == 37
+        send = torch.zeros(2 * world * arena * CHUNK, dtype=torch.uint8, device="cuda")
+        send_dir = torch.zeros(2 * world * arena * 8, dtype=torch.uint8, device="cuda")
+        recv = torch.zeros(world * arena * CHUNK, dtype=torch.uint8, device="cuda")
+        recv_dir = torch.zeros(world * arena * 8, dtype=torch.uint8, device="cuda")
+        assert hc.shard_setup(send.data_ptr(), send_dir.data_ptr(), arena, recv.data_ptr(), recv_dir.data_ptr(), arena)
+        data = open(inputs["plain.fa"], "rb").read()
+        buf = torch.zeros(len(data) + 256, dtype=torch.uint8, device="cuda")
+        buf[:len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        hc.shard_extract(buf.data_ptr(), len(data), 0)
+        counts = hc.shard_pack(0)
+        torch.cuda.synchronize()
+        got = []
+        for d in range(world):
+            c = counts[d]
+            dirs = send_dir[d * arena * 8:(d * arena + c) * 8].cpu().numpy().view(np.uint32).reshape(-1, 2)
+            chunks = send[d * arena * CHUNK:(d * arena + c) * CHUNK].cpu().numpy().view(np.uint32).reshape(-1, CHUNK // 4)
+            for (region, n), recs in zip(dirs, chunks):
+                assert region // (1024 // world) == d            # the chunk sits in its owner's arena
+                got.extend((int(region) << 32) | int(x) for x in recs[:n])
+        # the host's version: canonical 21-mers of the sequence, position = matrix x key, region = top 10 bits of the 37
+        seq = "".join(l.strip() for l in data.decode().splitlines() if not l.startswith(">"))
+        cols, c = info["matrix_columns"], info["matrix_c"]
+        hb = 2 * k - 37
+        want = []
+        for i in range(len(seq) - k + 1):
+            key = canonical_int(mer_to_int(seq[i:i + k]), k)
+            h, x, j = 0, key, 0
+            while x:
+                if x & 1:
+                    h ^= cols[c - 1 - j]
+                x >>= 1
+                j += 1
+            pos = h & ((1 << 37) - 1)
+            want.append(((pos >> 27) << 32) | ((pos & ((1 << 27) - 1)) << hb) | (key >> 37))
+        assert sorted(got) == sorted(want)
+
+
+@pytest.mark.parametrize("name", sorted(__import__("cases").DISK_CASES))
+def test_disk_spill_and_merge_matches_reference_golden(name, built, workdir, inputs):
+    """--disk: the table does not double; when it is full the engine calls the spill hook (jfgpu_set_spill), the driver writes
+    <output>0, <output>1, ... and merges them at the end (count_main.cc:346-371).  Header and body against the reference's."""
+    from cases import DISK_CASES
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_disk.json")))
+    args, ins = DISK_CASES[name]
+    db = os.path.join(workdir, "gpu_%s.jf" % name)
+    jfutil.run([jfutil.OUR_JF, "count"] + list(args) + ["-o", db] + [inputs[i] for i in ins])
+    h, b = jfutil.split_db(db)
+    g = golden[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"] and jfutil.md5(b) == g["body_md5"]
+    assert not os.path.exists(db + "0")              # intermediate files are unlinked after the merge
+    # --no-merge leaves the intermediate files, each a valid database of the same geometry
+    db2 = os.path.join(workdir, "gpu_%s_parts.jf" % name)
+    jfutil.run([jfutil.OUR_JF, "count"] + list(args) + ["--no-merge", "-o", db2] + [inputs[i] for i in ins])
+    parts = [db2 + str(i) for i in range(64) if os.path.exists(db2 + str(i))]
+    assert len(parts) >= 2
+    total = {}
+    for part in parts:
+        hp, bp = jfutil.split_db(part)
+        assert hp["size"] == h["size"] and hp["matrix1"] == h["matrix1"]
+        for key, v in jfutil.records(hp, bp):
+            total[key] = total.get(key, 0) + v
+    lo = int(args[args.index("-L") + 1]) if "-L" in args else 0
+    cap = (1 << (8 * h["counter_len"])) - 1
+    assert {key: min(v, cap) for key, v in total.items() if v >= lo} == dict(jfutil.records(h, b))

@@ -28,12 +28,26 @@ def test_library_exports_every_declared_symbol(built):
     assert b"sm_100a" in lib.jfgpu_version()
 
 
-def test_struct_layouts_match_header(built):
+def test_struct_layouts_match_header(built, tmp_path):
+    """Every field of every ctypes mirror sits where the C compiler puts the field of the same name in include/jfgpu.h."""
     from jellyfish_b200 import _lib
-    # sizes computed by hand from include/jfgpu.h
-    assert ctypes.sizeof(_lib.Params) == 4 * 2 + 8 + 4 * 8 + 8 + 8 + 8 + 6 * 8
-    assert ctypes.sizeof(_lib.Stats) == 11 * 8
-    assert ctypes.sizeof(_lib.TableInfo) == 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
+    structs = {"jfgpu_params": _lib.Params, "jfgpu_stats": _lib.Stats, "jfgpu_table_info": _lib.TableInfo,
+               "jfgpu_bloom_info": _lib.BloomInfo, "jfgpu_shard_buffers": _lib.ShardBuffers}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "jfgpu.h"', "int main(void) {"]
+    for cname, st in structs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f, _ in st._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(jfutil.ROOT, "include"), "-o", str(exe), str(src)])
+    want = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, st in structs.items():
+        assert ctypes.sizeof(st) == int(want[cname]), cname
+        for f, _ in st._fields_:
+            assert getattr(st, f).offset == int(want["%s.%s" % (cname, f)]), (cname, f)
 
 
 def test_reference_matrix_stream(built):
