@@ -70,7 +70,7 @@ typedef struct {
   double   bf_fp;          /* --bf-fp  (0 = the reference's default 0.01)              */
   uint64_t max_batch_bytes;/* device staging buffer size for jfgpu_feed (0 = default) */
   uint64_t pool_bytes;     /* HBM set aside for the k-mer record pool of the region-by-region
-                              insertion (0 = 60% of the free memory, at most 64 GB)      */
+                              insertion (0 = 70% of the free memory, at most 64 GB)      */
   uint32_t no_partition;   /* 1: always insert straight into the table (random HBM access) */
   uint32_t part_min_mb;    /* tables of at least this many MB are filled region by region
                               (0 = default 256); tests use 1 to exercise that path on small tables */

@@ -3,11 +3,14 @@
 // include/jellyfish/file_header.hpp:26-108):
 //   9 decimal digits = length of (terse JSON + padding), the JSON, then '\0' padding so
 //   that 9 + length is a multiple of "alignment" (8).  The record body starts there.
+// The byte layout is the format's; the code is this repository's own (framing as a pure string function, provenance
+// fields as separate helpers).
 #ifndef JFB_FILE_HEADER_HPP
 #define JFB_FILE_HEADER_HPP
 #include <unistd.h>
 #include <limits.h>
 #include <sys/utsname.h>
+#include <cstdlib>
 #include <ctime>
 #include <cctype>
 #include <iostream>
@@ -20,13 +23,61 @@
 namespace jfb {
 
 class file_header {
-  static const int MAX_HEADER_DIGITS = 9;
+  // Framing of the header: LEN_DIGITS decimal digits giving the number of bytes that follow up to the record body, the terse
+  // JSON text, zero bytes up to the next multiple of "alignment" (counted from the start of the file).
+  static constexpr size_t LEN_DIGITS = 9;
   json   root_;
   size_t offset_;
 
-  static void chomp(std::string& s) {
-    size_t found = s.find_last_not_of(" \t\f\v\n\r");
-    if(found != std::string::npos) s.erase(found + 1); else s.clear();
+  static std::string frame(const std::string& text, size_t align) {
+    size_t total = LEN_DIGITS + text.size();
+    if(align > 1 && total % align) total += align - total % align;
+    char digits[LEN_DIGITS + 8];
+    snprintf(digits, sizeof(digits), "%0*zu", (int)LEN_DIGITS, total - LEN_DIGITS);
+    std::string out(digits, LEN_DIGITS);
+    out += text;
+    out.resize(total, '\0');
+    return out;
+  }
+  // [*lo, *hi) = the JSON text inside a framed header at `p`; false when `p` does not start with one
+  static bool unframe(const char* p, size_t n, size_t* lo, size_t* hi, size_t* body) {
+    size_t d = 0; unsigned long len = 0;
+    while(d < LEN_DIGITS && d < n && p[d] >= '0' && p[d] <= '9') { len = len * 10 + (unsigned long)(p[d] - '0'); ++d; }
+    if(d >= n || p[d] != '{' || len < 2 || d + len > n) return false;
+    size_t e = d + len;
+    while(e > d && p[e - 1] == '\0') --e;
+    *lo = d; *hi = e; *body = LEN_DIGITS + len;
+    return true;
+  }
+  // provenance fields ("hostname", "pwd", "time", "exe_path"); SOURCE_DATE_EPOCH pins them for reproducible files
+  static std::string host_name(bool pinned) {
+    if(pinned) return "hostname";
+    struct utsname u;
+    return uname(&u) == 0 ? std::string(u.nodename) : std::string();
+  }
+  static std::string work_dir(bool pinned) {
+    if(pinned) return ".";
+    std::vector<char> buf(PATH_MAX + 1, '\0');
+    return getcwd(buf.data(), buf.size()) ? std::string(buf.data()) : std::string();
+  }
+  static std::string time_stamp(const char* epoch) {
+    time_t t = time(nullptr);
+    const char* text;
+    if(epoch) {
+      char* end = nullptr;
+      const long long v = strtoll(epoch, &end, 10);
+      if(end == epoch || *end != '\0') { std::cerr << "SOURCE_DATE_EPOCH is not an integer" << std::endl; exit(1); }
+      t = (time_t)v;
+      text = asctime(gmtime(&t));
+    } else text = ctime(&t);
+    std::string s(text ? text : "");
+    while(!s.empty() && isspace((unsigned char)s.back())) s.pop_back();
+    return s;
+  }
+  static std::string exe_path() {
+    std::vector<char> buf(PATH_MAX + 1, '\0');
+    const ssize_t l = readlink("/proc/self/exe", buf.data(), buf.size() - 1);
+    return l > 0 ? std::string(buf.data(), (size_t)l) : std::string();
   }
 public:
   file_header() : root_(json::object()), offset_(0) { root_["alignment"] = json(8); }
@@ -36,30 +87,13 @@ public:
   size_t offset() const { return offset_; }
   int alignment() const { int a = (int)root_.at("alignment").as_i64(0); return a > 0 ? a : 0; }
 
-  // -- generic part ---------------------------------------------------------
+  // -- generic part (the keys generic_file_header.hpp:113-152 records) ----------------------
   void fill_standard() {
-    const char* sde = getenv("SOURCE_DATE_EPOCH");
-    // hostname
-    if(sde) root_["hostname"] = json("hostname");
-    else { struct utsname u; root_["hostname"] = json(uname(&u) == -1 ? "" : u.nodename); }
-    // pwd
-    if(sde) root_["pwd"] = json(".");
-    else { char path[PATH_MAX + 1]; if(!getcwd(path, sizeof(path))) path[0] = '\0'; root_["pwd"] = json(path); }
-    // time
-    time_t t = time(0);
-    std::string ts;
-    if(sde) {
-      std::istringstream iss(sde);
-      iss >> t;
-      if(iss.fail() || !iss.eof()) { std::cerr << "Error: Cannot parse SOURCE_DATE_EPOCH as integer\n"; exit(27); }
-      ts = asctime(gmtime(&t));
-    } else ts = ctime(&t);
-    chomp(ts);
-    root_["time"] = json(ts);
-    // exe_path
-    char path[PATH_MAX + 1];
-    ssize_t l = readlink("/proc/self/exe", path, sizeof(path));
-    root_["exe_path"] = json(l == -1 ? std::string() : std::string(path, l));
+    const char* epoch = getenv("SOURCE_DATE_EPOCH");
+    root_["hostname"] = json(host_name(epoch != nullptr));
+    root_["pwd"] = json(work_dir(epoch != nullptr));
+    root_["time"] = json(time_stamp(epoch));
+    root_["exe_path"] = json(exe_path());
   }
   void set_cmdline(int argc, char* argv[]) {
     json a = json::array();
@@ -74,46 +108,29 @@ public:
   }
 
   void write(std::ostream& os) {
-    std::string h = root_.dump();
-    size_t hlen = h.size();
-    int align = alignment(), padding = 0;
-    if(align > 0) {
-      padding = (MAX_HEADER_DIGITS + h.size()) % align;
-      if(padding) hlen += align - padding;
-    }
-    char len[16];
-    snprintf(len, sizeof(len), "%09lu", (unsigned long)hlen);
-    os.write(len, MAX_HEADER_DIGITS);
-    os.write(h.data(), h.size());
-    offset_ = MAX_HEADER_DIGITS + hlen;
-    if(padding) { std::string pad(align - padding, '\0'); os.write(pad.data(), pad.size()); }
+    const std::string framed = frame(root_.dump(), (size_t)alignment());
+    os.write(framed.data(), (std::streamsize)framed.size());
+    offset_ = framed.size();
   }
 
-  bool read(std::istream& is) {
-    std::string len;
-    for(int i = 0; i < MAX_HEADER_DIGITS && isdigit(is.peek()); ++i) len += (char)is.get();
-    if(is.peek() != '{') return false;
-    unsigned long hlen = strtoul(len.c_str(), 0, 10);
-    if(hlen < 2) return false;
-    offset_ = MAX_HEADER_DIGITS + hlen;
-    std::vector<char> buf(hlen);
-    is.read(buf.data(), hlen);
-    if(!is.good()) return false;
-    const char* end = buf.data() + hlen;
-    while(end > buf.data() && *(end - 1) == '\0') --end;
-    return json::parse(buf.data(), end, root_);
-  }
   // parse from memory (mmap'd database); returns false on failure
   bool read(const char* data, size_t size) {
-    size_t i = 0; std::string len;
-    for(; i < (size_t)MAX_HEADER_DIGITS && i < size && isdigit((unsigned char)data[i]); ++i) len += data[i];
-    if(i >= size || data[i] != '{') return false;
-    unsigned long hlen = strtoul(len.c_str(), 0, 10);
-    if(hlen < 2 || i + hlen > size) return false;
-    offset_ = MAX_HEADER_DIGITS + hlen;
-    const char* end = data + i + hlen;
-    while(end > data + i && *(end - 1) == '\0') --end;
-    return json::parse(data + i, end, root_);
+    size_t lo = 0, hi = 0, body = 0;
+    if(!unframe(data, size, &lo, &hi, &body)) return false;
+    offset_ = body;
+    return json::parse(data + lo, data + hi, root_);
+  }
+  bool read(std::istream& is) {
+    std::string buf(LEN_DIGITS, '\0');
+    is.read(&buf[0], (std::streamsize)LEN_DIGITS);
+    if((size_t)is.gcount() != LEN_DIGITS) return false;
+    size_t d = 0; unsigned long len = 0;
+    while(d < LEN_DIGITS && buf[d] >= '0' && buf[d] <= '9') { len = len * 10 + (unsigned long)(buf[d] - '0'); ++d; }
+    if(d != LEN_DIGITS || len < 2) return false;
+    buf.resize(LEN_DIGITS + len);
+    is.read(&buf[LEN_DIGITS], (std::streamsize)len);
+    if((size_t)is.gcount() != len) return false;
+    return read(buf.data(), buf.size());
   }
 
   // -- table description ------------------------------------------------------

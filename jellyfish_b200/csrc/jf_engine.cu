@@ -379,7 +379,7 @@ int part_alloc(jfgpu_engine* e) {
   if(ps.pool.p) return JFGPU_OK;
   size_t free_b = 0, total_b = 0;
   CUDA_OK(e, cudaMemGetInfo(&free_b, &total_b));
-  size_t want = e->p.pool_bytes ? (size_t)e->p.pool_bytes : std::min<size_t>((size_t)(free_b * 0.6), (size_t)64 << 30);
+  size_t want = e->p.pool_bytes ? (size_t)e->p.pool_bytes : std::min<size_t>((size_t)(free_b * 0.7), (size_t)64 << 30);
   const size_t floor_b = (size_t)e->n_sm * ps.P * CHUNK_BYTES * 2;        // every CTA keeps one open chunk per region
   if(want < floor_b) want = floor_b;
   // one arena per CTA of the staging kernels (persistent, one CTA per SM)
@@ -1540,7 +1540,7 @@ int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
   if(total == 0) return JFGPU_OK;
   // room in the CTAs' arenas of the local pool (as in run_batch): drain first when the bound says they could fill up
   const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
-  const uint64_t per_cta = ((total + 1023) / 1024 + e->n_sm - 1) / e->n_sm * 1024;     // (a CTA takes batches of 1024 chunks)
+  const uint64_t per_cta = (total + e->n_sm - 1) / e->n_sm + 1;                  // (chunk j goes to CTA j mod grid)
   const uint64_t need = per_cta * (CHUNK_BYTES / 4) / usable + 2;
   if(ps.bound_chunks + need > ps.arena_chunks) { rc = part_drain(e, st); if(rc) return rc; }
   if(ps.bound_chunks + need > ps.arena_chunks) return fail(e, JFGPU_ERR_NOMEM, "record pool smaller than one exchange round");
@@ -1556,7 +1556,7 @@ int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
   PartDev pd = part_dev(e);
   const size_t smem = (size_t)RING_P * 8 + (size_t)RING_P * RING * 4;
   cudaFuncSetAttribute(restage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = (int)std::min<uint64_t>((total + 1023) / 1024, (uint64_t)e->n_sm);
+  const int grid = e->n_sm;
   restage_kernel<1><<<grid, 1024, smem, st>>>(ra, pd); JF_LAUNCHED();
   CUDA_OK(e, cudaGetLastError());
   return JFGPU_OK;

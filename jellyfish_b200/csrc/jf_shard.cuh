@@ -79,15 +79,17 @@ __global__ void __launch_bounds__(1024, 1) restage_kernel(const RestageArgs ra, 
       st_cnt[p] = cnt | (fl << 16);
     }
   };
-  // The received chunks, flattened source after source, in batches of NTH: every THREAD owns one chunk of the batch and a trip
+  // The received chunks, flattened source after source, in batches of NTH per CTA: every THREAD owns one chunk of the batch and a trip
   // of the loop takes the same 16-byte piece (4 records) of all of them.  A chunk holds records of ONE global region -- `split`
   // own regions --, so walking chunk after chunk would pour thousands of records into a handful of rings per trip; across
   // 1024 chunks a trip's 4096 records spread over all the own regions the way K1's do.
   uint32_t total = 0;
   for(uint32_t s = 0; s < ra.n_src; ++s) total += ra.count[s];
   LocalStats ls = { 0, 0, 0, 0, 0 };
-  for(uint32_t base = blockIdx.x * NTH; base < total; base += gridDim.x * NTH) {      // (uniform over the CTA)
-    const uint32_t ci = base + tid;
+  // (chunk j of the list belongs to CTA j mod grid: every CTA gets the same number of chunks to within one, and the
+  // chunks of a batch lie far apart in the list)
+  for(uint32_t base = 0; base * gridDim.x + blockIdx.x < total; base += NTH) {      // (uniform over the CTA)
+    const uint32_t ci = (base + tid) * gridDim.x + blockIdx.x;
     uint32_t n = 0, own = 0;
     const uint4* src = nullptr;
     if(ci < total) {
@@ -108,14 +110,21 @@ __global__ void __launch_bounds__(1024, 1) restage_kernel(const RestageArgs ra, 
     __syncthreads();
     if((tid & 31) == 0) atomicMax(&s_nmax, n_max);
     __syncthreads();
-    const uint32_t pieces = (s_nmax + 3) / 4;
-    for(uint32_t piece = 0; piece < pieces; ++piece) {
-      if(piece * 4 < n) {
-        const uint4 v = __ldg(src + piece);
-        const uint32_t rec[4] = { v.x, v.y, v.z, v.w };
+    // two pieces (8 records) per thread and trip: half the ring passes; the pieces of the next trip are already on their way
+    const uint32_t trips = (s_nmax + 7) / 8;
+    uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
+    if(0 < n) nx0 = __ldg(src);
+    if(4 < n) nx1 = __ldg(src + 1);
+    for(uint32_t trip = 0; trip < trips; ++trip) {
+      const uint4 v0 = nx0, v1 = nx1;
+      const uint32_t r0 = trip * 8;
+      if(r0 + 8 < n) nx0 = __ldg(src + 2 * trip + 2);
+      if(r0 + 12 < n) nx1 = __ldg(src + 2 * trip + 3);
+      if(r0 < n) {
+        const uint32_t rec[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
 #pragma unroll
-        for(uint32_t q = 0; q < 4; ++q) {
-          if(piece * 4 + q >= n) break;
+        for(uint32_t q = 0; q < 8; ++q) {
+          if(r0 + q >= n) break;
           const uint32_t pos = rec[q] >> hb, high = rec[q] & hmask;            // position inside the global region
           const uint32_t p = own + (pos >> fine_bits);
           const uint32_t r2 = ((pos & fine_mask) << hb) | high;

@@ -126,6 +126,8 @@ class RecordExchange(object):
         self.round_bytes = hc.shard_round_bytes()
         if self.round_bytes < (1 << 20):
             return
+        # the chunk counts travel on a communicator of their own, so that they never queue behind the chunks of the round before
+        self.pg_counts = dist.new_group(backend="nccl") if dist.get_backend() == "nccl" else None
         self.sa = torch.cuda.Stream(device=dev)       # extraction
         self.sb = torch.cuda.Stream(device=dev)       # exchange + restaging
         self.sent = [torch.cuda.Event(), torch.cuda.Event()]     # bank b has been sent (may be overwritten)
@@ -176,14 +178,14 @@ class RecordExchange(object):
                     self.hc.shard_extract(src, ln, bank, begin and r == 0, end and off + ln >= n, stream=self.sa.cuda_stream)
                 ev[1].record(self.sa)
                 counts = self.hc.shard_pack(bank, stream=self.sa.cuda_stream)       # synchronises stream A
-            with torch.cuda.stream(self.sb):
-                ev[2].record(self.sb)
                 sc = torch.tensor(counts, dtype=torch.int64, device=self.dev)
                 rc = torch.empty_like(sc)
-                dist.all_to_all_single(rc, sc)
-                rcl = rc.tolist()
+                dist.all_to_all_single(rc, sc, group=self.pg_counts)
+                rcl = rc.tolist()                  # (waits for this tiny exchange only: stream B keeps working on the round before)
                 if max(rcl) > self.arena:
                     raise RuntimeError("route bucket capacity exceeded (%d chunks > %d)" % (max(rcl), self.arena))
+            with torch.cuda.stream(self.sb):
+                ev[2].record(self.sb)
                 outs = [self.recv[(s * self.arena) * CHUNK:(s * self.arena + rcl[s]) * CHUNK] for s in range(w)]
                 dist.all_to_all(outs, self._views(self.send, bank, counts, CHUNK))
                 outs_d = [self.recv_dir[(s * self.arena) * 8:(s * self.arena + rcl[s]) * 8] for s in range(w)]

@@ -43,7 +43,7 @@ def test_sharded_count_matches_golden(name, world, built, workdir, inputs):
     out = os.path.join(workdir, "multi_%s_%d" % (name, world))
     cfg = {"size": size, "k": k, "canonical": "-C" in args, "files": [inputs[i] for i in ins], "out": out, "batch_bytes": 300000}
     if name not in CASES:
-        cfg["engine"] = {"part_min_mb": 1, "pool_bytes": 256 << 20}      # small shards filled region by region
+        cfg["engine"] = {"part_min_mb": 1, "pool_bytes": 4 << 30}      # small shards filled region by region
     worker = os.path.join(os.path.dirname(__file__), "multi_worker.py")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", "29641", worker, json.dumps(cfg)],

@@ -511,7 +511,7 @@ def test_record_exchange_on_one_gpu(name, world, built, workdir, inputs):
     shards, bufs = [], []
     for r in range(world):
         hc = HashCounter(size, int(args[args.index("-c") + 1]) if "-c" in args else 7, k=k, canonical="-C" in args, shard_index=r, n_shards=world,
-                         allow_regrow=False, part_min_mb=1, pool_bytes=256 << 20)
+                         allow_regrow=False, part_min_mb=1, pool_bytes=4 << 30)      # (an arena must take a batch of 1024 chunks)
         send = torch.empty(2 * world * arena * CHUNK, dtype=torch.uint8, device="cuda")
         send_dir = torch.empty(2 * world * arena * 8, dtype=torch.uint8, device="cuda")
         recv = torch.empty(world * arena * CHUNK, dtype=torch.uint8, device="cuda")
