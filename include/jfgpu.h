@@ -189,7 +189,9 @@ int  jfgpu_shard_setup(jfgpu_handle h, const jfgpu_shard_buffers* buffers);   /*
 uint64_t jfgpu_shard_round_bytes(jfgpu_handle h);   /* text bytes one round (one bank) takes at most */
 int  jfgpu_shard_extract(jfgpu_handle h, const void* dev_bytes, size_t n, uint32_t flags, uint32_t bank, void* stream);
 int  jfgpu_shard_pack(jfgpu_handle h, uint32_t bank, uint64_t* chunks_per_dest /* [n_shards], host */, void* stream);
-int  jfgpu_shard_unpack(jfgpu_handle h, const uint64_t* chunks_per_src /* [n_shards], host */, void* stream);
+int  jfgpu_shard_unpack(jfgpu_handle h, const uint64_t* chunks_per_src /* [n_shards], host */, uint32_t self_bank, void* stream);
+/*   self_bank 0/1: this shard's own chunks were not exchanged -- they are read from its arena of that send bank (which must
+ *   stay untouched until `stream` has passed this call); any other value: they sit in the receive pool like everyone's. */
 
 /* -- mer_counter_base's operation (sub_commands/count_main.cc:133,152-184): JFGPU_OP_COUNT adds
  *    (hash_counter::add), JFGPU_OP_PRIME inserts keys with count 0 (hash_counter::set, the first pass

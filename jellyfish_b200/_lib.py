@@ -148,7 +148,7 @@ def load():
     lib.jfgpu_shard_extract.restype = C.c_int
     lib.jfgpu_shard_pack.argtypes = [H, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p]
     lib.jfgpu_shard_pack.restype = C.c_int
-    lib.jfgpu_shard_unpack.argtypes = [H, C.POINTER(C.c_uint64), C.c_void_p]
+    lib.jfgpu_shard_unpack.argtypes = [H, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p]
     lib.jfgpu_shard_unpack.restype = C.c_int
     _lib = lib
     return lib

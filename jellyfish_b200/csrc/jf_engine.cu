@@ -1526,7 +1526,7 @@ int jfgpu_shard_pack(jfgpu_handle e, uint32_t bank, uint64_t* counts, void* stre
   return JFGPU_OK;
 }
 
-int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
+int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, uint32_t self_bank, void* stream) {
   if(!e || !counts) return JFGPU_ERR_ARG;
   if(!e->sh.on) return fail(e, JFGPU_ERR_STATE, "jfgpu_shard_setup has not been called");
   cudaSetDevice(e->device);
@@ -1536,7 +1536,7 @@ int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
   int rc = part_alloc(e);
   if(rc) return rc;
   uint64_t total = 0;
-  for(uint32_t s = 0; s < G; ++s) { if(counts[s] > e->sh.seg_chunks) return fail(e, JFGPU_ERR_ARG, "more chunks than a receive segment holds"); total += counts[s]; }
+  for(uint32_t s = 0; s < G; ++s) { if(counts[s] > std::max(e->sh.seg_chunks, e->sh.arena_chunks)) return fail(e, JFGPU_ERR_ARG, "more chunks than a receive segment holds"); total += counts[s]; }
   if(total == 0) return JFGPU_OK;
   // room in the CTAs' arenas of the local pool (as in run_batch): drain first when the bound says they could fill up
   const uint64_t usable = CHUNK_BYTES / ps.rec_bytes - ps.margin;
@@ -1553,6 +1553,10 @@ int jfgpu_shard_unpack(jfgpu_handle e, const uint64_t* counts, void* stream) {
   for(uint32_t s = 0; s < G; ++s) ra.count[s] = (uint32_t)counts[s];
   ra.first_region = e->p.shard_index * e->sh.own_regions; ra.split_lg = e->sh.split_lg; ra.sbits = e->sh.sbits;
   ra.inv_lut = e->tab.inv_lut.as<uint64_t>(); ra.nbytes = e->nbytes;
+  if(self_bank <= 1) {             // this shard's own chunks stay in its arena of that send bank
+    const size_t a0 = ((size_t)self_bank * G + e->p.shard_index) * e->sh.arena_chunks;
+    ra.self_pool = e->sh.send_pool + a0 * CHUNK_BYTES; ra.self_dir = e->sh.send_dir + a0; ra.self_src = e->p.shard_index;
+  }
   PartDev pd = part_dev(e);
   const size_t smem = (size_t)RING_P * 8 + (size_t)RING_P * RING * 4;
   cudaFuncSetAttribute(restage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -22,6 +22,9 @@ struct RestageArgs {
   uint32_t first_region;         // first global region this shard owns
   uint32_t split_lg;             // log2(own regions per global region)
   uint32_t sbits;                // log2(slots of a global region)
+  const uint8_t* self_pool;      // when not NULL: this shard's own chunks are read where K1 left them (its arena of the send
+  const uint2* self_dir;         // bank) instead of travelling through the receive pool; self_src = this shard's rank
+  uint32_t self_src, pad0;
   const uint64_t* inv_lut;       // (failure path: the key of a record that found no slot)
   uint32_t nbytes;
 };
@@ -95,11 +98,12 @@ __global__ void __launch_bounds__(1024, 1) restage_kernel(const RestageArgs ra, 
     if(ci < total) {
       uint32_t s = 0, rel = ci;
       while(rel >= ra.count[s]) { rel -= ra.count[s]; ++s; }
-      const size_t at = (size_t)s * ra.seg_chunks + rel;
-      const uint2 d = __ldg(&ra.recv_dir[at]);
+      const bool from_self = ra.self_pool != nullptr && s == ra.self_src;
+      const size_t at = from_self ? (size_t)rel : (size_t)s * ra.seg_chunks + rel;
+      const uint2 d = __ldg(from_self ? &ra.self_dir[at] : &ra.recv_dir[at]);
       n = d.y;
       own = (d.x - ra.first_region) << ra.split_lg;              // first own region of that global region
-      src = reinterpret_cast<const uint4*>(ra.recv_pool + at * CHUNK_BYTES);
+      src = reinterpret_cast<const uint4*>((from_self ? ra.self_pool : ra.recv_pool) + at * CHUNK_BYTES);
     }
     // (chunks are full but for the last of every (CTA, region) pair of the sender: most trips are needed by most threads)
     uint32_t n_max = n;

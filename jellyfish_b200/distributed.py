@@ -186,14 +186,17 @@ class RecordExchange(object):
                     raise RuntimeError("route bucket capacity exceeded (%d chunks > %d)" % (max(rcl), self.arena))
             with torch.cuda.stream(self.sb):
                 ev[2].record(self.sb)
-                outs = [self.recv[(s * self.arena) * CHUNK:(s * self.arena + rcl[s]) * CHUNK] for s in range(w)]
-                dist.all_to_all(outs, self._views(self.send, bank, counts, CHUNK))
-                outs_d = [self.recv_dir[(s * self.arena) * 8:(s * self.arena + rcl[s]) * 8] for s in range(w)]
-                dist.all_to_all(outs_d, self._views(self.send_dir, bank, counts, 8))
-                self.sent[bank].record(self.sb)
+                # this rank's own chunks do not travel: the restaging reads them where K1 left them
+                me = self.rank
+                outs = [self.recv[(s * self.arena) * CHUNK:(s * self.arena + (0 if s == me else rcl[s])) * CHUNK] for s in range(w)]
+                ins = self._views(self.send, bank, [0 if d == me else c for d, c in enumerate(counts)], CHUNK)
+                dist.all_to_all(outs, ins)
+                outs_d = [self.recv_dir[(s * self.arena) * 8:(s * self.arena + (0 if s == me else rcl[s])) * 8] for s in range(w)]
+                dist.all_to_all(outs_d, self._views(self.send_dir, bank, [0 if d == me else c for d, c in enumerate(counts)], 8))
                 ev[3].record(self.sb)
-                self.hc.shard_unpack(rcl, stream=self.sb.cuda_stream)
+                self.hc.shard_unpack(rcl, self_bank=bank, stream=self.sb.cuda_stream)
                 ev[4].record(self.sb)
+                self.sent[bank].record(self.sb)      # (the bank is free again once its own chunks have been restaged)
         self.sa.synchronize()
         self.sb.synchronize()
         t = [0.0, 0.0, 0.0]

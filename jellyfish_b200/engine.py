@@ -183,9 +183,11 @@ class HashCounter(object):
         self._check(self._lib.jfgpu_shard_pack(self._h, bank, counts, C.c_void_p(stream or 0)))
         return list(counts)
 
-    def shard_unpack(self, counts, stream=None):
+    def shard_unpack(self, counts, self_bank=None, stream=None):
+        """counts: chunks received from every shard.  self_bank 0/1: this shard's own chunks are read from that send bank
+        instead of the receive pool (they were not exchanged)."""
         arr = (C.c_uint64 * len(counts))(*counts)
-        self._check(self._lib.jfgpu_shard_unpack(self._h, arr, C.c_void_p(stream or 0)))
+        self._check(self._lib.jfgpu_shard_unpack(self._h, arr, 0xFFFFFFFF if self_bank is None else self_bank, C.c_void_p(stream or 0)))
 
     OP_COUNT, OP_PRIME, OP_UPDATE = 0, 1, 2
 
