@@ -5,10 +5,6 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/r2p_gpu.txt 2>&1
 timeout 1200 python -m pytest tests -q -m gpu --tb=short > gpurun_out/r2p_pytest.txt 2>&1
 timeout 600 python bench.py --steps 4 --warmup 3 --dump > gpurun_out/r2p_bench_k21.txt 2>&1
-timeout 300 python bench.py --config k31 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2p_bench_k31.txt 2>&1
-timeout 300 python bench.py --config k63 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2p_bench_k63.txt 2>&1
-timeout 400 python bench.py --config bf --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2p_bench_bf.txt 2>&1
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2p_bench_reference.txt 2>&1
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2p_traffic.csv $B > gpurun_out/ncu_launch.log 2>&1
 cap() {  # name regex skip
@@ -18,5 +14,8 @@ cap() {  # name regex skip
 }
 cap r2p_k1 extract_kernel 12
 cap r2p_insert win_insert2 20
-cap r2p_scatter win_scatter 20
+timeout 300 python bench.py --config k31 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2p_bench_k31.txt 2>&1
+timeout 300 python bench.py --config k63 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2p_bench_k63.txt 2>&1
+timeout 400 python bench.py --config bf --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2p_bench_bf.txt 2>&1
+timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2p_bench_reference.txt 2>&1
 du -sm gpurun_out; tail -12 gpurun_out/r2p_pytest.txt; for f in k21 k31 k63 bf reference; do echo == $f; tail -c 400 gpurun_out/r2p_bench_$f.txt; echo; done
