@@ -435,7 +435,7 @@ def main():
             st2 = one_step_host()
         barrier()
         wall2 = time.perf_counter() - t0
-        assert st2["kmers"] == kmers_per_step
+        assert st2["kmers"] == kmers_per_step and (world > 1 or st2["distinct"] == st["distinct"]), "the host feed counted something else"
         t = torch.tensor([wall2], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

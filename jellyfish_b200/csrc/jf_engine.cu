@@ -993,9 +993,7 @@ int spill_table(jfgpu_engine* e, uint64_t n_failed) {
   CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_keys.p, 0, e->tab.ovf_size * 8, e->cs));
   CUDA_OK(e, cudaMemsetAsync(e->tab.ovf_vals.p, 0, e->tab.ovf_size * 8, e->cs));
   unsigned long long* st = e->stats.as<unsigned long long>();
-  unsigned long long inserted_before = 0;
-  CUDA_OK(e, cudaMemcpyAsync(&inserted_before, st + STAT_INSERTED, 8, cudaMemcpyDeviceToHost, e->cs));
-  CUDA_OK(e, cudaMemsetAsync(st + STAT_DISTINCT, 0, 8, e->cs));
+  CUDA_OK(e, cudaMemsetAsync(st + STAT_DISTINCT, 0, 8, e->cs));       // (statistics of the table restart; STAT_INSERTED counts occurrences and goes on)
   CUDA_OK(e, cudaMemsetAsync(st + STAT_REPROBES, 0, 8, e->cs));
   CUDA_OK(e, cudaMemsetAsync(st + STAT_OVERFLOWED, 0, 8, e->cs));
   CUDA_OK(e, cudaMemsetAsync(st + STAT_FAILED, 0, 8, e->cs));
@@ -1010,9 +1008,7 @@ int spill_table(jfgpu_engine* e, uint64_t n_failed) {
   int rc = insert_keys_into(e, e->tab, e->fail_keys[old_fail].as<uint64_t>(), e->fail_counts[old_fail].as<uint64_t>(), n_failed, e->cs);
   e->op = op;
   if(rc) return rc;
-  // the failed keys were counted as occurrences when they failed? no: they are counted now, once
-  CUDA_OK(e, cudaStreamSynchronize(e->cs));
-  (void)inserted_before;
+  CUDA_OK(e, cudaStreamSynchronize(e->cs));       // (the keys that had found no slot are counted as inserted now, once)
   e->spills++;
   return JFGPU_OK;
 }

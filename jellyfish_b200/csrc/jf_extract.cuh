@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(NTH, (NTH == 512 ? 2 : 1)) extract_kernel(cons
                 }
               }
               s = base_symbol(b);
-              if(have_q && (signed char)a.in[g + qoff] < (signed char)a.min_qual) s = SYM_BREAK;
+              if(have_q) {                             // (a quality line shorter than its read is reported by the thread at the line start;
+                const long long qp = g + qoff;          //  nobody reads past the text for it)
+                if(qp >= (long long)a.n_look || (signed char)a.in[qp] < (signed char)a.min_qual) s = SYM_BREAK;
+              }
             } else if(ty == 1) {
               if(b == '\r') { if(!cr_dropped(a.in, (uint64_t)(g0 + i), a.n_look)) s = SYM_BREAK; }
               else s = base_symbol(b);
