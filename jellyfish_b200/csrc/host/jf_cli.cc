@@ -34,6 +34,7 @@
 
 #include "jfgpu.h"
 #include "jf_file_header.hpp"
+#include "jf_inputs.hpp"
 
 namespace {
 
@@ -168,6 +169,7 @@ struct count_args {
   int device = 0;
   std::vector<const char*> files;
   std::vector<const char*> if_files;
+  jfb::generator_spec gen;             // -g / -G / -S
 };
 
 struct sink_ctx { FILE* f; bool ok; bool text; unsigned k, key_bytes, rec; };
@@ -191,69 +193,49 @@ int file_sink(void* ctx, const void* recs, size_t n) {
   return 0;
 }
 
-// ---- stream files through an engine: a reader thread fills pinned buffers, the caller's thread feeds them ----
-void stream_files(jfgpu_handle h, const std::vector<const char*>& file_list) {
-  const size_t BUF = (size_t)64 << 20;
-  struct chunk { char* data; size_t n; uint32_t flags; bool last; std::string error; };
-  const int NBUF = 3;
-  std::vector<char*> bufs(NBUF);
-  for(int i = 0; i < NBUF; ++i) { bufs[i] = (char*)jfgpu_host_alloc(BUF); if(!bufs[i]) die("pinned host allocation failed"); }
-  std::mutex mu; std::condition_variable cv;
-  std::queue<chunk> ready; std::queue<char*> freeb;
-  for(int i = 0; i < NBUF; ++i) freeb.push(bufs[i]);
-  std::thread reader([&] {
-    auto get_buf = [&]() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !freeb.empty(); }); char* b = freeb.front(); freeb.pop(); return b; };
-    auto put = [&](chunk c) { std::unique_lock<std::mutex> l(mu); ready.push(c); cv.notify_all(); };
-    for(size_t fi = 0; fi < file_list.size(); ++fi) {
-      int fd = ::open(file_list[fi], O_RDONLY);
-      if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + file_list[fi] + "'"}); return; }
-      bool first = true, eof = false;
-      char* cur = get_buf();
-      size_t have = 0;
-      // read one chunk ahead so that the last one can carry FILE_END
-      std::string io_error;
-      auto fill = [&](char* b) -> size_t {
-        size_t n = 0;
-        while(n < BUF) {
-          ssize_t r = ::read(fd, b + n, BUF - n);
-          if(r < 0 && errno == EINTR) continue;
-          if(r < 0) { io_error = std::string("Error reading file '") + file_list[fi] + "': " + strerror(errno); eof = true; break; }   // never a silent truncation
-          if(r == 0) { eof = true; break; }
-          n += r;
-        }
-        return n;
-      };
-      have = fill(cur);
-      while(true) {
-        char* nxt = nullptr; size_t nn = 0;
-        if(!eof) { nxt = get_buf(); nn = fill(nxt); }
-        if(!io_error.empty()) { ::close(fd); put(chunk{nullptr, 0, 0, true, io_error}); return; }
-        bool last_of_file = eof && nn == 0;
-        uint32_t fl = (first ? JFGPU_FILE_BEGIN : 0) | (last_of_file ? JFGPU_FILE_END : 0);
-        put(chunk{cur, have, fl, false, ""});
-        first = false;
-        if(last_of_file) { if(nxt) { std::unique_lock<std::mutex> l(mu); freeb.push(nxt); } break; }
-        cur = nxt; have = nn;
-      }
-      ::close(fd);
-    }
-    put(chunk{nullptr, 0, 0, true, ""});
-  });
-  std::string feed_error;
-  int feed_rc = 0;
-  while(true) {
-    chunk ck;
-    { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !ready.empty(); }); ck = ready.front(); ready.pop(); }
-    if(ck.last) { if(!ck.error.empty()) feed_error = ck.error; break; }
-    if(!feed_rc && feed_error.empty()) {
-      feed_rc = jfgpu_feed(h, ck.data, ck.n, ck.flags);
-      if(feed_rc) feed_error = jfgpu_last_error(h);
-    }
-    { std::unique_lock<std::mutex> l(mu); freeb.push(ck.data); cv.notify_all(); }
+// ---- stream the inputs through an engine: a reader thread fills pinned buffers, the caller's thread feeds them (host/jf_inputs.hpp) ----
+void stream_files(jfgpu_handle h, const std::vector<const char*>& file_list, const jfb::generator_spec& gen = jfb::generator_spec()) {
+  static_assert((uint32_t)jfb::INPUT_FILE_BEGIN == (uint32_t)JFGPU_FILE_BEGIN && (uint32_t)jfb::INPUT_FILE_END == (uint32_t)JFGPU_FILE_END, "chunk flags are the engine's");
+  jfb::input_buffers mem = { [](size_t n) { return jfgpu_host_alloc(n); }, [](void* p) { jfgpu_host_free(p); } };
+  const std::string err = jfb::stream_inputs(file_list, gen, mem,
+    [&](const char* data, size_t n, uint32_t flags) { return jfgpu_feed(h, data, n, flags); },
+    [&]() { return std::string(jfgpu_last_error(h)); });
+  if(!err.empty()) die(err);
+}
+
+// `inputs`: the byte stream `count` / `bc` would hand to the engine for these arguments (files, then the outputs of the -g
+// commands), on standard output; --marks lists the chunks and their flags on standard error.  Needs no device: a way to look at
+// what a set of generator commands really produces.
+int inputs_main(int argc, char* argv[]) {
+  jfb::generator_spec gen;
+  bool marks = false; size_t chunk_bytes = (size_t)64 << 20;
+  enum { O_MARKS = 1000, O_CHUNK };
+  static struct option longs[] = {
+    {"generator", required_argument, 0, 'g'}, {"Generators", required_argument, 0, 'G'}, {"shell", required_argument, 0, 'S'},
+    {"marks", no_argument, 0, O_MARKS}, {"chunk", required_argument, 0, O_CHUNK}, {0, 0, 0, 0} };
+  optind = 1; int c;
+  while((c = getopt_long(argc, argv, "g:G:S:", longs, 0)) != -1) switch(c) {
+    case 'g': gen.cmds_path = optarg; break;
+    case 'G': gen.concurrent = (uint32_t)parse_u64(optarg, false, "-G"); break;
+    case 'S': gen.shell = optarg; break;
+    case O_MARKS: marks = true; break;
+    case O_CHUNK: chunk_bytes = (size_t)parse_u64(optarg, true, "--chunk"); if(chunk_bytes == 0) usage_error("--chunk must be positive"); break;
+    default: usage_error("Usage: jellyfish-b200 inputs [-g path] [-G n] [-S shell] [--marks] [--chunk bytes] file:path*");
   }
-  reader.join();
-  if(!feed_error.empty()) die(feed_error);
-  for(int i = 0; i < NBUF; ++i) jfgpu_host_free(bufs[i]);
+  std::vector<const char*> files;
+  for(int i = optind; i < argc; ++i) files.push_back(argv[i]);
+  jfb::input_buffers mem = { [](size_t n) { return malloc(n); }, [](void* p) { free(p); } };
+  std::string werr;
+  const std::string err = jfb::stream_inputs(files, gen, mem,
+    [&](const char* data, size_t n, uint32_t flags) -> int {
+      if(marks) std::cerr << "chunk " << n << (flags & JFGPU_FILE_BEGIN ? " begin" : "") << (flags & JFGPU_FILE_END ? " end" : "") << "\n";
+      if(n && fwrite(data, 1, n, stdout) != n) { werr = "Error writing the standard output"; return 1; }
+      return 0;
+    },
+    [&]() { return werr; }, chunk_bytes);
+  fflush(stdout);
+  if(!err.empty()) die(err);
+  return 0;
 }
 
 // load_bloom_filter (sub_commands/count_main.cc:191-206): header checks, then the counter bytes go to the device
@@ -289,13 +271,18 @@ int bc_main(int argc, char* argv[]) {
   header.set_cmdline(argc, argv);
   uint32_t mer_len = 0; uint64_t size = 0; double fpr = 0.001; bool canonical = false, mer_given = false, size_given = false, timing_given = false;
   const char* output = "mer_bloom_filter"; const char* timing = ""; int device = 0;
+  jfb::generator_spec gen;
   enum { O_TIMING = 1000, O_DEVICE };
   static struct option longs[] = {
     {"mer-len", required_argument, 0, 'm'}, {"size", required_argument, 0, 's'}, {"fpr", required_argument, 0, 'f'},
     {"threads", required_argument, 0, 't'}, {"Files", required_argument, 0, 'F'}, {"output", required_argument, 0, 'o'},
-    {"canonical", no_argument, 0, 'C'}, {"timing", required_argument, 0, O_TIMING}, {"device", required_argument, 0, O_DEVICE}, {0, 0, 0, 0} };
+    {"canonical", no_argument, 0, 'C'}, {"timing", required_argument, 0, O_TIMING}, {"device", required_argument, 0, O_DEVICE},
+    {"generator", required_argument, 0, 'g'}, {"Generators", required_argument, 0, 'G'}, {"shell", required_argument, 0, 'S'}, {0, 0, 0, 0} };
   optind = 1; int c;
-  while((c = getopt_long(argc, argv, "m:s:f:t:F:o:C", longs, 0)) != -1) switch(c) {
+  while((c = getopt_long(argc, argv, "m:s:f:t:F:o:Cg:G:S:", longs, 0)) != -1) switch(c) {
+    case 'g': gen.cmds_path = optarg; break;
+    case 'G': gen.concurrent = (uint32_t)parse_u64(optarg, false, "-G"); break;
+    case 'S': gen.shell = optarg; break;
     case 'm': mer_len = (uint32_t)parse_u64(optarg, false, "-m"); mer_given = true; break;
     case 's': size = parse_u64(optarg, true, "-s"); size_given = true; break;
     case 'f': fpr = atof(optarg); break;
@@ -332,7 +319,7 @@ int bc_main(int argc, char* argv[]) {
   header.write(out);
   out.close();
   auto after_init_time = clk::now();
-  stream_files(h, files);
+  stream_files(h, files, gen);
   if(jfgpu_finish(h, nullptr) != JFGPU_OK) die(jfgpu_last_error(h));
   auto after_count_time = clk::now();
   FILE* f = fopen(output, "ab");
@@ -387,9 +374,9 @@ int count_main(int argc, char* argv[]) {
     case 's': a.size = parse_u64(optarg, true, "-s"); a.size_given = true; break;
     case 't': a.threads = (uint32_t)parse_u64(optarg, false, "-t"); break;
     case 'F': a.Files = (uint32_t)parse_u64(optarg, false, "-F"); break;
-    case 'g': a.generator_given = true; break;
-    case 'G': a.Generators = (uint32_t)parse_u64(optarg, false, "-G"); break;
-    case 'S': break;
+    case 'g': a.generator_given = true; a.gen.cmds_path = optarg; break;
+    case 'G': a.Generators = (uint32_t)parse_u64(optarg, false, "-G"); a.gen.concurrent = a.Generators; break;
+    case 'S': a.gen.shell = optarg; break;
     case 'o': a.output = optarg; break;
     case 'c': a.counter_len = (uint32_t)parse_u64(optarg, false, "-c"); break;
     case O_OCL: a.out_counter_len = (uint32_t)parse_u64(optarg, false, "--out-counter-len"); break;
@@ -420,7 +407,6 @@ int count_main(int argc, char* argv[]) {
   if(!a.size_given) usage_error("Missing required switch --size");
   if(a.bc_given && a.bf_size_given) usage_error("Switches [--bf-size] and [--bc] conflict");
   if(a.sam_given) usage_error("SAM/BAM/CRAM not supported (missing htslib).");
-  if(a.generator_given) usage_error("generators (-g) are not supported by jellyfish-b200");
   // count_main.cc:234-256
   if(a.min_qual_char_given) {
     if(a.min_qual_char.size() != 1) usage_error("[-Q, --min-qual-char] must be one character.");
@@ -501,7 +487,7 @@ int count_main(int argc, char* argv[]) {
     if(jfgpu_set_op(h, JFGPU_OP_UPDATE) != JFGPU_OK) die(jfgpu_last_error(h));
   }
   if(a.bc_given) load_bloom_counter(h, a.bc_path, a.mer_len);                 // count_main.cc:311-315
-  stream_files(h, a.files);
+  stream_files(h, a.files, a.gen);           // files, then the outputs of the -g commands (count_main.cc:297-303)
   jfgpu_stats st;
   if(jfgpu_finish(h, &st) != JFGPU_OK) die(jfgpu_last_error(h));
   auto after_count_time = clk::now();
@@ -837,7 +823,7 @@ void merge_sum(const std::vector<std::string>& inputs, const char* output, jfb::
 }  // namespace
 
 int main(int argc, char* argv[]) {
-  if(argc < 2) { std::cerr << "Too few arguments\nUsage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, bc, dump, query, info, histo, stats, merge.\n"; return 1; }
+  if(argc < 2) { std::cerr << "Too few arguments\nUsage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, bc, dump, query, info, histo, stats, merge, inputs.\n"; return 1; }
   std::string cmd = argv[1];
   if(cmd == "count") return count_main(argc - 1, argv + 1);
   if(cmd == "bc") return bc_main(argc - 1, argv + 1);
@@ -847,6 +833,7 @@ int main(int argc, char* argv[]) {
   if(cmd == "histo") return histo_main(argc - 1, argv + 1);
   if(cmd == "stats") return stats_main(argc - 1, argv + 1);
   if(cmd == "merge") return merge_main(argc - 1, argv + 1);
+  if(cmd == "inputs") return inputs_main(argc - 1, argv + 1);
   if(cmd == "--version" || cmd == "-V") { std::cout << jfgpu_version() << std::endl; return 0; }
   if(cmd == "--help" || cmd == "-h" || cmd == "help") { std::cout << "Usage: jellyfish-b200 <cmd> [options] arg...\nWhere <cmd> is one of: count, bc, dump, query, info, histo, stats, merge.\n"; return 0; }
   std::cerr << "Unknown command '" << cmd << "'\n";

@@ -697,3 +697,63 @@ def test_disk_spill_and_merge_matches_reference_golden(name, built, workdir, inp
     lo = int(args[args.index("-L") + 1]) if "-L" in args else 0
     cap = (1 << (8 * h["counter_len"])) - 1
     assert {key: min(v, cap) for key, v in total.items() if v >= lo} == dict(jfutil.records(h, b))
+
+
+def _generator_file(workdir, inputs, tag, names):
+    """A -g file whose commands write the given inputs on their standard output, every second one through gunzip when
+    gzip is here (the reference's own use: tests/multi_file.sh:16-23); blank lines and comments in between."""
+    import shlex
+    import shutil
+    import subprocess
+    lines = ["", "   ", "# generator commands of " + tag]
+    for i, n in enumerate(names):
+        path = inputs[n]
+        if i % 2 == 1 and shutil.which("gzip") and shutil.which("gunzip"):
+            gz = os.path.join(workdir, "%s_%d.gz" % (tag, i))
+            with open(gz, "wb") as f:
+                subprocess.run(["gzip", "-c", path], stdout=f, check=True)
+            lines.append("  gunzip -c %s" % shlex.quote(gz))
+        else:
+            lines.append("cat %s" % shlex.quote(path))
+        lines.append("")
+    cmds = os.path.join(workdir, tag + "_cmds")
+    with open(cmds, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return cmds
+
+
+@pytest.mark.parametrize("name,width", [("multi_files", 2), ("fq_fa_mixed", 3), ("k63_multi", 1)])
+def test_generator_commands_count_like_files(name, width, built, workdir, inputs):
+    """-g / -G / -S (lib/generator_manager.cc, count_main.cc:260-267,297-303): the first input as a file, the others as the
+    outputs of generator commands run `width` at a time -- every output one input file of its own -- against the reference's
+    golden for the same inputs given as files (the database does not depend on how or in which order the inputs arrive)."""
+    args, ins = CASES[name]
+    cmds = _generator_file(workdir, inputs, "gen_" + name, ins[1:])
+    h, b = _count_cli(workdir, inputs, "gen_" + name, args, ins[:1], extra=["-g", cmds, "-G", str(width), "-S", "/bin/sh"])
+    g = GOLDEN[name]
+    assert jfutil.semantic(h) == g["header"]
+    assert len(b) == g["body_len"] and jfutil.md5(b) == g["body_md5"]
+
+
+def test_bloom_counter_from_generator_commands(built, workdir, inputs):
+    """`bc -g` (bc_main.cc:95-103,127-143; tests/bloom_counter.sh:11-15): no file argument at all, the file byte for byte"""
+    bargs, bins, _, _ = BC_CASES["bc_k21C"]
+    g = GOLDEN_BC["bc_k21C"]
+    cmds = _generator_file(workdir, inputs, "gen_bc", bins)
+    bc = os.path.join(workdir, "gpu_gen_bc.bc")
+    jfutil.run([jfutil.OUR_JF, "bc"] + bargs + ["-g", cmds, "-G", "2", "-o", bc])
+    hb, bb = jfutil.split_db(bc)
+    assert {k: hb.get(k) for k in g["bc_header"]} == g["bc_header"]
+    assert len(bb) == g["bc_len"] and jfutil.md5(bb) == g["bc_md5"]
+
+
+def test_failing_generator_command_fails_the_count(built, workdir, inputs):
+    """tests/multi_file.sh:25-33"""
+    import subprocess
+    cmds = os.path.join(workdir, "gen_fail_cmds")
+    with open(cmds, "w") as f:
+        f.write("cat %s\nfalse\n" % inputs["plain.fa"])
+    r = subprocess.run([jfutil.OUR_JF, "count", "-m", "21", "-s", "600k", "-C", "-g", cmds, "-G", "2", "-o", os.path.join(workdir, "gen_fail.jf")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0
+    assert b"Command 'false' exited with error status 1" in r.stderr and b"Some generator commands failed" in r.stderr
