@@ -21,7 +21,9 @@
 #include <sys/types.h>
 #include <sys/wait.h>
 #include <unistd.h>
+#include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -63,13 +65,45 @@ inline bool read_generator_commands(const char* path, std::vector<std::string>* 
   return true;
 }
 
+// The process groups of the running commands: SIGTERM / SIGINT / SIGHUP to this process end them too (the reference's manager
+// process does the same for its children, generator_manager.cc:120-160), then the signal takes its default course.
+namespace detail {
+constexpr int MAX_LIVE_GROUPS = 256;
+inline std::atomic<pid_t>* live_groups() { static std::atomic<pid_t> g[MAX_LIVE_GROUPS]; return g; }
+inline void end_commands_and_reraise(int sig) {
+  std::atomic<pid_t>* g = live_groups();
+  for(int i = 0; i < MAX_LIVE_GROUPS; ++i) { const pid_t p = g[i].load(); if(p > 0) ::kill(-p, SIGTERM); }
+  ::signal(sig, SIG_DFL);
+  ::raise(sig);
+}
+inline void watch_signals_once() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    struct sigaction act;
+    memset(&act, 0, sizeof(act));
+    act.sa_handler = end_commands_and_reraise;
+    const int sigs[] = { SIGTERM, SIGINT, SIGHUP };
+    for(int sg : sigs) {
+      struct sigaction old;
+      if(sigaction(sg, nullptr, &old) == 0 && old.sa_handler == SIG_DFL) sigaction(sg, &act, nullptr);     // (an ignored signal stays ignored)
+    }
+  });
+}
+inline int group_enter(pid_t p) {
+  std::atomic<pid_t>* g = live_groups();
+  for(int i = 0; i < MAX_LIVE_GROUPS; ++i) { pid_t none = 0; if(g[i].compare_exchange_strong(none, p)) return i; }
+  return -1;
+}
+inline void group_leave(int slot) { if(slot >= 0) live_groups()[slot].store(0); }
+}  // namespace detail
+
 // One running generator command: its standard output arrives through read().
 class command_stream {
   static constexpr size_t BLOCK = (size_t)4 << 20;      // bytes per read of the pipe
   static constexpr size_t MAX_QUEUED = 64;              // blocks a command may run ahead of the engine (256 MB)
   std::string cmd_;
   pid_t pid_ = -1;
-  int fd_ = -1;
+  int fd_ = -1, slot_ = -1;
   std::thread pump_;
   std::mutex mu_;
   std::condition_variable cv_;
@@ -103,6 +137,7 @@ class command_stream {
 
  public:
   command_stream(const std::string& cmd, const char* shell, std::string* error) : cmd_(cmd) {
+    detail::watch_signals_once();
     int pfd[2];
     if(::pipe2(pfd, O_CLOEXEC) != 0) { *error = std::string("Failed to create a pipe for command '") + cmd + "': " + strerror(errno); return; }
     ::fcntl(pfd[0], F_SETPIPE_SZ, 1 << 20);            // (best effort)
@@ -121,6 +156,7 @@ class command_stream {
     ::close(pfd[1]);
     if(rc != 0) { pid_ = -1; ::close(pfd[0]); *error = std::string("Failed to run '") + shell + "'. Command '" + cmd + "' not run: " + strerror(rc); return; }
     fd_ = pfd[0];
+    slot_ = detail::group_enter(pid_);
     pump_ = std::thread([this] { pump(); });
   }
   command_stream(const command_stream&) = delete;
@@ -133,16 +169,20 @@ class command_stream {
     }
     if(fd_ >= 0) ::close(fd_);
     if(pid_ > 0) { int st; while(::waitpid(pid_, &st, 0) < 0 && errno == EINTR) {} }
+    detail::group_leave(slot_);
   }
   bool started() const { return pid_ > 0; }
   const std::string& command() const { return cmd_; }
 
-  // up to n bytes of the output; 0 = the command closed its output (or the pipe failed: see finish())
-  size_t read(char* dst, size_t n) {
+  // up to n bytes of the output; 0 = the command closed its output (or the pipe failed: see finish()), or `stop` was raised
+  size_t read(char* dst, size_t n, const std::atomic<bool>* stop = nullptr) {
     size_t got = 0;
     std::unique_lock<std::mutex> l(mu_);
     while(got < n) {
-      cv_.wait(l, [&] { return !blocks_.empty() || eof_; });
+      while(blocks_.empty() && !eof_) {
+        if(stop && stop->load()) return got;
+        cv_.wait_for(l, std::chrono::milliseconds(50));
+      }
       if(blocks_.empty()) break;
       std::vector<char>& b = blocks_.front();
       const size_t take = std::min(n - got, b.size() - head_off_);
@@ -164,6 +204,7 @@ class command_stream {
       pid_t r;
       while((r = ::waitpid(pid_, &st, 0)) < 0 && errno == EINTR) {}
       pid_ = -1;
+      detail::group_leave(slot_); slot_ = -1;
       if(r < 0) { if(msg.empty()) msg = std::string("Command '") + cmd_ + "' could not be waited for"; }
       else if(WIFEXITED(st) && WEXITSTATUS(st) != 0) msg = std::string("Command '") + cmd_ + "' exited with error status " + std::to_string(WEXITSTATUS(st));
       else if(WIFSIGNALED(st)) msg = std::string("Command '") + cmd_ + "' killed by signal " + std::to_string(WTERMSIG(st));
@@ -198,6 +239,7 @@ inline std::string stream_inputs(const std::vector<const char*>& files, const ge
   std::mutex mu; std::condition_variable cv;
   std::queue<chunk> ready; std::queue<char*> freeb;
   for(int i = 0; i < NBUF; ++i) freeb.push(bufs[i]);
+  std::atomic<bool> stop(false);                         // the feeding side has failed: read no further, end the commands
   std::thread reader([&] {
     auto get_buf = [&]() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !freeb.empty(); }); char* b = freeb.front(); freeb.pop(); return b; };
     auto put = [&](chunk c) { std::unique_lock<std::mutex> l(mu); ready.push(c); cv.notify_all(); };
@@ -208,6 +250,7 @@ inline std::string stream_inputs(const std::vector<const char*>& files, const ge
       auto fill = [&](char* b) -> size_t {
         size_t n = 0;
         while(n < BUF) {
+          if(stop.load()) { io_error = "stopped"; eof = true; break; }
           const size_t r = more(b + n, BUF - n, &io_error);
           if(r == 0) { eof = true; break; }                 // (never a silent truncation: a failed read sets io_error)
           n += r;
@@ -231,7 +274,7 @@ inline std::string stream_inputs(const std::vector<const char*>& files, const ge
         cur = nxt; have = nn;
       }
     };
-    for(size_t fi = 0; fi < files.size(); ++fi) {
+    for(size_t fi = 0; fi < files.size() && !stop.load(); ++fi) {
       const int fd = ::open(files[fi], O_RDONLY);
       if(fd < 0) { put(chunk{nullptr, 0, 0, true, std::string("Can't open file '") + files[fi] + "'"}); return; }
       const std::string err = one_input([&](char* dst, size_t n, std::string* e) -> size_t {
@@ -250,7 +293,7 @@ inline std::string stream_inputs(const std::vector<const char*>& files, const ge
     size_t next_cmd = 0;
     const size_t width = std::max<uint32_t>(gen.concurrent, 1);
     std::string failed;
-    while(next_cmd < cmds.size() || !running.empty()) {
+    while(!stop.load() && (next_cmd < cmds.size() || !running.empty())) {
       while(next_cmd < cmds.size() && running.size() < width) {
         std::string err;
         std::unique_ptr<command_stream> cs(new command_stream(cmds[next_cmd], shell, &err));
@@ -260,12 +303,13 @@ inline std::string stream_inputs(const std::vector<const char*>& files, const ge
       }
       if(!failed.empty() || running.empty()) break;
       command_stream& cs = *running.front();
-      std::string err = one_input([&](char* dst, size_t n, std::string*) -> size_t { return cs.read(dst, n); });
+      std::string err = one_input([&](char* dst, size_t n, std::string*) -> size_t { return cs.read(dst, n, &stop); });
       if(err.empty()) err = cs.finish();
       running.pop_front();
       if(!err.empty()) { failed = err; break; }
     }
     running.clear();                                        // (terminates what is still running after a failure)
+    if(stop.load()) { put(chunk{nullptr, 0, 0, true, ""}); return; }
     if(!failed.empty()) { put(chunk{nullptr, 0, 0, true, failed + "\nSome generator commands failed"}); return; }
     put(chunk{nullptr, 0, 0, true, ""});
   });
@@ -277,7 +321,7 @@ inline std::string stream_inputs(const std::vector<const char*>& files, const ge
     if(ck.last) { if(!ck.error.empty() && error.empty()) error = ck.error; break; }
     if(!feed_rc && error.empty()) {
       feed_rc = feed(ck.data, ck.n, ck.flags);
-      if(feed_rc) error = feed_error();
+      if(feed_rc) { error = feed_error(); stop.store(true); }
     }
     { std::unique_lock<std::mutex> l(mu); freeb.push(ck.data); cv.notify_all(); }
   }

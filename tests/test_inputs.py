@@ -107,3 +107,48 @@ def test_shell_switch_selects_the_shell(seqdir):
     (seqdir / "cmds").write_text("[[ -n $BASH_VERSION ]] && printf '>bash\\nAC\\n'\n")
     r = _inputs(["-g", "cmds", "-S", "/bin/bash"], seqdir)
     assert r.returncode == 0 and r.stdout == b">bash\nAC\n", r.stderr
+
+
+def test_failed_feed_stops_an_endless_generator(seqdir):
+    """when the consumer fails (here: the standard output cannot be written; in `count`: the engine reports an error) the reader
+    stops and the commands are ended -- an endless generator must not keep the run alive"""
+    (seqdir / "cmds").write_text("yes ACGT\n")
+    with open("/dev/full", "wb") as sink:
+        r = subprocess.run([jfutil.OUR_JF, "inputs", "-g", "cmds"], cwd=seqdir, stdout=sink, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode != 0 and b"Error writing the standard output" in r.stderr
+
+
+def _running(cmdline):
+    n = 0
+    for pid in os.listdir("/proc"):
+        if pid.isdigit():
+            try:
+                with open("/proc/%s/cmdline" % pid, "rb") as f:
+                    n += f.read().replace(b"\0", b" ").strip() == cmdline
+            except OSError:
+                pass
+    return n
+
+
+def test_sigterm_to_the_driver_ends_the_commands(seqdir):
+    """generator_manager.cc:120-160: a killed run takes its generator commands with it"""
+    import signal
+    import time
+    secs = "9%05d.25" % (os.getpid() % 100000)
+    (seqdir / "cmds").write_text("cat a.fa\nexec sleep %s\n" % secs)
+    p = subprocess.Popen([jfutil.OUR_JF, "inputs", "-g", "cmds", "-G", "2"], cwd=seqdir, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        deadline = time.time() + 20
+        while not _running(b"sleep " + secs.encode()) and time.time() < deadline:
+            time.sleep(0.05)
+        assert _running(b"sleep " + secs.encode()) == 1
+        p.send_signal(signal.SIGTERM)
+        p.wait(timeout=20)
+        assert p.returncode == -signal.SIGTERM
+        deadline = time.time() + 10
+        while _running(b"sleep " + secs.encode()) and time.time() < deadline:
+            time.sleep(0.05)
+        assert _running(b"sleep " + secs.encode()) == 0
+    finally:
+        if p.poll() is None:
+            p.kill()
