@@ -129,11 +129,11 @@ struct db_reader {
     key_bytes = (header.key_len() + 7) / 8;
     counter_len = header.counter_len();
     rec = key_bytes + counter_len;
-    if(header.format() == "binary/sorted") {
+    if(header.format() == "binary/sorted" || header.format() == "text/sorted") {
       matrix = header.matrix(1);
       size_mask = header.size() - 1;
-      n_records = rec ? (file_size - body_off) / rec : 0;
     }
+    if(header.format() == "binary/sorted") n_records = rec ? (file_size - body_off) / rec : 0;
   }
   void key_at(size_t i, uint64_t* w) const {
     w[0] = w[1] = 0;
@@ -341,7 +341,8 @@ int bc_main(int argc, char* argv[]) {
 }
 
 // k-way SUM merge of binary/sorted files into `output` under header `oh` (defined with merge_main below)
-void merge_sum(const std::vector<std::string>& inputs, const char* output, jfb::file_header& oh, uint64_t lower, uint64_t upper);
+enum merge_op { MERGE_SUM, MERGE_MIN, MERGE_MAX, MERGE_JACCARD };      // merge_files.hpp: SUM, MIN, MAX, JACCARD
+void merge_dbs(const std::vector<std::string>& inputs, const char* output, jfb::file_header& oh, uint64_t lower, uint64_t upper, merge_op op = MERGE_SUM);
 
 int count_main(int argc, char* argv[]) {
   using clk = std::chrono::system_clock;
@@ -502,7 +503,7 @@ int count_main(int argc, char* argv[]) {
       write_table(last.c_str(), false);
       if(!a.no_merge) {
         const uint64_t lo = a.lower_given ? a.lower : 0, hi = a.upper_given ? a.upper : std::numeric_limits<uint64_t>::max();
-        merge_sum(spill.files, a.output, header, lo, hi);
+        merge_dbs(spill.files, a.output, header, lo, hi);
         if(!a.no_unlink) for(const std::string& f : spill.files) unlink(f.c_str());
       }
     }
@@ -733,46 +734,47 @@ int stats_main(int argc, char* argv[]) {
 int merge_main(int argc, char* argv[]) {
   const char* output = "mer_counts_merged.jf";
   uint64_t lower = 0, upper = std::numeric_limits<uint64_t>::max();
+  bool lower_given = false, min_flag = false, max_flag = false, jaccard_flag = false;
   static struct option longs[] = { {"output", required_argument, 0, 'o'}, {"lower-count", required_argument, 0, 'L'},
-    {"upper-count", required_argument, 0, 'U'}, {0, 0, 0, 0} };
+    {"upper-count", required_argument, 0, 'U'}, {"min", no_argument, 0, 'm'}, {"max", no_argument, 0, 'M'}, {"jaccard", no_argument, 0, 'j'},
+    {0, 0, 0, 0} };
   optind = 1; int c;
-  while((c = getopt_long(argc, argv, "o:L:U:", longs, 0)) != -1) switch(c) {
+  while((c = getopt_long(argc, argv, "o:L:U:mMj", longs, 0)) != -1) switch(c) {
     case 'o': output = optarg; break;
-    case 'L': lower = parse_u64(optarg, false, "-L"); break; case 'U': upper = parse_u64(optarg, false, "-U"); break;
-    default: usage_error("Usage: jellyfish-b200 merge [options] input:string+ (only the SUM operation is implemented)");
+    case 'L': lower = parse_u64(optarg, false, "-L"); lower_given = true; break; case 'U': upper = parse_u64(optarg, false, "-U"); break;
+    case 'm': min_flag = true; break; case 'M': max_flag = true; break; case 'j': jaccard_flag = true; break;
+    default: usage_error("Usage: jellyfish-b200 merge [options] input:string+");
   }
+  if(min_flag && max_flag) usage_error("Switches [-M, --max] and [-m, --min] conflict");
+  // merge_main.cc:31-37: with --min a k-mer absent from one input has count 0 and is left out unless -L says otherwise
+  if(!lower_given && min_flag) lower = 1;
+  merge_op op = MERGE_SUM;
+  if(min_flag) op = MERGE_MIN;
+  if(max_flag) op = MERGE_MAX;
+  if(jaccard_flag) op = MERGE_JACCARD;
   const int n = argc - optind;
   if(n < 2) usage_error("Requires at least 2 arguments.");
-  std::vector<db_reader> dbs(n);
-  for(int i = 0; i < n; ++i) {
-    dbs[i].open(argv[optind + i]);
-    if(dbs[i].header.format() != "binary/sorted") die(std::string("Can only merge binary/sorted files: '") + argv[optind + i] + "'");
-    if(i) {
-      const jfb::file_header &a = dbs[0].header, &b = dbs[i].header;
-      if(a.key_len() != b.key_len()) die("Can't merge hashes of different key lengths");
-      if(a.size() != b.size()) die("Can't merge hash with different size");
-      if(a.matrix(1) != b.matrix(1)) die("Can't merge hash with different hash function");
-      if(a.max_reprobe_offset() != b.max_reprobe_offset()) die("Can't merge hashes with different reprobing strategies");
-    }
-  }
   jfb::file_header oh;
   oh.fill_standard();
   oh.set_cmdline(argc, argv);
   std::vector<std::string> inputs;
   for(int i = 0; i < n; ++i) inputs.push_back(argv[optind + i]);
-  dbs.clear();
-  merge_sum(inputs, output, oh, lower, upper);
+  merge_dbs(inputs, output, oh, lower, upper, op);          // (checks that the inputs go together)
   return 0;
 }
 
-void merge_sum(const std::vector<std::string>& inputs, const char* output, jfb::file_header& oh, uint64_t lower, uint64_t upper) {
+// k-way merge in (position, key) order (merge_files.cc:44-104): per key the sum, the minimum (0 when an input lacks the key) or the
+// maximum of the counts; JACCARD writes the two similarities instead of a database
+void merge_dbs(const std::vector<std::string>& inputs, const char* output, jfb::file_header& oh, uint64_t lower, uint64_t upper, merge_op op) {
   const int n = (int)inputs.size();
   std::vector<db_reader> dbs(n);
   for(int i = 0; i < n; ++i) {
     dbs[i].open(inputs[i].c_str());
-    if(dbs[i].header.format() != "binary/sorted") die(std::string("Can only merge binary/sorted files: '") + inputs[i] + "'");
+    const std::string& fmt = dbs[i].header.format();
+    if(fmt != "binary/sorted" && fmt != "text/sorted") die(std::string("Unknown format '") + fmt + "'");
     if(i) {
       const jfb::file_header &a = dbs[0].header, &b = dbs[i].header;
+      if(a.format() != b.format()) die(std::string("Can't merge files with different formats (") + a.format() + ", " + b.format() + ")");
       if(a.key_len() != b.key_len()) die("Can't merge hashes of different key lengths");
       if(a.size() != b.size()) die("Can't merge hash with different size");
       if(a.matrix(1) != b.matrix(1)) die("Can't merge hash with different hash function");
@@ -780,43 +782,81 @@ void merge_sum(const std::vector<std::string>& inputs, const char* output, jfb::
     }
   }
   const jfb::file_header& h0 = dbs[0].header;
+  const bool text = h0.format() == "text/sorted";
   // exactly the keys merge_files() sets (merge_files.cc:125-138,160-165) on top of what the caller's header holds
   oh.size(h0.size()); oh.key_len(h0.key_len()); oh.matrix(h0.matrix(1));
   oh.max_reprobe(h0.max_reprobe()); { std::vector<uint64_t> r = h0.reprobes(); oh.set_reprobes(r.data()); }
   unsigned ocl_min = h0.counter_len();
   for(int i = 1; i < n; ++i) ocl_min = std::min<unsigned>(ocl_min, dbs[i].header.counter_len());
-  oh.format("binary/sorted"); oh.counter_len(ocl_min);
+  oh.format(h0.format());
+  if(!text) oh.counter_len(ocl_min);
   std::ofstream out(output, std::ios::binary);
   if(!out.good()) die(std::string("Can't open out file '") + output + "'");
-  oh.write(out);
-  struct item { uint64_t pos; uint64_t key[2]; int src; };
+  if(op != MERGE_JACCARD) oh.write(out);
+  struct item { uint64_t pos; uint64_t key[2]; uint64_t val; int src; };
   auto greater = [](const item& a, const item& b) {
     if(a.pos != b.pos) return a.pos > b.pos;
     if(a.key[1] != b.key[1]) return a.key[1] > b.key[1];
     return a.key[0] > b.key[0];
   };
   std::priority_queue<item, std::vector<item>, decltype(greater)> heap(greater);
+  // cursors: record index in a binary body; byte offset of the next "MER count" line in a text body (text_dumper.hpp:50-80)
   std::vector<size_t> cur(n, 0);
+  const unsigned k = dbs[0].k;
   auto push = [&](int i) {
-    if(cur[i] < dbs[i].n_records) { item it; dbs[i].key_at(cur[i], it.key); it.pos = dbs[i].pos_of(it.key); it.src = i; heap.push(it); }
+    item it; it.src = i;
+    if(!text) {
+      if(cur[i] >= dbs[i].n_records) return;
+      dbs[i].key_at(cur[i], it.key); it.val = dbs[i].val_at(cur[i]); ++cur[i];
+    } else {
+      const char* p = (const char*)dbs[i].base + dbs[i].body_off + cur[i];
+      const char* end = (const char*)dbs[i].base + dbs[i].file_size;
+      while(p < end && (*p == '\n' || *p == ' ' || *p == '\t' || *p == '\r')) ++p;
+      if(p >= end) return;
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+      const char* stop = nl ? nl : end;
+      std::string mer(p, std::min<size_t>(k, (size_t)(stop - p)));
+      char* num_end = nullptr;
+      const std::string num(p + mer.size(), (size_t)(stop - p) - mer.size());        // (a copy: the mapping may end right behind the line)
+      it.val = strtoull(num.c_str(), &num_end, 10);
+      if(!string_to_mer(mer.c_str(), k, it.key) || num_end == num.c_str())
+        die(std::string("Invalid record in text file '") + inputs[i] + "'");
+      cur[i] = (size_t)((nl ? nl + 1 : end) - ((const char*)dbs[i].base + dbs[i].body_off));
+    }
+    it.pos = dbs[i].pos_of(it.key);
+    heap.push(it);
   };
   for(int i = 0; i < n; ++i) push(i);
   const unsigned key_bytes = dbs[0].key_bytes, ocl = ocl_min;
   const uint64_t maxv = ocl >= 8 ? ~(uint64_t)0 : (((uint64_t)1 << (8 * ocl)) - 1);
+  uint64_t inter = 0, winter = 0, uni = 0, wuni = 0;
+  std::string line;
   while(!heap.empty()) {
     item top = heap.top();
-    uint64_t sum = 0;
+    uint64_t sum = 0, minc = std::numeric_limits<uint64_t>::max(), maxc = 0;
+    int present = 0;
     while(!heap.empty() && heap.top().key[0] == top.key[0] && heap.top().key[1] == top.key[1]) {
-      int i = heap.top().src; heap.pop();
-      sum += dbs[i].val_at(cur[i]); ++cur[i];
+      const int i = heap.top().src;
+      const uint64_t v = heap.top().val;
+      heap.pop();
+      sum += v; minc = std::min(minc, v); maxc = std::max(maxc, v); ++present;
       push(i);
     }
-    if(sum >= lower && sum <= upper) {
-      out.write((const char*)top.key, key_bytes);
-      uint64_t v = std::min(sum, maxv);
-      out.write((const char*)&v, ocl);
+    if(present < n) minc = 0;
+    if(op == MERGE_JACCARD) { inter += minc > 0; winter += minc; uni += 1; wuni += maxc; continue; }
+    const uint64_t val = op == MERGE_MIN ? minc : op == MERGE_MAX ? maxc : sum;
+    if(val >= lower && val <= upper) {
+      if(text) {
+        line = mer_to_string(top.key, k); line += ' '; line += std::to_string((unsigned long long)val); line += '\n';
+        out.write(line.data(), line.size());
+      } else {
+        out.write((const char*)top.key, key_bytes);
+        uint64_t v = std::min(val, maxv);
+        out.write((const char*)&v, ocl);
+      }
     }
   }
+  if(op == MERGE_JACCARD) out << "Jaccard  " << (double)inter / (double)uni << '\n' << "wJaccard " << (double)winter / (double)wuni << '\n';
   out.close();
 }
 

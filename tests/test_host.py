@@ -165,3 +165,38 @@ def test_merge_matches_reference(built, workdir, inputs):
     h1, b1 = jfutil.split_db(m1)
     h2, b2 = jfutil.split_db(m2)
     assert b1 == b2 and jfutil.semantic(h1) == jfutil.semantic(h2)
+    # the other operations (merge_main.cc:31-37, merge_files.cc:63-95): minimum (a k-mer missing from an input counts 0 and
+    # is dropped unless -L 0 keeps it), maximum, count filters, three inputs, and the Jaccard similarities
+    c = os.path.join(workdir, "m_c.jf")
+    jfutil.run([jfutil.REF_JF, "count", "-m", "17", "-s", "1M", "-C", "-o", c, inputs["multi.fa"], inputs["dangling.fa"]])
+    for tag, switches, files in [("min", ["--min"], [a, c]), ("min0", ["-m", "-L", "0"], [a, b]), ("max", ["--max"], [a, b, c]),
+                                 ("maxLU", ["-M", "-L", "2", "-U", "3"], [a, c]), ("sum3", ["-L", "2"], [a, b, c]),
+                                 ("min3", ["-m"], [c, a, c])]:
+        r1, r2 = os.path.join(workdir, "m_ref_%s.jf" % tag), os.path.join(workdir, "m_our_%s.jf" % tag)
+        jfutil.run([jfutil.REF_JF, "merge"] + switches + ["-o", r1] + files)
+        jfutil.run([jfutil.OUR_JF, "merge"] + switches + ["-o", r2] + files)
+        h1, b1 = jfutil.split_db(r1)
+        h2, b2 = jfutil.split_db(r2)
+        assert b1 == b2 and jfutil.semantic(h1) == jfutil.semantic(h2), tag
+        assert len(b1) > 0 or tag == "never"
+    for files in ([a, c], [a, b], [a, b, c]):
+        j1, j2 = os.path.join(workdir, "m_ref.jaccard"), os.path.join(workdir, "m_our.jaccard")
+        jfutil.run([jfutil.REF_JF, "merge", "--jaccard", "-o", j1] + files)
+        jfutil.run([jfutil.OUR_JF, "merge", "-j", "-o", j2] + files)
+        assert open(j1, "rb").read() == open(j2, "rb").read()
+        assert open(j2).read().startswith("Jaccard  ")
+    r = subprocess.run([jfutil.OUR_JF, "merge", "-m", "-M", "-o", m2, a, b], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"conflict" in r.stderr
+    # text/sorted databases merge as text (merge_files.cc:168-172, text_dumper.hpp:50-80); formats must agree
+    ta, tb = os.path.join(workdir, "m_ta.jf"), os.path.join(workdir, "m_tb.jf")
+    jfutil.run([jfutil.REF_JF, "count", "-m", "17", "-s", "1M", "-C", "--text", "-o", ta, inputs["multi.fa"]])
+    jfutil.run([jfutil.REF_JF, "count", "-m", "17", "-s", "1M", "-C", "--text", "-o", tb, inputs["multi2.fa"], inputs["dangling.fa"]])
+    for tag, switches in [("tsum", []), ("tmin", ["-m"]), ("tmaxL", ["-M", "-L", "2"])]:
+        r1, r2 = os.path.join(workdir, "m_ref_%s.jf" % tag), os.path.join(workdir, "m_our_%s.jf" % tag)
+        jfutil.run([jfutil.REF_JF, "merge"] + switches + ["-o", r1, ta, tb])
+        jfutil.run([jfutil.OUR_JF, "merge"] + switches + ["-o", r2, ta, tb])
+        h1, b1 = jfutil.split_db(r1)
+        h2, b2 = jfutil.split_db(r2)
+        assert b1 == b2 and len(b1) > 0 and jfutil.semantic(h1) == jfutil.semantic(h2), tag
+    r = subprocess.run([jfutil.OUR_JF, "merge", "-o", m2, a, ta], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"different formats (binary/sorted, text/sorted)" in r.stderr
