@@ -97,7 +97,8 @@ with tempfile.TemporaryDirectory() as d:
             report(it, "query -s", a)
         # merge (same -m/-s => same matrix)
         ma, mb = os.path.join(d, "ma.jf"), os.path.join(d, "mb.jf")
-        extra = (["-L", str(rng.choice([1, 2, 3]))] if rng.random() < 0.3 else []) + (["-U", str(rng.choice([2, 100]))] if rng.random() < 0.3 else [])
+        extra = (["-L", str(rng.choice([0, 1, 2, 3]))] if rng.random() < 0.3 else []) + (["-U", str(rng.choice([2, 100]))] if rng.random() < 0.3 else [])
+        extra += rng.choice([[], [], ["-m"], ["--max"]])
         x = subprocess.run([jfutil.REF_JF, "merge", "-o", ma] + extra + dbs, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         y = subprocess.run([jfutil.OUR_JF, "merge", "-o", mb] + extra + dbs, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         if x.returncode != y.returncode:
@@ -107,6 +108,28 @@ with tempfile.TemporaryDirectory() as d:
             h2, b2 = jfutil.split_db(mb)
             if jfutil.semantic(h1) != jfutil.semantic(h2) or b1 != b2:
                 report(it, "merge output", extra + dbs)
+        # jaccard (two text lines instead of a database), three inputs
+        ja, jb = os.path.join(d, "ja.txt"), os.path.join(d, "jb.txt")
+        three = dbs + [dbs[0]] if rng.random() < 0.5 else dbs
+        x = subprocess.run([jfutil.REF_JF, "merge", "-j", "-o", ja] + three, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        y = subprocess.run([jfutil.OUR_JF, "merge", "-j", "-o", jb] + three, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if x.returncode != y.returncode or (x.returncode == 0 and open(ja, "rb").read() != open(jb, "rb").read()):
+            report(it, "merge --jaccard", three)
+        # text/sorted databases of the same inputs, merged as text
+        tdbs = []
+        for j in range(2):
+            t = os.path.join(d, "t%d_%d.jf" % (it, j))
+            subprocess.run([jfutil.REF_JF, "count", "-t", "2"] + [c for c in cargs if c not in ("--out-counter-len",)][:4 + ("-C" in cargs)] + ["--text", "-o", t, fas[j]], check=True)
+            tdbs.append(t)
+        x = subprocess.run([jfutil.REF_JF, "merge", "-o", ma] + extra + tdbs, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        y = subprocess.run([jfutil.OUR_JF, "merge", "-o", mb] + extra + tdbs, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if x.returncode != y.returncode:
+            report(it, "text merge exit %d/%d %s | %s" % (x.returncode, y.returncode, x.stderr[-100:], y.stderr[-100:]), extra + tdbs)
+        elif x.returncode == 0:
+            h1, b1 = jfutil.split_db(ma)
+            h2, b2 = jfutil.split_db(mb)
+            if jfutil.semantic(h1) != jfutil.semantic(h2) or b1 != b2:
+                report(it, "text merge output", extra + tdbs)
         if bad:
             keep = "/tmp/fuzz_readers_fail"
             os.makedirs(keep, exist_ok=True)
