@@ -200,3 +200,13 @@ def test_merge_matches_reference(built, workdir, inputs):
         assert b1 == b2 and len(b1) > 0 and jfutil.semantic(h1) == jfutil.semantic(h2), tag
     r = subprocess.run([jfutil.OUR_JF, "merge", "-o", m2, a, ta], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"different formats (binary/sorted, text/sorted)" in r.stderr
+    # the last step of --disk (count_main.cc:356-371): many intermediate files of one run, here written by the reference itself
+    part = os.path.join(workdir, "m_part")
+    jfutil.run([jfutil.REF_JF, "count", "-m", "21", "-s", "40k", "-C", "--disk", "--no-merge", "-t", "2", "-o", part, inputs["plain.fa"]])
+    parts = [part + str(i) for i in range(64) if os.path.exists(part + str(i))]
+    assert len(parts) >= 3
+    jfutil.run([jfutil.REF_JF, "merge", "-o", m1] + parts)
+    jfutil.run([jfutil.OUR_JF, "merge", "-o", m2] + parts)
+    h1, b1 = jfutil.split_db(m1)
+    h2, b2 = jfutil.split_db(m2)
+    assert b1 == b2 and len(b1) > 0 and jfutil.semantic(h1) == jfutil.semantic(h2)
